@@ -1,0 +1,372 @@
+// api.cu -- the C ABI of libaicp_b200.so (include/aicp_b200.h).  Thin: argument checks, host<->device staging on the
+// handle's stream, and calls into index.cu / normals.cu / icp.cu / overlap.cu.  No compute happens on the host.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "handle.cuh"
+
+namespace aicp {
+
+static std::string g_create_error;
+static std::mutex g_mutex;
+
+int fail(Handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->last_error = buf;
+  else { std::lock_guard<std::mutex> lk(g_mutex); g_create_error = buf; }
+  return code;
+}
+
+int fail_cuda(Handle* h, cudaError_t e, const char* expr, int line) {
+  cudaGetLastError();   // clear the sticky flag where possible
+  return fail(h, AICP_B200_ERR_CUDA, "CUDA error %s (%s) at line %d: %s", cudaGetErrorName(e), cudaGetErrorString(e), line, expr);
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// make `n` points available on the device: device pointers are used in place, host pointers are staged into `buf`
+int upload_points(Handle* h, DevBuf<float4>& buf, const float* xyzw, int64_t n, const float4** out_dev) {
+  if (is_device_ptr(xyzw)) { *out_dev = reinterpret_cast<const float4*>(xyzw); return AICP_B200_OK; }
+  CUDA_TRY(buf.reserve((size_t)n));
+  CUDA_TRY(cudaMemcpyAsync(buf.p, xyzw, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  *out_dev = buf.p;
+  return AICP_B200_OK;
+}
+
+// copy `bytes` from a device buffer to a host-or-device destination
+static int download(Handle* h, void* dst, const void* src_dev, size_t bytes) {
+  CUDA_TRY(cudaMemcpyAsync(dst, src_dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return AICP_B200_OK;
+}
+
+static int stage_owned(Handle* h, DevBuf<float4>& buf, const float* xyzw, int64_t n) {
+  // registration keeps its own copy of both clouds (the reference copies into its DP members too,
+  // pointmatcher_registration.cpp:16-20), so device inputs are copied device-to-device
+  CUDA_TRY(buf.reserve((size_t)n));
+  CUDA_TRY(cudaMemcpyAsync(buf.p, xyzw, sizeof(float4) * (size_t)n,
+                           is_device_ptr(xyzw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  return AICP_B200_OK;
+}
+
+static int load_config(Handle* h) {
+  if (!h->cfg_from_file) return AICP_B200_OK;
+  std::string err;
+  aicp_b200_icp_config cfg;
+  int rc = parse_icp_yaml(h->cfg_path.c_str(), &cfg, &err);
+  if (rc) return fail(h, rc, "%s", err.c_str());
+  h->cfg = cfg;
+  return AICP_B200_OK;
+}
+
+static int bind_device(Handle* h) {
+  CUDA_TRY(cudaSetDevice(h->device));
+  return AICP_B200_OK;
+}
+
+}  // namespace aicp
+
+using namespace aicp;
+
+#define H_CHECK(h) do { if (!(h)) return AICP_B200_ERR_BAD_ARG; int rc__ = bind_device(h); if (rc__) return rc__; } while (0)
+
+extern "C" {
+
+const char* aicp_b200_version(void) { return "aicp_b200 0.1 (sm_100a)"; }
+
+int aicp_b200_create(const char* icp_yaml_path, int device, aicp_b200_handle** out) {
+  if (!out) return AICP_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  Handle* h = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(nullptr, AICP_B200_ERR_CUDA, "no CUDA device available (%s); libaicp_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= count) return fail(nullptr, AICP_B200_ERR_BAD_ARG, "device %d out of range (%d devices)", device, count);
+  Handle* nh = new Handle();
+  nh->device = device;
+  default_icp_config(&nh->cfg);
+  if (icp_yaml_path && *icp_yaml_path) { nh->cfg_path = icp_yaml_path; nh->cfg_from_file = true; }
+  h = nh;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&nh->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete nh;
+    return fail(nullptr, AICP_B200_ERR_CUDA, "cannot initialise CUDA device %d", device);
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&nh->ev[i]);
+  (void)h;
+  *out = reinterpret_cast<aicp_b200_handle*>(nh);
+  return AICP_B200_OK;
+}
+
+int aicp_b200_comm_destroy(aicp_b200_handle* hh);
+
+int aicp_b200_destroy(aicp_b200_handle* hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return AICP_B200_OK;
+  cudaSetDevice(h->device);
+  if (h->comm) aicp_b200_comm_destroy(hh);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_node.release(); h->normals.release();
+  h->read_in.release(); h->read0.release(); h->read_out.release(); h->read_init.release();
+  h->match_pos.release(); h->d2.release(); h->hist.release(); h->trace_idx.release();
+  h->tmp_ix.release(); h->tmp_a.release(); h->tmp_b.release(); h->tmp_i.release(); h->tmp_f.release();
+  h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release();
+  if (h->st) cudaFree(h->st);
+  if (h->st_host) cudaFreeHost(h->st_host);
+  for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return AICP_B200_OK;
+}
+
+const char* aicp_b200_last_error(const aicp_b200_handle* hh) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  if (h) return h->last_error.c_str();
+  std::lock_guard<std::mutex> lk(g_mutex);
+  return g_create_error.c_str();
+}
+
+int aicp_b200_set_config(aicp_b200_handle* hh, const char* icp_yaml_path) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return AICP_B200_ERR_BAD_ARG;
+  if (icp_yaml_path && *icp_yaml_path) { h->cfg_path = icp_yaml_path; h->cfg_from_file = true; }
+  else { h->cfg_path.clear(); h->cfg_from_file = false; default_icp_config(&h->cfg); }
+  return AICP_B200_OK;
+}
+
+int aicp_b200_set_config_struct(aicp_b200_handle* hh, const aicp_b200_icp_config* cfg) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !cfg) return AICP_B200_ERR_BAD_ARG;
+  h->cfg = *cfg;
+  h->cfg_path.clear();
+  h->cfg_from_file = false;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_get_config(aicp_b200_handle* hh, aicp_b200_icp_config* cfg) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !cfg) return AICP_B200_ERR_BAD_ARG;
+  int rc = load_config(h);
+  if (rc) return rc;
+  *cfg = h->cfg;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_parse_icp_yaml(const char* icp_yaml_path, aicp_b200_icp_config* cfg, char* err, int err_len) {
+  if (!cfg) return AICP_B200_ERR_BAD_ARG;
+  std::string e;
+  int rc = parse_icp_yaml(icp_yaml_path, cfg, &e);
+  if (err && err_len > 0) { strncpy(err, e.c_str(), (size_t)err_len - 1); err[err_len - 1] = 0; }
+  return rc;
+}
+
+int aicp_b200_register(aicp_b200_handle* hh, const float* ref_xyzw, int64_t n_ref, const float* read_xyzw, int64_t n_read,
+                       const float* init_T, float* out_T, aicp_b200_stats* stats) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!ref_xyzw || !read_xyzw || !out_T || n_ref < 1 || n_read < 1 || n_ref > (1ll << 30) || n_read > (1ll << 30))
+    return fail(h, AICP_B200_ERR_BAD_ARG, "registerClouds: null cloud or empty cloud (n_ref %lld, n_read %lld)", (long long)n_ref, (long long)n_read);
+  int rc = load_config(h);     // the reference re-reads the YAML on every call (pointmatcher_registration.cpp:103)
+  if (rc) return rc;
+  if ((rc = stage_owned(h, h->ref_in, ref_xyzw, n_ref))) return rc;
+  if ((rc = stage_owned(h, h->read_in, read_xyzw, n_read))) return rc;
+  h->n_ref = n_ref; h->n_read = n_read;
+  float init_host[16];
+  const float* init = nullptr;
+  if (init_T) {
+    if (is_device_ptr(init_T)) { CUDA_TRY(cudaMemcpy(init_host, init_T, sizeof(init_host), cudaMemcpyDeviceToHost)); init = init_host; }
+    else init = init_T;
+  }
+  return run_registration(h, init, true, stats, out_T);
+}
+
+int aicp_b200_set_reference(aicp_b200_handle* hh, const float* ref_xyzw, int64_t n_ref) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!ref_xyzw || n_ref < 1 || n_ref > (1ll << 30)) return fail(h, AICP_B200_ERR_BAD_ARG, "set_reference: null or empty cloud");
+  int rc = load_config(h);
+  if (rc) return rc;
+  if ((rc = stage_owned(h, h->ref_in, ref_xyzw, n_ref))) return rc;
+  h->n_ref = n_ref;
+  h->ref_ready = false;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_register_to_reference(aicp_b200_handle* hh, const float* read_xyzw, int64_t n_read, const float* init_T,
+                                    float* out_T, aicp_b200_stats* stats) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (h->n_ref < 1) return fail(h, AICP_B200_ERR_BAD_ARG, "register_to_reference: call aicp_b200_set_reference first");
+  if (!read_xyzw || !out_T || n_read < 1 || n_read > (1ll << 30)) return fail(h, AICP_B200_ERR_BAD_ARG, "register_to_reference: null or empty reading");
+  int rc = load_config(h);
+  if (rc) return rc;
+  if ((rc = stage_owned(h, h->read_in, read_xyzw, n_read))) return rc;
+  h->n_read = n_read;
+  bool rebuild = !h->ref_ready || h->ref_knn != h->cfg.knn_normals;
+  return run_registration(h, init_T, rebuild, stats, out_T);
+}
+
+int aicp_b200_get_output_reading(aicp_b200_handle* hh, float* xyzw, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!xyzw || n != h->n_read || !h->read_out.p) return fail(h, AICP_B200_ERR_BAD_ARG, "get_output_reading: no registration of %lld points has run", (long long)n);
+  return download(h, xyzw, h->read_out.p, sizeof(float4) * (size_t)n);
+}
+
+int aicp_b200_get_initialized_reading(aicp_b200_handle* hh, float* xyzw, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!xyzw || n != h->n_read || !h->read_in.p) return fail(h, AICP_B200_ERR_BAD_ARG, "get_initialized_reading: no registration of %lld points has run", (long long)n);
+  // pointmatcher_registration.hpp:37-46: falls back to the raw reading when no initial transform was given
+  return download(h, xyzw, h->has_init_reading ? h->read_init.p : h->read_in.p, sizeof(float4) * (size_t)n);
+}
+
+int aicp_b200_get_reference_normals(aicp_b200_handle* hh, float* normals_xyzd, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!normals_xyzd || !h->ref_ready || n != h->n_ref) return fail(h, AICP_B200_ERR_BAD_ARG, "get_reference_normals: no reference of %lld points", (long long)n);
+  CUDA_TRY(h->tmp_b.reserve((size_t)n));
+  int rc = scatter_normals(h, h->ref_ix.pts.p, h->normals.p, h->ref_ix.n, h->tmp_b.p);
+  if (rc) return rc;
+  return download(h, normals_xyzd, h->tmp_b.p, sizeof(float4) * (size_t)n);
+}
+
+int aicp_b200_enable_match_trace(aicp_b200_handle* hh, int enable) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return AICP_B200_ERR_BAD_ARG;
+  h->trace_matches = enable != 0;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_set_profiling(aicp_b200_handle* hh, int enable) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return AICP_B200_ERR_BAD_ARG;
+  h->profiling = enable != 0;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_get_trace_matches(aicp_b200_handle* hh, int32_t* idx, int64_t iters, int64_t n_read) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!idx || !h->trace_idx.p || n_read != h->trace_n || iters > h->trace_iters || iters < 0)
+    return fail(h, AICP_B200_ERR_BAD_ARG, "get_trace_matches: trace holds %lld x %lld", (long long)h->trace_iters, (long long)h->trace_n);
+  if (iters == 0) return AICP_B200_OK;
+  return download(h, idx, h->trace_idx.p, sizeof(int32_t) * (size_t)(iters * n_read));
+}
+
+int aicp_b200_surface_normals(aicp_b200_handle* hh, const float* xyzw, int64_t n, int32_t knn, float* out_normals, int32_t* out_knn) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!xyzw || !out_normals || n < 1) return fail(h, AICP_B200_ERR_BAD_ARG, "surface_normals: null or empty cloud");
+  const float4* pts;
+  int rc = upload_points(h, h->tmp_a, xyzw, n, &pts);
+  if (rc) return rc;
+  if ((rc = build_index(h, h->tmp_ix, pts, n))) return rc;
+  CUDA_TRY(h->tmp_b.reserve((size_t)h->tmp_ix.n_pad * 2));
+  int* knn_dev = nullptr;
+  if (out_knn) { CUDA_TRY(h->tmp_i.reserve((size_t)n * knn)); knn_dev = h->tmp_i.p; }
+  float4* nm = h->tmp_b.p;              // Morton order
+  float4* no = h->tmp_b.p + h->tmp_ix.n_pad;   // original order
+  if ((rc = run_surface_normals(h, h->tmp_ix, knn, nm, knn_dev))) return rc;
+  if ((rc = scatter_normals(h, h->tmp_ix.pts.p, nm, h->tmp_ix.n, no))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if ((rc = download(h, out_normals, no, sizeof(float4) * (size_t)n))) return rc;
+  if (out_knn) return download(h, out_knn, knn_dev, sizeof(int32_t) * (size_t)n * knn);
+  return AICP_B200_OK;
+}
+
+int aicp_b200_match(aicp_b200_handle* hh, const float* ref_xyzw, int64_t n_ref, const float* qry_xyzw, int64_t n_qry,
+                    int32_t* out_idx, float* out_d2) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!ref_xyzw || !qry_xyzw || !out_idx || !out_d2 || n_ref < 1 || n_qry < 0) return fail(h, AICP_B200_ERR_BAD_ARG, "match: bad arguments");
+  if (n_qry == 0) return AICP_B200_OK;
+  const float4 *ref, *qry;
+  int rc = upload_points(h, h->tmp_a, ref_xyzw, n_ref, &ref);
+  if (rc) return rc;
+  if ((rc = upload_points(h, h->tmp_b, qry_xyzw, n_qry, &qry))) return rc;
+  if ((rc = build_index(h, h->tmp_ix, ref, n_ref))) return rc;
+  CUDA_TRY(h->tmp_i.reserve((size_t)n_qry));
+  CUDA_TRY(h->tmp_f.reserve((size_t)n_qry));
+  if ((rc = run_match_stage(h, h->tmp_ix, qry, n_qry, h->tmp_i.p, h->tmp_f.p))) return rc;
+  if ((rc = download(h, out_idx, h->tmp_i.p, sizeof(int32_t) * (size_t)n_qry))) return rc;
+  return download(h, out_d2, h->tmp_f.p, sizeof(float) * (size_t)n_qry);
+}
+
+int aicp_b200_trim_threshold(aicp_b200_handle* hh, const float* d2, int64_t n, float ratio, float* out_limit, int64_t* out_n_valid) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!d2 || !out_limit || n < 0 || n > (1ll << 30)) return fail(h, AICP_B200_ERR_BAD_ARG, "trim_threshold: bad arguments");
+  const float* dev = d2;
+  if (!is_device_ptr(d2)) {
+    CUDA_TRY(h->tmp_f.reserve((size_t)(n > 0 ? n : 1)));
+    if (n > 0) CUDA_TRY(cudaMemcpyAsync(h->tmp_f.p, d2, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    dev = h->tmp_f.p;
+  }
+  return run_trim_stage(h, dev, n, ratio, out_limit, out_n_valid);
+}
+
+int aicp_b200_overlap(aicp_b200_handle* hh, const float* ref_xyzw, int64_t n_ref, const double ref_origin[3],
+                      const float* read_xyzw, int64_t n_read, const double read_origin[3], double resolution,
+                      float* overlap_pct, int64_t counts[3]) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!ref_xyzw || !read_xyzw || !ref_origin || !read_origin || !overlap_pct || n_ref < 0 || n_read < 0 ||
+      n_ref > (1ll << 30) || n_read > (1ll << 30))
+    return fail(h, AICP_B200_ERR_BAD_ARG, "overlap: bad arguments");
+  const float4 *ref, *read;
+  int rc = upload_points(h, h->tmp_a, ref_xyzw, n_ref > 0 ? n_ref : 1, &ref);
+  if (rc) return rc;
+  if ((rc = upload_points(h, h->tmp_b, read_xyzw, n_read > 0 ? n_read : 1, &read))) return rc;
+  return run_overlap(h, ref, n_ref, ref_origin, read, n_read, read_origin, resolution, overlap_pct, counts);
+}
+
+float aicp_b200_autotune_ratio(float overlap_pct) {
+  // app.cpp:198-202
+  float current_ratio = overlap_pct / 100.0;
+  if (current_ratio < 0.25) current_ratio = 0.25;
+  else if (current_ratio > 0.70) current_ratio = 0.70;
+  // fileIO.cpp:194-198: std::stringstream << float (precision 6, general format), parsed back by libpointmatcher
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%g", (double)current_ratio);
+  return strtof(buf, nullptr);
+}
+
+int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                             const float* const* read_xyzw, const int64_t* n_read, const float* ratios, float* out_T,
+                             aicp_b200_stats* stats) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n_pairs < 0 || (n_pairs > 0 && (!ref_xyzw || !n_ref || !read_xyzw || !n_read || !out_T)))
+    return fail(h, AICP_B200_ERR_BAD_ARG, "register_batch: bad arguments");
+  int rc = load_config(h);
+  if (rc) return rc;
+  bool from_file = h->cfg_from_file;
+  h->cfg_from_file = false;                 // one parse for the whole batch
+  const float base_ratio = h->cfg.ratio;
+  for (int64_t i = 0; i < n_pairs && rc == AICP_B200_OK; ++i) {
+    if (ratios) h->cfg.ratio = ratios[i];
+    rc = aicp_b200_register(hh, ref_xyzw[i], n_ref[i], read_xyzw[i], n_read[i], nullptr, out_T + 16 * i, stats ? stats + i : nullptr);
+  }
+  h->cfg.ratio = base_ratio;
+  h->cfg_from_file = from_file;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// handle.cuh -- host-side state behind an aicp_b200_handle: device buffers that persist across calls (no per-call
+// cudaMalloc on the steady-state path), the stream, the parsed libpointmatcher chain and the last error text.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "search.cuh"
+
+namespace aicp {
+
+// grow-only device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// per-index reduction results (device)
+struct IndexMeta {
+  int bmin[3], bmax[3];          // ordered-int encoded bounding box
+  long long csum[3];             // sum of round(coord * 2^16)
+  int nonfinite;
+  int pad;
+};
+
+// Morton-ordered spatial index over one cloud
+struct SpatialIndex {
+  DevBuf<float4> pts;            // Morton order, .w = original index
+  DevBuf<float4> node;           // 2 float4 per heap node
+  DevBuf<unsigned int> keys, keys_alt, vals, vals_alt;
+  DevBuf<int> flags;             // bottom-up refit arrival counters
+  DevBuf<unsigned char> sort_tmp;
+  IndexMeta* meta = nullptr;     // device
+  int n = 0, n_pad = 0, first_leaf = 1;
+  IndexView view() const { return IndexView{pts.p, node.p, n, first_leaf}; }
+  void release() {
+    pts.release(); node.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release();
+    flags.release(); sort_tmp.release();
+    if (meta) cudaFree(meta);
+    meta = nullptr;
+  }
+};
+
+struct Comm;   // multi-GPU state (comm.cu)
+
+struct Handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  aicp_b200_icp_config cfg;
+  std::string cfg_path;
+  bool cfg_from_file = false;
+  std::string last_error;
+  int launches = 0;
+
+  // reference side
+  DevBuf<float4> ref_in;
+  SpatialIndex ref_ix;           // original frame (normals search)
+  DevBuf<float4> refc_pts;       // centred points, Morton order
+  DevBuf<float4> refc_node;      // centred boxes
+  DevBuf<float4> normals;        // Morton order (nx,ny,nz,density)
+  int64_t n_ref = 0;
+  bool ref_ready = false;
+  int ref_knn = 0;
+
+  // reading side
+  DevBuf<float4> read_in, read0, read_out, read_init;
+  DevBuf<int> match_pos;
+  DevBuf<float> d2;
+  DevBuf<unsigned int> hist;
+  int64_t n_read = 0;
+  bool has_init_reading = false;
+
+  // loop state
+  DeviceState* st = nullptr;     // device
+  DeviceState* st_host = nullptr;  // pinned
+  DevBuf<int> trace_idx;
+  bool trace_matches = false;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;   // 3 setup + 4 per iteration
+  int64_t trace_iters = 0, trace_n = 0;
+
+  // scratch for stage entry points and overlap
+  SpatialIndex tmp_ix;
+  DevBuf<float4> tmp_a, tmp_b;
+  DevBuf<int> tmp_i;
+  DevBuf<float> tmp_f;
+  DevBuf<unsigned int> ovl_bits_a, ovl_bits_b;
+  DevBuf<unsigned long long> ovl_counts;
+
+  Comm* comm = nullptr;
+};
+
+// ---- index.cu
+int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n);
+// ---- normals.cu
+int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig);
+// ---- icp.cu
+int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference, aicp_b200_stats* stats, float* out_T);
+int run_match_stage(Handle* h, const SpatialIndex& ix, const float4* qry, int64_t n_qry, int* out_idx, float* out_d2);
+int scatter_normals(Handle* h, const float4* pts_morton, const float4* normals_morton, int n, float4* out_dev);
+int run_trim_stage(Handle* h, const float* d2_dev, int64_t n, float ratio, float* out_limit, int64_t* out_n_valid);
+// ---- overlap.cu
+int run_overlap(Handle* h, const float4* ref, int64_t n_ref, const double* ref_origin, const float4* read, int64_t n_read,
+                const double* read_origin, double resolution, float* overlap_pct, int64_t* counts);
+// ---- config_yaml.cpp
+int parse_icp_yaml(const char* path, aicp_b200_icp_config* cfg, std::string* err);
+void default_icp_config(aicp_b200_icp_config* cfg);
+// ---- api.cu
+bool is_device_ptr(const void* p);
+int upload_points(Handle* h, DevBuf<float4>& buf, const float* xyzw, int64_t n, const float4** out_dev);
+
+}  // namespace aicp

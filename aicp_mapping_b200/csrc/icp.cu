@@ -1,0 +1,583 @@
+// icp.cu -- the device-resident point-to-plane ICP loop.
+//
+// replaces T = icp_(reading, reference, init) at aicp_core/src/registration/pointmatcher_registration.cpp:111, i.e.
+// [UPSTREAM] PM::ICP::operator() with the chain of aicp_core/config/icp/icp_autotuned.yaml:27-51:
+//   KDTreeMatcher{knn 1, epsilon 0}  ->  TrimmedDistOutlierFilter{ratio}  ->  PointToPlaneErrorMinimizer
+//   ->  CounterTransformationChecker + DifferentialTransformationChecker.
+//
+// One iteration = four launches on one stream, no host synchronisation anywhere in the loop:
+//   k_match       reading' -> T_iter * reading' (float, fixed order), exact NN in the centred reference index,
+//                 writes (position, d2), builds the first radix-select histogram; its last block picks the digit
+//   k_select x2   digits 2 and 3 of the radix select over the float bit pattern of d2 -> exact k-th order statistic
+//   k_accumulate  weights (d2 <= limit), F = [p x n; n], exact fixed-point sums of F F^T and F (delta.n) reduced
+//                 with a transposed warp shuffle and 128-bit integer atomics; its last block solves the 6x6 system in
+//                 float64, updates T_iter and evaluates both transformation checkers (-> st->done)
+// Every kernel returns immediately once st->done is set, so the host can enqueue max_iterations iterations blindly.
+#include "detmath.cuh"
+#include "handle.cuh"
+
+namespace aicp {
+
+__device__ __forceinline__ int ld_int(const int* p) { return *(const volatile int*)p; }
+
+__device__ __forceinline__ void raise_status(DeviceState* st, int code) {
+  atomicCAS(&st->status, 0, code);
+  *(volatile int*)&st->done = 1;
+}
+
+// ---- setup --------------------------------------------------------------------------------------------------------
+__global__ void k_loop_init(DeviceState* st, const IndexMeta* __restrict__ meta, long long n_ref, int have_init) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->status = 0; st->done = 0; st->stop_reason = 0; st->iter = 0; st->hist_n = 1;
+  st->prefix = 0; st->k_rem = 0; st->n_valid = 0; st->limit = 0.f; st->n_used_last = 0;
+  for (int i = 0; i < 4; ++i) st->ticket[i] = 0;
+  for (int i = 0; i < AICP_NSUM; ++i) { st->sum_lo[i] = 0; st->sum_hi[i] = 0; }
+  if (meta->nonfinite) { st->status = AICP_B200_ERR_NONFINITE_INPUT; st->done = 1; }
+  // A.1 step 2: centre on the mean of the (filtered) reference; exact fixed-point sum -> order independent
+  for (int d = 0; d < 3; ++d) st->mu[d] = (float)((double)meta->csum[d] / (AICP_CENTROID_SCALE * (double)n_ref));
+  st->mu[3] = 0.f;
+  for (int d = 0; d < 3; ++d) {
+    float lo = __fsub_rn(ordered_to_float(meta->bmin[d]), st->mu[d]);
+    float hi = __fsub_rn(ordered_to_float(meta->bmax[d]), st->mu[d]);
+    if (!(fabsf(lo) <= 1024.f) || !(fabsf(hi) <= 1024.f)) { if (!st->status) st->status = AICP_B200_ERR_EXTENT; st->done = 1; }
+  }
+  if (!have_init) for (int i = 0; i < 16; ++i) st->T_init[i] = (i % 5 == 0) ? 1.f : 0.f;
+  // A.1 step 5: T_refMean_dataIn = T_refIn_refMean^-1 * T_init
+  for (int i = 0; i < 16; ++i) st->M0[i] = st->T_init[i];
+  for (int d = 0; d < 3; ++d) st->M0[12 + d] = __fsub_rn(st->T_init[12 + d], st->mu[d]);
+  st->M0[3] = st->M0[7] = st->M0[11] = 0.f; st->M0[15] = 1.f;
+  for (int i = 0; i < 16; ++i) st->T_iter[i] = (i % 5 == 0) ? 1.f : 0.f;
+  det_quat_from_T(st->T_iter, st->quat_hist[0]);
+  st->tr_hist[0][0] = st->tr_hist[0][1] = st->tr_hist[0][2] = 0.0;
+}
+
+// reference' = reference - mean: points and node boxes (float subtraction is monotone, so the boxes stay valid)
+__global__ void __launch_bounds__(256) k_centre(const float4* __restrict__ pts, int n_pad, const float4* __restrict__ node,
+                                                int n_node4, const DeviceState* __restrict__ st, float4* __restrict__ pts_c,
+                                                float4* __restrict__ node_c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float mx = st->mu[0], my = st->mu[1], mz = st->mu[2];
+  if (i < n_pad) {
+    float4 p = __ldg(&pts[i]);
+    pts_c[i] = make_float4(__fsub_rn(p.x, mx), __fsub_rn(p.y, my), __fsub_rn(p.z, mz), p.w);
+  }
+  if (i < n_node4) {
+    float4 b = __ldg(&node[i]);
+    node_c[i] = make_float4(__fsub_rn(b.x, mx), __fsub_rn(b.y, my), __fsub_rn(b.z, mz), 0.f);
+  }
+}
+
+// reading' = T_refMean_dataIn * reading; optional initialised reading (init_T * reading) for getInitializedReading
+__global__ void __launch_bounds__(256) k_read_prepare(const float4* __restrict__ read, int n, DeviceState* st,
+                                                      float4* __restrict__ read0, float4* __restrict__ read_init) {
+  __shared__ float sM[16], sI[16];
+  if (threadIdx.x < 16) { sM[threadIdx.x] = st->M0[threadIdx.x]; sI[threadIdx.x] = st->T_init[threadIdx.x]; }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(&read[i]);
+  if (!isfinite(p.x) || !isfinite(p.y) || !isfinite(p.z)) { raise_status(st, AICP_B200_ERR_NONFINITE_INPUT); return; }
+  float3 q = xform_f(sM, p.x, p.y, p.z);
+  if (!(fabsf(q.x) <= 1024.f) || !(fabsf(q.y) <= 1024.f) || !(fabsf(q.z) <= 1024.f)) raise_status(st, AICP_B200_ERR_EXTENT);
+  read0[i] = make_float4(q.x, q.y, q.z, p.w);
+  if (read_init) {
+    float3 r = xform_f(sI, p.x, p.y, p.z);
+    read_init[i] = make_float4(r.x, r.y, r.z, p.w);
+  }
+}
+
+// ---- trimmed quantile: 3-digit radix select on the bit pattern of d2 (positive floats order like their bits) --------
+// digit 1 = bits 30..20, digit 2 = bits 19..9, digit 3 = bits 8..0
+__device__ __forceinline__ bool d2_valid(float d) { return d > 0.f && d < INFINITY; }   // Matches::getDistsQuantile filter
+
+// executed by all 256 threads of the last block of a histogram pass
+__device__ void select_pick(DeviceState* st, unsigned int* hist, int pass, float ratio) {
+  __shared__ unsigned long long s_warp[8];
+  __shared__ unsigned long long s_target;
+  const int t = threadIdx.x;
+  unsigned int h[8];
+  unsigned long long local = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { h[j] = __ldcg(&hist[t * 8 + j]); local += h[j]; }
+  // block exclusive scan of `local`
+  unsigned long long incl = local;
+  const int lane = t & 31, w = t >> 5;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= off) incl += o;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  unsigned long long base = 0, total = 0;
+  for (int i = 0; i < 8; ++i) { if (i < w) base += s_warp[i]; total += s_warp[i]; }
+  unsigned long long excl = base + incl - local;
+  if (t == 0) {
+    unsigned long long target;
+    if (pass == 1) {
+      st->n_valid = total;
+      if (total == 0) { raise_status(st, AICP_B200_ERR_NO_VALID_MATCH); target = 0; }
+      else if (ratio == 1.0f) target = total - 1;
+      else {
+        float fi = __fmul_rn(__ull2float_rn(total), ratio);      // size_t * float in float32, truncated (A.4)
+        target = (unsigned long long)fi;
+        if (target > total - 1) target = total - 1;
+      }
+    } else {
+      target = st->k_rem;
+    }
+    s_target = target;
+  }
+  __syncthreads();
+  unsigned long long target = s_target;
+  unsigned long long cum = excl;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (h[j] != 0 && cum <= target && target < cum + h[j]) {
+      unsigned int bin = (unsigned)(t * 8 + j);
+      st->k_rem = target - cum;
+      if (pass == 1) st->prefix = bin;
+      else if (pass == 2) st->prefix = (st->prefix << 11) | bin;
+      else {
+        unsigned int key = (st->prefix << 9) | bin;
+        st->limit = __uint_as_float(key);
+      }
+    }
+    cum += h[j];
+    hist[t * 8 + j] = 0;
+  }
+}
+
+__device__ __forceinline__ bool block_is_last(unsigned int* ticket) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+__device__ __forceinline__ void hist_flush(const unsigned int* sh, unsigned int* hist) {
+  for (int b = threadIdx.x; b < AICP_HIST_BINS; b += blockDim.x)
+    if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+
+__global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __restrict__ read0, int n, DeviceState* st,
+                                               int* __restrict__ match_pos, float* __restrict__ d2out,
+                                               unsigned int* hist, int* trace_idx, float ratio) {
+  if (ld_int(&st->done)) return;
+  __shared__ unsigned int sh[AICP_HIST_BINS];
+  __shared__ float sT[16];
+  for (int b = threadIdx.x; b < AICP_HIST_BINS; b += blockDim.x) sh[b] = 0;
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->T_iter[threadIdx.x];
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float4 r = __ldg(&read0[i]);
+    float3 p = xform_f(sT, r.x, r.y, r.z);
+    int pos; float d;
+    nn_search(ix, p.x, p.y, p.z, &pos, &d);
+    match_pos[i] = pos;
+    d2out[i] = d;
+    if (trace_idx) trace_idx[(size_t)st->iter * n + i] = __float_as_int(__ldg(&ix.pts[pos]).w);
+    if (d2_valid(d)) atomicAdd(&sh[__float_as_uint(d) >> 20], 1u);
+  }
+  __syncthreads();
+  hist_flush(sh, hist);
+  if (block_is_last(&st->ticket[0])) select_pick(st, hist, 1, ratio);
+}
+
+// pass 1: plain histogram of digit 1 (stage entry point); pass 2 / 3: next digits among keys matching the prefix
+__global__ void __launch_bounds__(256) k_select(const float* __restrict__ d2, int n, DeviceState* st, unsigned int* hist,
+                                                int pass, float ratio) {
+  if (ld_int(&st->done)) return;
+  __shared__ unsigned int sh[AICP_HIST_BINS];
+  for (int b = threadIdx.x; b < AICP_HIST_BINS; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  const unsigned int prefix = st->prefix;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float d = __ldg(&d2[i]);
+    if (!d2_valid(d)) continue;
+    unsigned int key = __float_as_uint(d);
+    if (pass == 1) atomicAdd(&sh[key >> 20], 1u);
+    else if (pass == 2) { if ((key >> 20) == prefix) atomicAdd(&sh[(key >> 9) & 2047u], 1u); }
+    else { if ((key >> 9) == prefix) atomicAdd(&sh[key & 511u], 1u); }
+  }
+  __syncthreads();
+  hist_flush(sh, hist);
+  if (block_is_last(&st->ticket[1])) select_pick(st, hist, pass, ratio);
+}
+
+// ---- normal equations ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long fixed_term(float a, float b) {
+  return __double2ll_rn(((double)a * (double)b) * AICP_FIXED_SCALE);
+}
+
+__device__ __forceinline__ void atomic_add_128(unsigned long long* lo, long long* hi, long long v) {
+  unsigned long long vlo = (unsigned long long)v;
+  unsigned long long old = atomicAdd(lo, vlo);
+  unsigned long long carry = (old + vlo < old) ? 1ull : 0ull;
+  unsigned long long vhi = (v < 0 ? ~0ull : 0ull) + carry;
+  if (vhi) atomicAdd((unsigned long long*)hi, vhi);
+}
+
+// A.5 solve + pose update, A.7 checkers; one thread
+__device__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read) {
+  long long hi[AICP_NSUM];
+  unsigned long long lo[AICP_NSUM];
+  for (int i = 0; i < AICP_NSUM; ++i) {
+    lo[i] = __ldcg(&st->sum_lo[i]); hi[i] = __ldcg(&st->sum_hi[i]);
+    st->sum_lo[i] = 0; st->sum_hi[i] = 0;
+  }
+  long long n_used = (long long)lo[27];
+  double x[6];
+  det_solve6(hi, lo, x);
+  float dT[16], T[16];
+  det_pose_increment(x, dT);
+  for (int i = 0; i < 16; ++i) T[i] = st->T_iter[i];
+  mat4_mul_f(dT, T, T);                                    // T_iter = dT * T_iter
+  for (int i = 0; i < 16; ++i) st->T_iter[i] = T[i];
+  int it = st->iter;
+  aicp_b200_iter_trace* tr = &st->trace[it];
+  for (int i = 0; i < 16; ++i) tr->T_iter[i] = T[i];
+  tr->limit_d2 = st->limit; tr->n_valid = (long long)st->n_valid; tr->n_used = n_used;
+  tr->rot_err = __longlong_as_double(0x7FF8000000000000ll); tr->trans_err = tr->rot_err;
+  st->n_used_last = n_used;
+  ++it;
+  st->iter = it;
+  bool has_nan = false;
+  for (int i = 0; i < 16; ++i) if (T[i] != T[i]) has_nan = true;
+  if (has_nan) { raise_status(st, AICP_B200_ERR_NAN); return; }
+  bool iterate = true;
+  if (it >= lp.max_iterations) { iterate = false; st->stop_reason = AICP_B200_STOP_COUNTER; }
+  int hn = st->hist_n;
+  det_quat_from_T(T, st->quat_hist[hn]);
+  st->tr_hist[hn][0] = (double)T[12]; st->tr_hist[hn][1] = (double)T[13]; st->tr_hist[hn][2] = (double)T[14];
+  ++hn;
+  st->hist_n = hn;
+  if (hn > lp.smooth_length) {
+    double re = 0.0, te = 0.0;
+    for (int i = hn - 1; i >= hn - lp.smooth_length; --i) {
+      re = re + det_quat_angular_distance(st->quat_hist[i], st->quat_hist[i - 1]);
+      double dx = st->tr_hist[i][0] - st->tr_hist[i - 1][0], dy = st->tr_hist[i][1] - st->tr_hist[i - 1][1],
+             dz = st->tr_hist[i][2] - st->tr_hist[i - 1][2];
+      te = te + sqrt((dx * dx + dy * dy) + dz * dz);
+    }
+    re = re / (double)lp.smooth_length;
+    te = te / (double)lp.smooth_length;
+    tr->rot_err = re; tr->trans_err = te;
+    if (re < (double)lp.min_diff_rot && te < (double)lp.min_diff_trans) {
+      if (iterate) st->stop_reason = AICP_B200_STOP_DIFFERENTIAL;
+      iterate = false;
+    }
+  }
+  if (!iterate) *(volatile int*)&st->done = 1;
+}
+
+__global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
+                                                    const float4* __restrict__ read0, const int* __restrict__ match_pos,
+                                                    const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp) {
+  if (ld_int(&st->done)) return;
+  __shared__ float sT[16];
+  __shared__ long long s_part[8][32];
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->T_iter[threadIdx.x];
+  __syncthreads();
+  const float limit = st->limit;
+  long long v[32];
+#pragma unroll
+  for (int s = 0; s < 32; ++s) v[s] = 0;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float d = __ldg(&d2[i]);
+    if (d <= limit) {                                        // TrimmedDist weight (A.4)
+      float4 r = __ldg(&read0[i]);
+      float3 p = xform_f(sT, r.x, r.y, r.z);
+      int pos = __ldg(&match_pos[i]);
+      float4 q = __ldg(&refc[pos]);
+      float4 nr = __ldg(&normals[pos]);
+      float F[6];
+      F[0] = __fsub_rn(__fmul_rn(p.y, nr.z), __fmul_rn(p.z, nr.y));      // c = p x n
+      F[1] = __fsub_rn(__fmul_rn(p.z, nr.x), __fmul_rn(p.x, nr.z));
+      F[2] = __fsub_rn(__fmul_rn(p.x, nr.y), __fmul_rn(p.y, nr.x));
+      F[3] = nr.x; F[4] = nr.y; F[5] = nr.z;
+      float ddx = __fsub_rn(p.x, q.x), ddy = __fsub_rn(p.y, q.y), ddz = __fsub_rn(p.z, q.z);
+      float res = __fmul_rn(ddx, nr.x);
+      res = __fadd_rn(res, __fmul_rn(ddy, nr.y));
+      res = __fadd_rn(res, __fmul_rn(ddz, nr.z));
+      int s = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) v[s++] = fixed_term(F[a], F[b]);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) v[s++] = fixed_term(F[a], res);
+      v[27] = 1;
+    }
+  }
+  // transposed warp reduction: after 5 exchange rounds lane L holds the warp total of slot L (31 shuffles, not 32*5)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int s = 0; s < off; ++s) {
+      long long keep = upper ? v[s + off] : v[s];
+      long long send = upper ? v[s] : v[s + off];
+      long long recv = __shfl_xor_sync(0xFFFFFFFFu, send, off);
+      v[s] = keep + recv;
+    }
+  }
+  s_part[w][lane] = v[0];
+  __syncthreads();
+  if (w == 0) {
+    long long tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += s_part[k][lane];
+    if (lane < AICP_NSUM && tot != 0) atomic_add_128(&st->sum_lo[lane], &st->sum_hi[lane], tot);
+  }
+  if (block_is_last(&st->ticket[2])) {
+    if (threadIdx.x == 0) solve_and_check(st, lp, n);
+  }
+}
+
+// ---- epilogue ----------------------------------------------------------------------------------------------------
+// A.1 step 7: T = T_refIn_refMean * T_iter * T_refMean_dataIn, evaluated left to right
+__global__ void k_finalize(DeviceState* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float Tmu[16], Y[16];
+  for (int i = 0; i < 16; ++i) Tmu[i] = (i % 5 == 0) ? 1.f : 0.f;
+  Tmu[12] = st->mu[0]; Tmu[13] = st->mu[1]; Tmu[14] = st->mu[2];
+  mat4_mul_f(Tmu, st->T_iter, Y);
+  mat4_mul_f(Y, st->M0, st->T_final);
+}
+
+// pointmatcher_registration.cpp:128-131: out_read_cloud_ = T * reading (the unfiltered copy)
+__global__ void __launch_bounds__(256) k_transform_out(const float4* __restrict__ read, int n, const DeviceState* __restrict__ st,
+                                                       float4* __restrict__ out) {
+  __shared__ float sT[16];
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->T_final[threadIdx.x];
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(&read[i]);
+  float3 q = xform_f(sT, p.x, p.y, p.z);
+  out[i] = make_float4(q.x, q.y, q.z, p.w);
+}
+
+// un-permute Morton-ordered normals (api: get_reference_normals)
+__global__ void __launch_bounds__(256) k_scatter_normals(const float4* __restrict__ pts, const float4* __restrict__ normals, int n,
+                                                         float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[__float_as_int(__ldg(&pts[i]).w)] = normals[i];
+}
+
+// stage entry point: plain exact NN of queries (no transform, no histogram)
+__global__ void __launch_bounds__(256) k_match_plain(IndexView ix, const float4* __restrict__ qry, int n, int* __restrict__ out_idx,
+                                                     float* __restrict__ out_d2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = __ldg(&qry[i]);
+  int pos; float d;
+  nn_search(ix, q.x, q.y, q.z, &pos, &d);
+  out_idx[i] = __float_as_int(__ldg(&ix.pts[pos]).w);
+  out_d2[i] = d;
+}
+
+__global__ void k_stage_reset(DeviceState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->status = 0; st->done = 0; st->prefix = 0; st->k_rem = 0; st->n_valid = 0; st->limit = 0.f;
+    for (int i = 0; i < 4; ++i) st->ticket[i] = 0;
+  }
+}
+
+// ---- host orchestration ------------------------------------------------------------------------------------------------
+static int ensure_state(Handle* h) {
+  if (!h->st) {
+    CUDA_TRY(cudaMalloc((void**)&h->st, sizeof(DeviceState)));
+    CUDA_TRY(cudaMemsetAsync(h->st, 0, sizeof(DeviceState), h->stream));
+  }
+  if (!h->st_host) CUDA_TRY(cudaMallocHost((void**)&h->st_host, sizeof(DeviceState)));
+  CUDA_TRY(h->hist.reserve(AICP_HIST_BINS));
+  static_assert(AICP_HIST_BINS == 2048, "select_pick assumes 256 threads x 8 bins");
+  return AICP_B200_OK;
+}
+
+static int status_to_error(Handle* h, int status) {
+  switch (status) {
+    case AICP_B200_OK: return AICP_B200_OK;
+    case AICP_B200_ERR_NONFINITE_INPUT: return fail(h, status, "input cloud contains non-finite coordinates");
+    case AICP_B200_ERR_EXTENT: return fail(h, status, "cloud extends more than 1024 m from the reference centroid");
+    case AICP_B200_ERR_NO_VALID_MATCH: return fail(h, status, "TrimmedDistOutlierFilter: no finite positive distance (ConvergenceError)");
+    case AICP_B200_ERR_NAN: return fail(h, status, "NaN in the iteration transform (ConvergenceError)");
+    default: return fail(h, status, "device raised status %d", status);
+  }
+}
+
+int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference, aicp_b200_stats* stats, float* out_T) {
+  int rc = ensure_state(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  const aicp_b200_icp_config& cfg = h->cfg;
+  if (cfg.max_iterations < 1 || cfg.max_iterations > AICP_B200_MAX_ITERS || cfg.smooth_length < 1 ||
+      cfg.smooth_length > AICP_B200_MAX_ITERS)
+    return fail(h, AICP_B200_ERR_BAD_ARG, "maxIterationCount / smoothLength outside [1,%d]", AICP_B200_MAX_ITERS);
+  if (!(cfg.ratio > 0.f) || cfg.ratio > 1.f) return fail(h, AICP_B200_ERR_BAD_ARG, "TrimmedDistOutlierFilter ratio %g outside (0,1]", cfg.ratio);
+  const int n_read = (int)h->n_read, n_ref = (int)h->n_ref;
+  h->launches = 0;
+  const bool prof = h->profiling;
+  if (prof) {
+    size_t need = 3 + 4 * (size_t)cfg.max_iterations;
+    while (h->prof_ev.size() < need) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
+  }
+  auto mark = [&](size_t i) { if (prof) cudaEventRecord(h->prof_ev[i], s); };
+  CUDA_TRY(cudaEventRecord(h->ev[0], s));
+  mark(0);
+
+  if (rebuild_reference) {
+    h->ref_ready = false;
+    rc = build_index(h, h->ref_ix, h->ref_in.p, n_ref);
+    if (rc) return rc;
+    mark(1);
+    CUDA_TRY(h->normals.reserve((size_t)h->ref_ix.n_pad));
+    CUDA_TRY(h->refc_pts.reserve((size_t)h->ref_ix.n_pad));
+    CUDA_TRY(h->refc_node.reserve((size_t)4 * h->ref_ix.first_leaf));
+    rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr);
+    if (rc) return rc;
+    h->ref_knn = cfg.knn_normals;
+    mark(2);
+  } else { mark(1); mark(2); }
+  if (cfg.reading_normals) {
+    // the reference runs the same filter on the reading (icp_autotuned.yaml:9-14); PointToPlane never reads the result
+    rc = build_index(h, h->tmp_ix, h->read_in.p, n_read);
+    if (rc) return rc;
+    CUDA_TRY(h->tmp_a.reserve((size_t)h->tmp_ix.n_pad));
+    rc = run_surface_normals(h, h->tmp_ix, cfg.knn_normals, h->tmp_a.p, nullptr);
+    if (rc) return rc;
+  }
+  if (init_T_host) {
+    memcpy(h->st_host->T_init, init_T_host, 16 * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(h->st->T_init, h->st_host->T_init, 16 * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  k_loop_init<<<1, 32, 0, s>>>(h->st, h->ref_ix.meta, (long long)n_ref, init_T_host ? 1 : 0);
+  if (rebuild_reference) {
+    int n4 = 4 * h->ref_ix.first_leaf;
+    int m = h->ref_ix.n_pad > n4 ? h->ref_ix.n_pad : n4;
+    k_centre<<<(m + 255) / 256, 256, 0, s>>>(h->ref_ix.pts.p, h->ref_ix.n_pad, h->ref_ix.node.p, n4, h->st, h->refc_pts.p,
+                                            h->refc_node.p);
+    h->launches += 1;
+  }
+  CUDA_TRY(h->read0.reserve((size_t)n_read));
+  CUDA_TRY(h->read_out.reserve((size_t)n_read));
+  CUDA_TRY(h->match_pos.reserve((size_t)n_read));
+  CUDA_TRY(h->d2.reserve((size_t)n_read));
+  float4* read_init = nullptr;
+  if (init_T_host) { CUDA_TRY(h->read_init.reserve((size_t)n_read)); read_init = h->read_init.p; }
+  h->has_init_reading = init_T_host != nullptr;
+  int* trace_idx = nullptr;
+  if (h->trace_matches) {
+    CUDA_TRY(h->trace_idx.reserve((size_t)cfg.max_iterations * n_read));
+    trace_idx = h->trace_idx.p;
+    h->trace_iters = cfg.max_iterations; h->trace_n = n_read;
+  }
+  const int blocks = (n_read + 255) / 256;
+  k_read_prepare<<<blocks, 256, 0, s>>>(h->read_in.p, n_read, h->st, h->read0.p, read_init);
+  h->launches += 2;
+  CUDA_TRY(cudaEventRecord(h->ev[1], s));
+
+  IndexView cix{h->refc_pts.p, h->refc_node.p, h->ref_ix.n, h->ref_ix.first_leaf};
+  LoopParams lp{cfg.ratio, cfg.max_iterations, cfg.min_diff_rot, cfg.min_diff_trans, cfg.smooth_length};
+  const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
+  for (int it = 0; it < cfg.max_iterations; ++it) {
+    mark(3 + 4 * (size_t)it);
+    k_match<<<blocks, 256, 0, s>>>(cix, h->read0.p, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio);
+    mark(4 + 4 * (size_t)it);
+    k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 2, cfg.ratio);
+    k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 3, cfg.ratio);
+    mark(5 + 4 * (size_t)it);
+    k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, h->read0.p, h->match_pos.p, h->d2.p, n_read, h->st, lp);
+    mark(6 + 4 * (size_t)it);
+  }
+  h->launches += 4 * cfg.max_iterations;
+  CUDA_TRY(cudaEventRecord(h->ev[2], s));
+  k_finalize<<<1, 32, 0, s>>>(h->st);
+  k_transform_out<<<blocks, 256, 0, s>>>(h->read_in.p, n_read, h->st, h->read_out.p);
+  h->launches += 2;
+  CUDA_TRY(cudaMemcpyAsync(h->st_host, h->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord(h->ev[3], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+
+  const DeviceState* hs = h->st_host;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->iterations = hs->iter;
+    stats->stop_reason = hs->stop_reason;
+    stats->weighted_point_used_ratio = (float)hs->n_used_last / (float)n_read;
+    for (int d = 0; d < 3; ++d) stats->mean_ref[d] = hs->mu[d];
+    stats->n_ref = n_ref; stats->n_read = n_read;
+    cudaEventElapsedTime(&stats->ms_total, h->ev[0], h->ev[3]);
+    cudaEventElapsedTime(&stats->ms_setup, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&stats->ms_iterations, h->ev[1], h->ev[2]);
+    stats->gpu_launches = h->launches;
+    if (prof) {
+      stats->profiled = 1;
+      float ms = 0.f;
+      cudaEventElapsedTime(&stats->ms_index, h->prof_ev[0], h->prof_ev[1]);
+      cudaEventElapsedTime(&stats->ms_normals, h->prof_ev[1], h->prof_ev[2]);
+      for (int it = 0; it < hs->iter && it < cfg.max_iterations; ++it) {
+        cudaEventElapsedTime(&ms, h->prof_ev[3 + 4 * it], h->prof_ev[4 + 4 * it]); stats->ms_match += ms;
+        cudaEventElapsedTime(&ms, h->prof_ev[4 + 4 * it], h->prof_ev[5 + 4 * it]); stats->ms_select += ms;
+        cudaEventElapsedTime(&ms, h->prof_ev[5 + 4 * it], h->prof_ev[6 + 4 * it]); stats->ms_accumulate += ms;
+      }
+    }
+    int nt = hs->iter < AICP_B200_MAX_ITERS ? hs->iter : AICP_B200_MAX_ITERS;
+    memcpy(stats->trace, hs->trace, sizeof(aicp_b200_iter_trace) * (size_t)nt);
+  }
+  if (hs->status) return status_to_error(h, hs->status);
+  h->ref_ready = true;
+  if (out_T) memcpy(out_T, hs->T_final, 16 * sizeof(float));
+  return AICP_B200_OK;
+}
+
+int run_match_stage(Handle* h, const SpatialIndex& ix, const float4* qry, int64_t n_qry, int* out_idx, float* out_d2) {
+  if (n_qry == 0) return AICP_B200_OK;
+  k_match_plain<<<(unsigned)((n_qry + 255) / 256), 256, 0, h->stream>>>(ix.view(), qry, (int)n_qry, out_idx, out_d2);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return AICP_B200_OK;
+}
+
+int run_trim_stage(Handle* h, const float* d2_dev, int64_t n64, float ratio, float* out_limit, int64_t* out_n_valid) {
+  int rc = ensure_state(h);
+  if (rc) return rc;
+  if (!(ratio > 0.f) || ratio > 1.f) return fail(h, AICP_B200_ERR_BAD_ARG, "ratio %g outside (0,1]", ratio);
+  cudaStream_t s = h->stream;
+  int n = (int)n64;
+  int blocks = (n + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  k_stage_reset<<<1, 32, 0, s>>>(h->st);
+  CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * AICP_HIST_BINS, s));
+  for (int pass = 1; pass <= 3; ++pass) k_select<<<blocks, 256, 0, s>>>(d2_dev, n, h->st, h->hist.p, pass, ratio);
+  CUDA_TRY(cudaMemcpyAsync(h->st_host, h->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  if (out_n_valid) *out_n_valid = (int64_t)h->st_host->n_valid;
+  if (h->st_host->status) return status_to_error(h, h->st_host->status);
+  *out_limit = h->st_host->limit;
+  return AICP_B200_OK;
+}
+
+int scatter_normals(Handle* h, const float4* pts_morton, const float4* normals_morton, int n, float4* out_dev) {
+  k_scatter_normals<<<(n + 255) / 256, 256, 0, h->stream>>>(pts_morton, normals_morton, n, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return AICP_B200_OK;
+}
+
+}  // namespace aicp

@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's registration plug-in interface, over the C ABI.
+
+Mirrors (same names, argument meaning and error behaviour where Python allows):
+  aicp::AbstractRegistrator                 aicp_core/include/aicp_registration/abstract_registrator.hpp:8-19
+  aicp::PointmatcherRegistration            aicp_core/include/aicp_registration/pointmatcher_registration.hpp:22-67
+  aicp::create_registrator                  aicp_core/include/aicp_registration/registration.hpp:9-19
+  RegistrationParams                        aicp_core/include/aicp_registration/common.hpp:7-23
+  replaceRatioConfigFile                    aicp_core/src/utils/fileIO.cpp:179-214
+  App::computeRegistration                  aicp_core/src/registration/app.cpp:187-216
+  parseTransformationDeg                    aicp_core/src/utils/cloudIO.cpp:261-302
+
+The C++ adapter a maintainer would compile into aicp_core is include/aicp_b200_adapter.hpp; this module is the same
+thing for the Python test and benchmark harness.  All arithmetic happens in libaicp_b200.so on the GPU.
+"""
+import ctypes as C
+import math
+import sys
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class PointmatcherRegistrationParams:
+    configFileName: str = ""
+    initialTransform: str = ""      # "x,y,theta" (metres, metres, degrees)
+    printOutputStatistics: bool = False
+
+
+@dataclass
+class RegistrationParams:
+    type: str = ""
+    sensorRange: float = -1.0
+    sensorAngularView: float = -1.0
+    loadPosesFrom: str = ""
+    initialTransform: str = ""
+    pointmatcher: PointmatcherRegistrationParams = field(default_factory=PointmatcherRegistrationParams)
+
+
+def parseTransformationDeg(transform, cloudDimension=3):
+    """cloudIO.cpp:261-302: "[x,y,theta_deg]" -> 4x4 float32 (identity, with a message, when unparsable)."""
+    T = np.eye(cloudDimension + 1, dtype=np.float32)
+    s = transform.replace("[", "").replace("]", "").replace(",", " ").replace(";", " ").split()
+    try:
+        v = [float(np.float32(float(x))) for x in s[:3]]
+        if len(v) < 3:
+            raise ValueError
+    except ValueError:
+        sys.stderr.write("[Cloud IO] An error occured while trying to parse the initial transformation.\n"
+                         "No initial transformation will be used\n")
+        return T
+    th = v[2] * math.pi / 180.0
+    T[0, 0] = math.cos(th); T[0, 1] = -math.sin(th)
+    T[1, 0] = math.sin(th); T[1, 1] = math.cos(th)
+    T[0, cloudDimension] = v[0]
+    T[1, cloudDimension] = v[1]
+    return T
+
+
+def replaceRatioConfigFile(in_file, out_file, ratio):
+    """fileIO.cpp:179-214, byte for byte: on every line holding "ratio: " the 11 characters from its start are replaced
+    by "ratio: " + (ostream << float), and every line (plus one trailing empty line at EOF) is written with '\\n'."""
+    try:
+        with open(in_file, "r") as f:
+            text = f.read()
+    except OSError:
+        sys.stderr.write("[File IO] Could not open config file for params update.\n")
+        text = ""
+    lines = text.split("\n")          # getline until eof: a final '\n' yields one extra empty line, as in the reference
+    word = "ratio: "
+    repl = word + ("%g" % float(np.float32(ratio)))
+    out = []
+    for line in lines:
+        pos = line.find(word)
+        if pos != -1:
+            line = line[:pos] + repl + line[pos + len(word) + 4:]
+        out.append(line + "\n")
+    with open(out_file, "w") as f:
+        f.write("".join(out))
+
+
+class B200Registration:
+    """AbstractRegistrator implemented by libaicp_b200.so.  One instance == one aicp_b200_handle (one GPU stream)."""
+
+    def __init__(self, params=None, device=-1):
+        self.params_ = params or RegistrationParams(type="B200")
+        self._lib = capi.lib()
+        self._h = C.c_void_p()
+        path = self.params_.pointmatcher.configFileName
+        rc = self._lib.aicp_b200_create(path.encode() if path else None, int(device), C.byref(self._h))
+        if rc:
+            raise capi.AicpError(rc, self._lib.aicp_b200_last_error(None).decode())
+        self.stats = capi.Stats()
+        self._last_T = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.aicp_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise capi.AicpError(rc, self._lib.aicp_b200_last_error(self._h).decode())
+
+    # ---- AbstractRegistrator ------------------------------------------------------------------------------------
+    def updateConfigParams(self, config_name):
+        """pointmatcher_registration.hpp:52-54.  The file is re-read at the start of every registerClouds."""
+        self.params_.pointmatcher.configFileName = config_name
+        self._check(self._lib.aicp_b200_set_config(self._h, config_name.encode() if config_name else None))
+
+    def registerClouds(self, cloud_ref, cloud_read):
+        """pointmatcher_registration.cpp:14-23,92-151.  Clouds: n x 3 / n x 4 float32 numpy arrays or n x 4 CUDA
+        tensors.  Returns final_transform (4x4 float32) -- the reference writes it through an out-parameter."""
+        pr, nr, keep_r = capi.ptr_and_count(cloud_ref)
+        pq, nq, keep_q = capi.ptr_and_count(cloud_read)
+        init = None
+        if self.params_.pointmatcher.initialTransform:
+            init = self.applyInitialization()
+        return self._register(pr, nr, pq, nq, init)
+
+    def _register(self, pr, nr, pq, nq, init):
+        T = np.zeros(16, dtype=np.float32)
+        init_c = capi.mat_to_colmajor(init) if init is not None else None
+        rc = self._lib.aicp_b200_register(self._h, pr, nr, pq, nq,
+                                          C.c_void_p(init_c.ctypes.data) if init_c is not None else None,
+                                          T.ctypes.data_as(C.POINTER(C.c_float)), C.byref(self.stats))
+        self._check(rc)
+        self._last_T = capi.colmajor_to_mat(T)
+        return self._last_T
+
+    def applyInitialization(self):
+        """pointmatcher_registration.cpp:71-89: parse "x,y,theta", fall back to identity when it is not rigid."""
+        T = parseTransformationDeg(self.params_.pointmatcher.initialTransform, 3)
+        if abs(1.0 - float(np.linalg.det(T[:3, :3].astype(np.float64)))) > 1e-3:      # RigidTransformation::checkParameters
+            sys.stderr.write("\n[Pointmatcher] Initial transformation is not rigid, identity will be used.\n")
+            T = np.eye(4, dtype=np.float32)
+        return T
+
+    def getOutputReading(self):
+        """pointmatcher_registration.hpp:48-50: T * reading, n x 4 float32."""
+        n = int(self.stats.n_read)
+        out = np.zeros((n, 4), dtype=np.float32)
+        self._check(self._lib.aicp_b200_get_output_reading(self._h, C.c_void_p(out.ctypes.data), n))
+        return out
+
+    def getInitializedReading(self):
+        """pointmatcher_registration.hpp:37-46."""
+        n = int(self.stats.n_read)
+        out = np.zeros((n, 4), dtype=np.float32)
+        self._check(self._lib.aicp_b200_get_initialized_reading(self._h, C.c_void_p(out.ctypes.data), n))
+        return out
+
+    # ---- conveniences beyond the reference interface ---------------------------------------------------------------
+    def getOutputTransform(self):
+        """Named in BASELINE.json; the reference returns the transform only through registerClouds' out-parameter."""
+        return self._last_T
+
+    def getWeightedPointUsedRatio(self):
+        """icp_.errorMinimizer->getWeightedPointUsedRatio(), printed at pointmatcher_registration.cpp:114."""
+        return float(self.stats.weighted_point_used_ratio)
+
+    def setConfig(self, **kw):
+        cfg = self.getConfig()
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        self._check(self._lib.aicp_b200_set_config_struct(self._h, C.byref(cfg)))
+
+    def getConfig(self):
+        cfg = capi.IcpConfig()
+        self._check(self._lib.aicp_b200_get_config(self._h, C.byref(cfg)))
+        return cfg
+
+    def setReference(self, cloud_ref):
+        p, n, keep = capi.ptr_and_count(cloud_ref)
+        self._check(self._lib.aicp_b200_set_reference(self._h, p, n))
+
+    def registerToReference(self, cloud_read, init_T=None):
+        p, n, keep = capi.ptr_and_count(cloud_read)
+        T = np.zeros(16, dtype=np.float32)
+        init_c = capi.mat_to_colmajor(init_T) if init_T is not None else None
+        rc = self._lib.aicp_b200_register_to_reference(self._h, p, n,
+                                                       C.c_void_p(init_c.ctypes.data) if init_c is not None else None,
+                                                       T.ctypes.data_as(C.POINTER(C.c_float)), C.byref(self.stats))
+        self._check(rc)
+        self._last_T = capi.colmajor_to_mat(T)
+        return self._last_T
+
+    def registerCloudsInit(self, cloud_ref, cloud_read, init_T):
+        """registerClouds with an explicit 4x4 initial guess instead of the "x,y,theta" string."""
+        pr, nr, keep_r = capi.ptr_and_count(cloud_ref)
+        pq, nq, keep_q = capi.ptr_and_count(cloud_read)
+        return self._register(pr, nr, pq, nq, init_T)
+
+    def getReferenceNormals(self):
+        n = int(self.stats.n_ref)
+        out = np.zeros((n, 4), dtype=np.float32)
+        self._check(self._lib.aicp_b200_get_reference_normals(self._h, C.c_void_p(out.ctypes.data), n))
+        return out
+
+    def enableMatchTrace(self, enable=True):
+        self._check(self._lib.aicp_b200_enable_match_trace(self._h, int(enable)))
+
+    def setProfiling(self, enable=True):
+        self._check(self._lib.aicp_b200_set_profiling(self._h, int(enable)))
+
+    def getTraceMatches(self):
+        it, n = int(self.stats.iterations), int(self.stats.n_read)
+        out = np.zeros((it, n), dtype=np.int32)
+        self._check(self._lib.aicp_b200_get_trace_matches(self._h, C.c_void_p(out.ctypes.data), it, n))
+        return out
+
+    def trace(self):
+        out = []
+        for i in range(int(self.stats.iterations)):
+            t = self.stats.trace[i]
+            out.append(dict(T_iter=capi.colmajor_to_mat(list(t.T_iter)), limit_d2=np.float32(t.limit_d2), n_valid=t.n_valid,
+                            n_used=t.n_used, rot_err=t.rot_err, trans_err=t.trans_err))
+        return out
+
+    # ---- stage entry points (parity tests) -----------------------------------------------------------------------
+    def surfaceNormals(self, cloud, knn=20, want_knn=True):
+        p, n, keep = capi.ptr_and_count(cloud)
+        normals = np.zeros((n, 4), dtype=np.float32)
+        ids = np.zeros((n, knn), dtype=np.int32) if want_knn else None
+        self._check(self._lib.aicp_b200_surface_normals(self._h, p, n, int(knn), C.c_void_p(normals.ctypes.data),
+                                                        C.c_void_p(ids.ctypes.data) if ids is not None else None))
+        return normals, ids
+
+    def match(self, cloud_ref, cloud_qry):
+        pr, nr, k1 = capi.ptr_and_count(cloud_ref)
+        pq, nq, k2 = capi.ptr_and_count(cloud_qry)
+        idx = np.zeros(nq, dtype=np.int32)
+        d2 = np.zeros(nq, dtype=np.float32)
+        self._check(self._lib.aicp_b200_match(self._h, pr, nr, pq, nq, C.c_void_p(idx.ctypes.data), C.c_void_p(d2.ctypes.data)))
+        return idx, d2
+
+    def trimThreshold(self, d2, ratio):
+        d2 = np.ascontiguousarray(d2, dtype=np.float32)
+        limit, nv = C.c_float(), C.c_int64()
+        self._check(self._lib.aicp_b200_trim_threshold(self._h, C.c_void_p(d2.ctypes.data), d2.shape[0], C.c_float(ratio),
+                                                       C.byref(limit), C.byref(nv)))
+        return np.float32(limit.value), nv.value
+
+
+def create_registrator(parameters, device=-1):
+    """registration.hpp:9-19 with the extra "B200" branch a maintainer adds."""
+    if parameters.type == "B200":
+        return B200Registration(parameters, device=device)
+    sys.stderr.write("Invalid registration type %s.\n" % parameters.type)
+    return None
+
+
+def autotune_ratio(octree_overlap):
+    """app.cpp:198-202 clamp followed by the text round trip of fileIO.cpp:194-198 (done in the library)."""
+    return float(capi.lib().aicp_b200_autotune_ratio(C.c_float(octree_overlap)))
+
+
+def computeRegistration(registr, reference, reading, octree_overlap, default_config_file, registration_config_file):
+    """App::computeRegistration, app.cpp:187-216: clamp the overlap into the trimmed ratio, rewrite the ICP chain file,
+    point the registrator at it, register."""
+    current_ratio = np.float32(octree_overlap / 100.0)
+    if current_ratio < 0.25:
+        current_ratio = np.float32(0.25)
+    elif current_ratio > 0.70:
+        current_ratio = np.float32(0.70)
+    replaceRatioConfigFile(default_config_file, registration_config_file, current_ratio)
+    registr.updateConfigParams(registration_config_file)
+    return registr.registerClouds(reference, reading)

@@ -283,3 +283,24 @@ def make_map_case(n_map=10485760, n_read=122880, trial=0, n_poses=1):
         E = _prior_error(rng)
         out.append(dict(read=apply_T(E, read_true), T_true=np.linalg.inv(E), read_origin=E[:3, :3] @ pose[:3, 3] + E[:3, 3]))
     return dict(map=map_xyz, readings=out, name="C4 %d-pt reading vs %d-pt map" % (n_read, n_map))
+
+
+def c1_pair(reading=1, fixture=None):
+    """C1: the planar sample scans of aicp_core/data (scan_00 = reference, scan_01 / scan_02 = readings) extruded to 3-D:
+    16 copies at z = 0.00 .. 0.75 m (34 592 wall points) plus a 0.1 m floor grid under the scan, because a flat z = 0
+    lift makes every normal +-z (point-to-plane degenerate).  Scans come from tests/golden/c1_scans.npz."""
+    import os
+    fixture = fixture or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                      "c1_scans.npz")
+    z = np.load(fixture)
+
+    def extrude(xy):
+        layers = [np.c_[xy, np.full(len(xy), np.float32(0.05 * k))] for k in range(16)]
+        lo, hi = xy.min(0), xy.max(0)
+        gx, gy = np.meshgrid(np.arange(lo[0], hi[0], 0.1), np.arange(lo[1], hi[1], 0.1), indexing="ij")
+        floor = np.c_[gx.ravel(), gy.ravel(), np.zeros(gx.size)]
+        return np.concatenate(layers + [floor], 0).astype(np.float32)
+    ref = extrude(z["scan_00"])
+    read = extrude(z["scan_0%d" % reading])
+    return dict(ref=ref, read=read, ref_origin=np.zeros(3), read_origin=np.zeros(3), T_true=None,
+                name="C1 aicp_core/data sample scans extruded to 3-D, %d / %d pts" % (len(ref), len(read)))

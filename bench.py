@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- ICP registrations/second of the AICP hot path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs P]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload: BASELINE.json configs[2], "Velodyne HDL-64 KITTI-shaped synthetic clouds (~128k pts, ground removed)
+point-to-plane ICP" -- the configuration the metric ("128k pts") is quoted on; 131 072 x 131 072 points per pair, chain of
+aicp_core/config/icp/icp_autotuned.yaml with epsilon 0 and the ratio auto-tuned from the octree overlap.
+A step = one pass of the hot path (registerClouds: index + normals + ICP loop + output cloud) over P cloud pairs per GPU.
+
+  value     registrations/s with both clouds already resident in HBM (device pointers through the C ABI); per-registration
+            device time from CUDA events on the library's own stream; L2 flushed before every registration.
+  e2e       the same through the plugin call with pinned HOST buffers (H2D of both clouds and D2H of the result inside).
+  roofline  dominant kernel k_match (exact NN + transform + histogram): algorithmic bytes 24 B/reading point per launch
+            over its CUDA-event duration, against the measured HBM copy peak.
+  cpu_baseline  the CPU oracle (a restatement of the reference's libpointmatcher path; the real one cannot be built here)
+            on the same pair on this box's host cores.
+Multi-GPU: independent pairs are sharded over ranks with no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 131072
+CACHE = os.path.join(tempfile.gettempdir(), "aicp_b200_bench_cache")
+
+
+def load_pair(trial, n_points=N_POINTS):
+    from aicp_mapping_b200 import synth
+    os.makedirs(CACHE, exist_ok=True)
+    path = os.path.join(CACHE, "c3_t%d_n%d.npz" % (trial, n_points))
+    if os.path.exists(path):
+        z = np.load(path)
+        return dict(ref=z["ref"], read=z["read"], ref_origin=z["ref_origin"], read_origin=z["read_origin"])
+    p = synth.make_pair(3, trial, n_points)
+    tmp = path + ".%d.tmp.npz" % os.getpid()
+    np.savez(tmp, ref=p["ref"], read=p["read"], ref_origin=p["ref_origin"], read_origin=p["read_origin"])
+    os.replace(tmp, path)
+    return p
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_oracle(pair, ratio, threads, reading_normals, repeats):
+    from oracle import oracle as orc
+    cfg = orc.default_config(ratio=ratio, threads=threads, reading_normals=reading_normals, use_kdtree=1)
+    times, iters = [], 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = orc.icp(pair["ref"], pair["read"], cfg, want_reading=True)
+        times.append(time.perf_counter() - t0)
+        iters = out.iterations
+        if out.rc != 0:
+            raise RuntimeError("oracle failed: " + out.error)
+    return float(np.median(times)), iters
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  libpointmatcher/libnabo/octomap cannot be built in
+    this image (no Eigen/PCL/yaml-cpp either), so this times the oracle port with every host thread it can use."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    pair = load_pair(0)
+    ov, _ = orc.overlap(pair["ref"], pair["ref_origin"], pair["read"], pair["read_origin"])
+    ratio, _ = orc.autotune_ratio(float(ov))
+    ratio = float(ratio)
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        time_oracle(pair, ratio, cores, 1, 1)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    sec, iters = time_oracle(pair, ratio, cores, 1, steps)
+    value = 1.0 / sec
+    sample = "%d registration(s) of C3 pair trial 0 (131072 x 131072 pts, ratio %.6f, %d ICP iterations), kd-tree oracle incl. the reading SurfaceNormal filter, OpenMP over queries" % (steps, ratio, iters)
+    line = {"impl": "reference", "metric": "ICP registrations/sec (128k pts)", "value": value, "unit": "registrations/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1, "n/a (CPU)"),
+            "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(pairs, l2):
+    return {"workload": "C3: Velodyne HDL-64 KITTI-shaped synthetic clouds, ground removed, 131072 reading x 131072 reference points, "
+                        "point-to-plane ICP chain of icp_autotuned.yaml (knn 20 normals, exact 1-NN epsilon 0, trimmed ratio auto-tuned "
+                        "from the octree overlap, <=20 iterations, differential stop 0.001 rad / 0.01 m / 4)",
+            "pairs_per_gpu_per_step": pairs, "points_per_cloud": N_POINTS, "l2": l2, "parallelism": "independent pairs sharded over GPUs"}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import aicp_mapping_b200 as ab
+    from aicp_mapping_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    P = args.pairs
+    # distinct pairs per rank (weak scaling: every rank registers P pairs per step)
+    trials = [(rank * 2 + i) % 16 for i in range(min(P, 2))]
+    pairs = [load_pair(t) for t in trials]
+    reg = ab.B200Registration(device=local_rank)
+    ovl = ab.B200Overlap(device=local_rank)
+    reg.setProfiling(True)
+    dev, host, ratios = [], [], []
+    for p in pairs:
+        ovl.computeOverlap(p["ref"], p["read"], p["ref_origin"], p["read_origin"])
+        ratios.append(ab.autotune_ratio(float(ovl.getOverlap())))
+        r4, q4 = capi.to_xyzw(p["ref"]), capi.to_xyzw(p["read"])
+        dev.append((torch.from_numpy(r4).cuda(), torch.from_numpy(q4).cuda()))
+        hr, hq = torch.from_numpy(r4).pin_memory(), torch.from_numpy(q4).pin_memory()
+        host.append((hr, hq, hr.numpy(), hq.numpy()))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def one_step(use_host):
+        """P registrations; returns (device ms summed, per-stage sums, launches, iterations)."""
+        ms = 0.0
+        agg = dict(match=0.0, select=0.0, accumulate=0.0, index=0.0, normals=0.0, iters=0, launches=0)
+        for j in range(P):
+            k = j % len(pairs)
+            reg.setConfig(ratio=ratios[k])
+            flush.zero_()
+            torch.cuda.synchronize()
+            if use_host:
+                reg.registerClouds(host[k][2], host[k][3])
+            else:
+                reg.registerClouds(dev[k][0], dev[k][1])
+            s = reg.stats
+            ms += s.ms_total
+            agg["match"] += s.ms_match; agg["select"] += s.ms_select; agg["accumulate"] += s.ms_accumulate
+            agg["index"] += s.ms_index; agg["normals"] += s.ms_normals
+            agg["iters"] += s.iterations; agg["launches"] += s.gpu_launches
+        return ms, agg
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms, agg = 0.0, None
+    for _ in range(args.steps):
+        ms, a = one_step(False)
+        dev_ms += ms
+        agg = a if agg is None else {k: agg[k] + a[k] for k in agg}
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+
+    # e2e: host buffers through the plugin call, wall clock around the synchronous calls (copies inside)
+    for _ in range(min(args.warmup, 2)):
+        one_step(True)
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        for j in range(P):
+            k = j % len(pairs)
+            reg.setConfig(ratio=ratios[k])
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            T = reg.registerClouds(host[k][2], host[k][3])
+            e2e_s += time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    n_reg_total = world * P * args.steps
+    value = n_reg_total / (dev_ms_max * 1e-3)
+    e2e_value = n_reg_total / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        iters_total = agg["iters"]
+        n_launch_match = iters_total                                   # k_match launches that did work
+        match_ms = agg["match"] / max(1, n_launch_match)
+        alg_match = 24.0 * N_POINTS                                    # read point 16 + write pos 4 + d2 4
+        achieved = alg_match / (match_ms * 1e-3) / 1e9
+        I = iters_total / (P * args.steps)
+        b_reg = 72.0 * N_POINTS + I * 84.0 * N_POINTS + 32.0 * N_POINTS
+        reg_ms = dev_ms / (P * args.steps)
+        line = {"metric": "ICP registrations/sec (128k pts)", "value": value, "unit": "registrations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(P, "flushed before every registration (256 MiB write)"),
+                "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_match, "avg_launch_ms": match_ms,
+                             "launches_timed": n_launch_match},
+                "roofline_registration": {"algorithmic_bytes": b_reg, "iterations_mean": I, "ms": reg_ms,
+                                          "achieved": b_reg / (reg_ms * 1e-3) / 1e9, "frac": b_reg / (reg_ms * 1e-3) / 1e9 / peak,
+                                          "unit": "GB/s"},
+                "stage_ms_per_registration": {k: agg[k] / (P * args.steps) for k in ("index", "normals", "match", "select", "accumulate")},
+                "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(P * 2 * N_POINTS * 16),
+                        "d2h_bytes_per_step": int(P * 64)},
+                "gpu_launches": int(agg["launches"]), "clocks": clocks, "wall_s": wall_s, "ratios": ratios}
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            sec_all, it_all = time_oracle(pairs[0], ratios[0], cores, 1, 3)
+            sec_one, _ = time_oracle(pairs[0], ratios[0], 1, 1, 1)
+            sec_lean, _ = time_oracle(pairs[0], ratios[0], cores, 0, 1)
+            line["cpu_baseline"] = {"value": 1.0 / sec_all, "unit": "registrations/s", "cores": cores, "kind": "port",
+                                    "sample": "3 registrations of C3 pair trial %d (131072 x 131072 pts, %d iterations) with the kd-tree "
+                                              "oracle incl. the reading SurfaceNormal filter, OpenMP over queries on all cores; "
+                                              "median" % (trials[0], it_all),
+                                    "value_1thread": 1.0 / sec_one, "value_without_reading_normals": 1.0 / sec_lean}
+        print(json.dumps(line), flush=True)
+    reg.close(); ovl.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=4, help="cloud pairs registered per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

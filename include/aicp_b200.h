@@ -1,0 +1,184 @@
+/*
+ * aicp_b200.h -- C ABI of libaicp_b200.so: the B200-native (sm_100a) replacement for AICP's registration hot path.
+ *
+ * Every entry point states the reference interface it replaces (paths relative to zbqq/aicp_mapping).
+ * The reference has no FFI of its own for this path (it is C++ calling libpointmatcher / octomap in-process), so the
+ * binding a maintainer adds is the C++ adapter in include/aicp_b200_adapter.hpp (B200Registration : AbstractRegistrator,
+ * B200Overlap : AbstractOverlapper) -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - points: `n` records of 4 floats (x, y, z, pad), 16-byte stride == sizeof(pcl::PointXYZ); pad is ignored on input
+ *     (aicp_core/src/utils/cloudIO.cpp:81-98 writes pad = 1 into the DataPoints feature matrix).
+ *   - transforms: 16 floats, column-major 4x4 == Eigen::Matrix4f::data().
+ *   - every pointer argument may be a host pointer or a device pointer of the handle's device; the library detects
+ *     which (cudaPointerGetAttributes).  Host buffers are copied through the handle's stream.
+ *   - all functions return AICP_B200_OK (0) or an error code; aicp_b200_last_error() gives the text.  Nothing here
+ *     calls exit() (the reference does: pointmatcher_registration.cpp:60-64,96-100).
+ *   - a handle is used by one thread at a time (same contract as the reference: app.cpp:528-550).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with AICP_B200_ERR_CUDA.
+ */
+#ifndef AICP_B200_H_
+#define AICP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AICP_B200_MAX_ITERS 256
+
+enum {
+  AICP_B200_OK = 0,
+  AICP_B200_ERR_BAD_ARG = 1,
+  AICP_B200_ERR_KNN_TOO_LARGE = 2,    /* SurfaceNormalDataPointsFilter needs knn < number of points */
+  AICP_B200_ERR_NO_VALID_MATCH = 3,   /* libpointmatcher ConvergenceError: no finite positive distance to trim */
+  AICP_B200_ERR_NAN = 4,              /* libpointmatcher ConvergenceError: NaN in the transformation */
+  AICP_B200_ERR_NONFINITE_INPUT = 5,
+  AICP_B200_ERR_EXTENT = 6,           /* |coordinate| > 1024 m in the reference-centred frame */
+  AICP_B200_ERR_CONFIG = 7,           /* unreadable / unsupported libpointmatcher YAML */
+  AICP_B200_ERR_CUDA = 8,
+  AICP_B200_ERR_COMM = 9
+};
+
+enum { AICP_B200_STOP_NONE = 0, AICP_B200_STOP_COUNTER = 1, AICP_B200_STOP_DIFFERENTIAL = 2 };
+
+typedef struct aicp_b200_handle aicp_b200_handle;
+
+/* The libpointmatcher chain parameters of aicp_core/config/icp/icp_autotuned.yaml:9-58 that the path uses. */
+typedef struct {
+  int32_t knn_normals;        /* referenceDataPointsFilters / SurfaceNormalDataPointsFilter.knn        (20) */
+  int32_t reading_normals;    /* 1: also run the reading SurfaceNormal filter (results unused by PointToPlane) (0) */
+  float   ratio;              /* outlierFilters / TrimmedDistOutlierFilter.ratio                       (0.70) */
+  int32_t max_iterations;     /* CounterTransformationChecker.maxIterationCount                        (20) */
+  float   min_diff_rot;       /* DifferentialTransformationChecker.minDiffRotErr                       (0.001) */
+  float   min_diff_trans;     /* DifferentialTransformationChecker.minDiffTransErr                     (0.01) */
+  int32_t smooth_length;      /* DifferentialTransformationChecker.smoothLength                        (4) */
+  float   matcher_epsilon;    /* KDTreeMatcher.epsilon as written in the file; the search is always exact (epsilon 0) */
+} aicp_b200_icp_config;
+
+typedef struct {
+  float   T_iter[16];         /* accumulated iteration transform in the reference-centred frame */
+  float   limit_d2;           /* trimmed squared-distance threshold of this iteration */
+  int64_t n_valid;            /* matches with finite, positive distance */
+  int64_t n_used;             /* matches with weight 1 */
+  double  rot_err, trans_err; /* DifferentialTransformationChecker means (NaN while the history is too short) */
+} aicp_b200_iter_trace;
+
+typedef struct {
+  int32_t iterations;
+  int32_t stop_reason;
+  float   weighted_point_used_ratio;  /* icp_.errorMinimizer->getWeightedPointUsedRatio(), pointmatcher_registration.cpp:114 */
+  float   mean_ref[3];
+  int64_t n_ref, n_read;
+  float   ms_total;                   /* device time of the whole call (CUDA events, includes host<->device copies) */
+  float   ms_setup;                   /* index + normals + centring */
+  float   ms_iterations;              /* ICP loop */
+  int32_t gpu_launches;               /* kernels launched by this call */
+  /* filled only when aicp_b200_set_profiling(h, 1): CUDA-event time of each stage on the handle's stream, summed over
+   * the iterations that actually ran */
+  int32_t profiled;
+  float   ms_index, ms_normals;       /* setup: Morton index build, SurfaceNormal filter */
+  float   ms_match, ms_select, ms_accumulate;   /* loop: k_match, 2 x k_select, k_accumulate(+solve) */
+  aicp_b200_iter_trace trace[AICP_B200_MAX_ITERS];
+} aicp_b200_stats;
+
+/* ---- lifetime --------------------------------------------------------------------------------------------------
+ * replaces: aicp::create_registrator(params) / PointmatcherRegistration(params)
+ *           aicp_core/include/aicp_registration/registration.hpp:9-19, pointmatcher_registration.cpp:7-9
+ * icp_yaml_path: libpointmatcher chain file, or NULL/"" for the chain defaults above (the reference calls
+ * icp_.setDefault() in that case, pointmatcher_registration.cpp:51-55).  device: CUDA ordinal, or -1 for the current one. */
+int aicp_b200_create(const char* icp_yaml_path, int device, aicp_b200_handle** out);
+int aicp_b200_destroy(aicp_b200_handle* h);
+const char* aicp_b200_last_error(const aicp_b200_handle* h);   /* h may be NULL: error of the last failed create */
+const char* aicp_b200_version(void);
+
+/* ---- configuration ---------------------------------------------------------------------------------------------
+ * replaces: PointmatcherRegistration::updateConfigParams(path)  pointmatcher_registration.hpp:52-54
+ *           + applyConfig() -> icp_.loadFromYaml()               pointmatcher_registration.cpp:48-68
+ * The file is only remembered here and re-read at the start of every aicp_b200_register call, because
+ * App::computeRegistration rewrites it before each registration (app.cpp:204-205, fileIO.cpp:179-214). */
+int aicp_b200_set_config(aicp_b200_handle* h, const char* icp_yaml_path);
+/* programmatic override (clears the path); used by the tests and the batched sweep */
+int aicp_b200_set_config_struct(aicp_b200_handle* h, const aicp_b200_icp_config* cfg);
+/* effective configuration (parses the remembered file now) */
+int aicp_b200_get_config(aicp_b200_handle* h, aicp_b200_icp_config* cfg);
+/* parse a libpointmatcher chain file without a handle (no CUDA needed) */
+int aicp_b200_parse_icp_yaml(const char* icp_yaml_path, aicp_b200_icp_config* cfg, char* err, int err_len);
+
+/* ---- registration ----------------------------------------------------------------------------------------------
+ * replaces: PointmatcherRegistration::registerClouds(cloud_ref, cloud_read, final_transform)
+ *           pointmatcher_registration.cpp:14-23,92-151   (T = icp_(reading, reference, init))
+ * init_T: NULL for identity, else the initial guess that applyInitialization() would build (:71-89).
+ * out_T: T such that T * reading aligns with the reference ("initialization is already included", :133).
+ * stats: nullable. */
+int aicp_b200_register(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref, const float* read_xyzw,
+                       int64_t n_read, const float* init_T, float* out_T, aicp_b200_stats* stats);
+
+/* Fixed-map localisation (BASELINE.json config 4; App with localize_against_prior_map, app.cpp:41-69,123-127):
+ * build the reference index + normals once, then register many readings against it. */
+int aicp_b200_set_reference(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref);
+int aicp_b200_register_to_reference(aicp_b200_handle* h, const float* read_xyzw, int64_t n_read, const float* init_T,
+                                    float* out_T, aicp_b200_stats* stats);
+
+/* replaces: getOutputReading(out)        pointmatcher_registration.hpp:48-50  (T * reading, unfiltered)
+ *           getInitializedReading(out)   pointmatcher_registration.hpp:37-46  (init_T * reading) */
+int aicp_b200_get_output_reading(aicp_b200_handle* h, float* xyzw, int64_t n);
+int aicp_b200_get_initialized_reading(aicp_b200_handle* h, float* xyzw, int64_t n);
+
+/* descriptors of the filtered reference of the last registration, original point order:
+ * normals_xyzd = (nx, ny, nz, density) -- SurfaceNormalDataPointsFilter keepNormals / keepDensities */
+int aicp_b200_get_reference_normals(aicp_b200_handle* h, float* normals_xyzd, int64_t n);
+
+/* parity instrumentation: when enabled the next registrations record the correspondence (original reference index)
+ * of every reading point at every iteration; fetch with get_trace_matches (iters x n_read int32, row per iteration) */
+int aicp_b200_enable_match_trace(aicp_b200_handle* h, int enable);
+/* measurement instrumentation: record CUDA events around every stage of the next registrations (see aicp_b200_stats) */
+int aicp_b200_set_profiling(aicp_b200_handle* h, int enable);
+int aicp_b200_get_trace_matches(aicp_b200_handle* h, int32_t* idx, int64_t iters, int64_t n_read);
+
+/* ---- stage entry points (same kernels as aicp_b200_register; exposed for the parity tests) -----------------------
+ * SurfaceNormalDataPointsFilter alone: out_normals n x 4, out_knn nullable n x knn (ids sorted by (d2, id)) */
+int aicp_b200_surface_normals(aicp_b200_handle* h, const float* xyzw, int64_t n, int32_t knn, float* out_normals,
+                              int32_t* out_knn);
+/* KDTreeMatcher{knn 1, epsilon 0}::findClosests: out_idx[i] = argmin_j (d2(q_i, ref_j), j), out_d2 = squared distance */
+int aicp_b200_match(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref, const float* qry_xyzw, int64_t n_qry,
+                    int32_t* out_idx, float* out_d2);
+/* TrimmedDistOutlierFilter threshold: k-th smallest finite positive d2, k = size_t(float(n_valid) * ratio) */
+int aicp_b200_trim_threshold(aicp_b200_handle* h, const float* d2, int64_t n, float ratio, float* out_limit,
+                             int64_t* out_n_valid);
+
+/* ---- overlap ---------------------------------------------------------------------------------------------------
+ * replaces: OctreesOverlap::computeOverlap(ref_cloud, read_cloud, ref_pose, read_pose, reading_tree) + getOverlap()
+ *           aicp_core/src/overlap/octrees_overlap.cpp:29-72 (createTree :153-218, getOverlappingNodes :113-151)
+ * origins: translation of the two sensor poses (only the translation is used as ray origin, :229-230).
+ * resolution: OverlapParams.octree_based.octomapResolution, i.e. (double)0.2f with the shipped config.
+ * counts: nullable, {|A^B|, |A|, |B|} voxel-key counts.  overlap_pct in [0,100]. */
+int aicp_b200_overlap(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref, const double ref_origin[3],
+                      const float* read_xyzw, int64_t n_read, const double read_origin[3], double resolution,
+                      float* overlap_pct, int64_t counts[3]);
+
+/* ---- auto-tune glue --------------------------------------------------------------------------------------------
+ * replaces (for callers that do not go through a file): App::computeRegistration's clamp, app.cpp:198-202, followed by
+ * the 6-significant-digit text round trip of replaceRatioConfigFile, fileIO.cpp:194-198.  Pure host code. */
+float aicp_b200_autotune_ratio(float overlap_pct);
+
+/* ---- batched registration (BASELINE.json config 5: independent pairs, no communication) --------------------------
+ * pairs share one configuration; ref/read arrays hold n_pairs pointers; out_T: n_pairs x 16; stats nullable array. */
+int aicp_b200_register_batch(aicp_b200_handle* h, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                             const float* const* read_xyzw, const int64_t* n_read, const float* ratios /*nullable*/,
+                             float* out_T, aicp_b200_stats* stats /*nullable, n_pairs*/);
+
+/* ---- multi-GPU single registration (BASELINE.json config 4: reading sharded, reference replicated) ---------------
+ * nccl_unique_id: the 128-byte ncclUniqueId obtained on rank 0 with aicp_b200_comm_unique_id and broadcast by the
+ * caller (e.g. torch.distributed).  After comm_init, aicp_b200_register* calls on every rank take that rank's SHARD of
+ * the reading; the trimmed quantile and the 6x6 normal equations are all-reduced over NCCL every iteration and every
+ * rank returns the same transform. */
+int aicp_b200_comm_unique_id(uint8_t id_out[128]);
+int aicp_b200_comm_init(aicp_b200_handle* h, const uint8_t nccl_unique_id[128], int rank, int n_ranks);
+int aicp_b200_comm_destroy(aicp_b200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

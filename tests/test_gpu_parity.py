@@ -1,0 +1,270 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libaicp_b200.so), against the CPU oracle on
+the same seeded inputs.  Bars (BASELINE.json north_star): correspondence indices bit-exact, final transforms within
+1e-5 m and 1e-5 rad, overlap within 1e-4.  By construction (exact integer reductions, float64 solve from + - * / sqrt)
+the whole trajectory is expected to be bit-identical, and the tests assert that too."""
+import os
+
+import numpy as np
+import pytest
+
+import aicp_mapping_b200 as ab
+from aicp_mapping_b200 import capi, synth
+from conftest import rot_angle
+
+pytestmark = pytest.mark.gpu
+
+TOL_M = 1e-5      # metres, BASELINE.json
+TOL_RAD = 1e-5    # radians, BASELINE.json
+NCPU = os.cpu_count() or 1
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def reg():
+    r = ab.B200Registration()
+    yield r
+    r.close()
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_transform_close(T_gpu, T_orc):
+    d = T_gpu.astype(np.float64) @ np.linalg.inv(T_orc.astype(np.float64))
+    assert np.linalg.norm(d[:3, 3]) <= TOL_M, "translation differs by %g m" % np.linalg.norm(d[:3, 3])
+    assert rot_angle(d[:3, :3]) <= TOL_RAD, "rotation differs by %g rad" % rot_angle(d[:3, :3])
+
+
+# ---- exact NN ------------------------------------------------------------------------------------------------------
+def test_match_bit_exact_random_lattice_duplicates(reg, orc):
+    rng = np.random.default_rng(11)
+    ref = rng.uniform(-5, 5, (5000, 3)).astype(np.float32)
+    ref[100:200] = ref[0:100]                       # duplicates: ties must go to the lowest ORIGINAL index
+    ref = np.round(ref * 4) / 4                     # lattice: many equidistant candidates
+    qry = np.round(rng.uniform(-6, 6, (4000, 3)).astype(np.float32) * 8) / 8
+    gi, gd = reg.match(ref, qry)
+    oi, od = orc.match(ref, qry, use_kdtree=False)
+    assert np.array_equal(gi, oi) and np.array_equal(u32(gd), u32(od))
+
+
+@pytest.mark.parametrize("n_ref,n_qry", [(1, 5), (7, 3), (8, 8), (9, 100), (1000, 1), (4097, 513)])
+def test_match_ragged_sizes(reg, orc, n_ref, n_qry):
+    rng = np.random.default_rng(100 + n_ref)
+    ref = rng.normal(0, 3, (n_ref, 3)).astype(np.float32)
+    qry = rng.normal(0, 4, (n_qry, 3)).astype(np.float32)
+    gi, gd = reg.match(ref, qry)
+    oi, od = orc.match(ref, qry, use_kdtree=False)
+    assert np.array_equal(gi, oi) and np.array_equal(u32(gd), u32(od))
+
+
+def test_match_bit_exact_full_size_lidar(reg, orc, pair_cache):
+    pair = pair_cache(3, 0)                         # 131 072 x 131 072, the headline workload
+    gi, gd = reg.match(pair["ref"], pair["read"])
+    oi, od = orc.match(pair["ref"], pair["read"], use_kdtree=True, threads=NCPU)
+    assert np.array_equal(gi, oi) and np.array_equal(u32(gd), u32(od))
+    # size-independent property: every reference point is its own nearest neighbour at distance 0
+    si, sd = reg.match(pair["ref"], pair["ref"])
+    dup = sd != 0
+    assert not dup.any()
+    same = si == np.arange(len(si))
+    assert np.array_equal(pair["ref"][si[~same]], pair["ref"][~same])      # only exact duplicates map elsewhere (lower id)
+    assert np.all(si[~same] < np.flatnonzero(~same))
+
+
+# ---- normals ---------------------------------------------------------------------------------------------------------
+def test_surface_normals_parity_small_and_degenerate(reg, orc):
+    rng = np.random.default_rng(12)
+    pts = rng.uniform(-2, 2, (3000, 3)).astype(np.float32)
+    pts[:, 2] = (0.3 * pts[:, 0] - 0.2 * pts[:, 1] + 0.01 * rng.normal(size=3000)).astype(np.float32)
+    pts[500:520] = pts[0:20]                        # duplicates inside neighbourhoods
+    gn, gk = reg.surfaceNormals(pts, 20)
+    on, ok = orc.surface_normals(pts, 20, use_kdtree=False)
+    assert np.array_equal(gk, ok)
+    assert np.array_equal(u32(gn), u32(on))
+    t = np.linspace(0, 1, 200, dtype=np.float32)
+    line = np.c_[t, 2 * t, -t].astype(np.float32)   # collinear neighbourhoods -> (0,1,0), SURVEY.md A.2
+    gn, _ = reg.surfaceNormals(line, 10)
+    on, _ = orc.surface_normals(line, 10)
+    assert np.array_equal(u32(gn), u32(on)) and np.array_equal(gn[:, :3], np.tile(np.float32([0, 1, 0]), (200, 1)))
+    with pytest.raises(capi.AicpError, match="KNN_TOO_LARGE"):
+        reg.surfaceNormals(pts[:20], 20)
+
+
+def test_surface_normals_parity_full_size(reg, orc, pair_cache):
+    pair = pair_cache(3, 0)
+    gn, gk = reg.surfaceNormals(pair["ref"], 20)
+    on, ok = orc.surface_normals(pair["ref"], 20, use_kdtree=True, threads=NCPU)
+    assert np.array_equal(gk, ok)
+    assert np.array_equal(u32(gn), u32(on))
+
+
+# ---- trimmed quantile --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ratio", [0.25, 0.358818, 0.5, 0.7, 0.999, 1.0])
+def test_trim_threshold_parity(reg, orc, ratio):
+    rng = np.random.default_rng(13)
+    d2 = rng.exponential(0.3, 200001).astype(np.float32) ** 2
+    d2[:50] = 0.0
+    d2[50:60] = np.inf
+    d2[1000:3000] = d2[999]                         # a heavy tie inside the distribution
+    gl, gn = reg.trimThreshold(d2, ratio)
+    ol, on = orc.trim_threshold(d2, ratio)
+    assert gn == on and u32([gl])[0] == u32([ol])[0]
+
+
+def test_trim_threshold_edge_cases(reg, orc):
+    assert reg.trimThreshold(np.float32([3.0]), 0.7) == orc.trim_threshold(np.float32([3.0]), 0.7)
+    with pytest.raises(capi.AicpError, match="NO_VALID_MATCH"):
+        reg.trimThreshold(np.zeros(100, dtype=np.float32), 0.5)
+    tiny = np.float32([1e-45, 1e-38, 3e38, 1.0, 2.0])       # denormals and huge values order like their bit patterns
+    for r in (0.3, 0.5, 0.9, 1.0):
+        assert reg.trimThreshold(tiny, r) == orc.trim_threshold(tiny, r)
+
+
+# ---- full chain ------------------------------------------------------------------------------------------------------
+def run_both(reg, orc, ref, read, ratio=0.7, init=None, threads=NCPU, **kw):
+    reg.setConfig(ratio=ratio, **kw)
+    reg.enableMatchTrace(True)
+    T = reg.registerClouds(ref, read) if init is None else reg.registerCloudsInit(ref, read, init)
+    cfg = orc.default_config(ratio=ratio, threads=threads, **kw)
+    o = orc.icp(ref, read, cfg, init_T=init, want_trace_idx=True, want_normals=True)
+    assert o.rc == 0
+    return T, o
+
+
+def assert_full_parity(reg, T, o):
+    st = reg.stats
+    assert st.iterations == o.iterations and st.stop_reason == o.stop_reason
+    assert_transform_close(T, o.T)
+    # correspondences of EVERY iteration are bit-exact
+    assert np.array_equal(reg.getTraceMatches(), o.trace_idx)
+    tr = reg.trace()
+    for g, c in zip(tr, o.trace):
+        assert g["n_valid"] == c["n_valid"] and g["n_used"] == c["n_used"]
+        assert u32([g["limit_d2"]])[0] == u32([c["limit_d2"]])[0]
+        assert np.array_equal(u32(g["T_iter"]), u32(c["T_iter"]))
+    assert np.array_equal(u32(T), u32(o.T))                               # by construction: bit-identical
+    assert np.array_equal(u32(reg.getOutputReading()), u32(o.reading))    # pointmatcher_registration.cpp:128-131
+    assert np.float32(reg.getWeightedPointUsedRatio()) == o.weighted_point_used_ratio
+    assert np.array_equal(u32(reg.getReferenceNormals()), u32(o.normals))
+
+
+@pytest.mark.parametrize("trial,ratio", [(0, 0.7), (1, 0.25), (2, 0.358818)])
+def test_icp_parity_cube_pairs(reg, orc, trial, ratio):
+    pair = synth.make_pair(5, trial)
+    T, o = run_both(reg, orc, pair["ref"], pair["read"], ratio)
+    assert_full_parity(reg, T, o)
+    err = T.astype(np.float64) @ np.linalg.inv(pair["T_true"])
+    assert np.linalg.norm(err[:3, 3]) < 5e-3 and rot_angle(err[:3, :3]) < 2e-3      # and it actually registers
+
+
+def test_icp_parity_c1_sample_scans(reg, orc):
+    for reading in (1, 2):
+        pair = synth.c1_pair(reading)
+        T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.7)
+        assert_full_parity(reg, T, o)
+
+
+def test_icp_parity_c2_vlp16(reg, orc, pair_cache):
+    pair = pair_cache(2, 0)
+    T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.7)
+    assert_full_parity(reg, T, o)
+
+
+def test_icp_parity_c3_hdl64_full_size(reg, orc, pair_cache):
+    pair = pair_cache(3, 0)
+    T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.7)
+    assert_full_parity(reg, T, o)
+    # second trial, auto-tuned ratio from the GPU overlap
+    pair = pair_cache(3, 1, 65536)
+    ov = ab.B200Overlap()
+    ov.computeOverlap(pair["ref"], pair["read"], pair["ref_origin"], pair["read_origin"])
+    ratio = ab.autotune_ratio(float(ov.getOverlap()))
+    T, o = run_both(reg, orc, pair["ref"], pair["read"], ratio)
+    assert_full_parity(reg, T, o)
+    ov.close()
+
+
+def test_icp_counter_stop_and_init_transform(reg, orc):
+    pair = synth.make_pair(5, 4, 6000)
+    T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.6, max_iterations=3)
+    assert reg.stats.iterations == 3 and reg.stats.stop_reason == capi.STOP_COUNTER
+    assert_full_parity(reg, T, o)
+    init = synth.rigid(0.02, -0.01, 0.0, 0, 0, 0.01).astype(np.float32)
+    T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.6, init=init, max_iterations=20)
+    assert_full_parity(reg, T, o)
+    assert np.array_equal(u32(reg.getInitializedReading()), u32(orc.transform_points(init, pair["read"])))
+
+
+def test_icp_through_yaml_file_like_app(reg, orc, tmp_path):
+    """App::computeRegistration path: clamp -> rewrite YAML -> updateConfigParams -> registerClouds (app.cpp:187-216)."""
+    pair = synth.make_pair(5, 5, 8000)
+    cfg_file = str(tmp_path / "icp_autotuned.yaml")
+    T = ab.computeRegistration(reg, pair["ref"], pair["read"], 35.8818, os.path.join(GOLDEN, "icp_autotuned_default.yaml"), cfg_file)
+    got = reg.getConfig()
+    assert got.ratio == np.float32(0.358818) and got.knn_normals == 20 and got.max_iterations == 20
+    o = orc.icp(pair["ref"], pair["read"], orc.default_config(ratio=float(np.float32(0.358818)), threads=NCPU))
+    assert reg.stats.iterations == o.iterations and np.array_equal(u32(T), u32(o.T))
+    reg.updateConfigParams(os.path.join(GOLDEN, "icp_3D_cfg_trimmed.yaml"))
+    with pytest.raises(capi.AicpError, match="CONFIG"):
+        reg.registerClouds(pair["ref"], pair["read"])
+    reg.updateConfigParams("")
+
+
+def test_icp_error_statuses_match_oracle(reg, orc):
+    pair = synth.make_pair(5, 6, 3000)
+    reg.setConfig(ratio=0.7, max_iterations=20)
+    with pytest.raises(capi.AicpError, match="NO_VALID_MATCH"):             # identical clouds: every distance is zero
+        reg.registerClouds(pair["ref"], pair["ref"])
+    assert orc.icp(pair["ref"], pair["ref"], orc.default_config()).error == "NO_VALID_MATCH"
+    bad = pair["read"].copy(); bad[17, 1] = np.nan
+    with pytest.raises(capi.AicpError, match="NONFINITE_INPUT"):
+        reg.registerClouds(pair["ref"], bad)
+    far = pair["read"].copy(); far[:, 0] += 5000.0
+    with pytest.raises(capi.AicpError, match="EXTENT"):
+        reg.registerClouds(pair["ref"], far)
+    assert orc.icp(pair["ref"], far, orc.default_config()).error == "EXTENT"
+    with pytest.raises(capi.AicpError, match="KNN_TOO_LARGE"):
+        reg.registerClouds(pair["ref"][:15], pair["read"])
+    T = reg.registerClouds(pair["ref"], pair["read"])                        # the handle still works afterwards
+    assert np.all(np.isfinite(T))
+
+
+def test_fixed_reference_reuse(reg, orc):
+    """aicp_b200_set_reference + register_to_reference give the same result as a full registerClouds."""
+    pair = synth.make_pair(5, 7, 9000)
+    reg.setConfig(ratio=0.6, max_iterations=20)
+    T_full = reg.registerClouds(pair["ref"], pair["read"])
+    reg.setReference(pair["ref"])
+    T_a = reg.registerToReference(pair["read"])
+    T_b = reg.registerToReference(pair["read"])
+    assert np.array_equal(u32(T_full), u32(T_a)) and np.array_equal(u32(T_a), u32(T_b))
+
+
+def test_device_pointers_are_used_in_place(reg, orc):
+    import torch
+    pair = synth.make_pair(5, 8, 5000)
+    reg.setConfig(ratio=0.7, max_iterations=20)
+    T_host = reg.registerClouds(pair["ref"], pair["read"])
+    ref_d = torch.from_numpy(capi.to_xyzw(pair["ref"])).cuda()
+    read_d = torch.from_numpy(capi.to_xyzw(pair["read"])).cuda()
+    T_dev = reg.registerClouds(ref_d, read_d)
+    assert np.array_equal(u32(T_host), u32(T_dev))
+
+
+# ---- overlap -------------------------------------------------------------------------------------------------------
+def test_overlap_parity(orc, pair_cache):
+    ov = ab.B200Overlap()
+    cases = [pair_cache(2, 0, 8192), pair_cache(3, 1, 65536), synth.make_pair(5, 0)]
+    for pair in cases:
+        counts = ov.computeOverlap(pair["ref"], pair["read"], pair["ref_origin"], pair["read_origin"])
+        o_ov, o_counts = orc.overlap(pair["ref"], pair["ref_origin"], pair["read"], pair["read_origin"])
+        assert counts == o_counts, pair["name"]
+        assert abs(float(ov.getOverlap()) - float(o_ov)) <= 1e-4 and u32([ov.getOverlap()])[0] == u32([o_ov])[0]
+    # identical clouds -> 100 %, disjoint -> 0 %
+    a = cases[0]["ref"]
+    ov.computeOverlap(a, a, [0, 0, 0.6], [0, 0, 0.6])
+    assert ov.getOverlap() == np.float32(100.0)
+    ov.computeOverlap(a, a + np.float32(500.0), [0, 0, 0.6], [500, 500, 500.6])
+    assert ov.getOverlap() == 0.0 and ov.counts[0] == 0
+    ov.close()
