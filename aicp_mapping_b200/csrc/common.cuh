@@ -55,6 +55,8 @@ struct DeviceState {
   // checkers
   double quat_hist[AICP_B200_MAX_ITERS + 1][4];
   double tr_hist[AICP_B200_MAX_ITERS + 1][3];
+  double ang_step[AICP_B200_MAX_ITERS + 1];   // |angularDistance(q_i, q_{i-1})|, cached so each iteration computes one
+  double trn_step[AICP_B200_MAX_ITERS + 1];   // ||t_i - t_{i-1}||
   aicp_b200_iter_trace trace[AICP_B200_MAX_ITERS];
 };
 

@@ -6,7 +6,8 @@
 // library is built with -fmad=false, so no step depends on CUDA's transcendental approximations.
 //
 // Algorithms (libpointmatcher behaviour per SURVEY.md Appendix A.5 / A.7):
-//   sincos : Cody-Waite reduction by pi/2 (33-bit head + tail), 11-term forward Taylor sums
+//   sincos : Cody-Waite reduction by pi/2 (33-bit head + tail), forward Taylor sums (<= 11 terms, stop when a term no
+//            longer changes the sum; factorial ratios applied as reciprocal multiplications)
 //   atan2  : three half-angle reductions + 11-term alternating series, first quadrant only
 //   jacobi : cyclic Jacobi eigen-decomposition of a symmetric NxN matrix
 //   solve6 : LLT with a relative pivot test standing in for fullPivHouseholderQr(A).isInvertible(); minimal-norm
@@ -25,18 +26,22 @@ __device__ inline void det_sincos(double x, double* s, double* c) {
   double r = (x - kd * pio2_hi) - kd * pio2_lo;
   double r2 = r * r;
   double term = r, ss = r;
+  for (int n = 1; n <= 11; ++n) {
+    double inv = 1.0 / (double)((2 * n) * (2 * n + 1));
+    term = (term * r2) * inv;
+    term = -term;
+    double ns = ss + term;
+    if (ns == ss) break;
+    ss = ns;
+  }
   double cterm = 1.0, cc = 1.0;
   for (int n = 1; n <= 11; ++n) {
-    double den_s = (double)((2 * n) * (2 * n + 1));
-    term = (term * r2) / den_s;
-    term = -term;
-    ss = ss + term;
-  }
-  for (int n = 1; n <= 11; ++n) {
-    double den_c = (double)((2 * n - 1) * (2 * n));
-    cterm = (cterm * r2) / den_c;
+    double inv = 1.0 / (double)((2 * n - 1) * (2 * n));
+    cterm = (cterm * r2) * inv;
     cterm = -cterm;
-    cc = cc + cterm;
+    double nc = cc + cterm;
+    if (nc == cc) break;
+    cc = nc;
   }
   long long k = (long long)kd;
   int quad = (int)(((k % 4) + 4) % 4);
@@ -51,9 +56,12 @@ __device__ inline double det_atan01(double z) {
   for (int h = 0; h < 3; ++h) u = u / (1.0 + sqrt(1.0 + u * u));
   double u2 = u * u, p = u, sum = u;
   for (int n = 1; n <= 11; ++n) {
+    double inv = 1.0 / (double)(2 * n + 1);
     p = p * u2;
     p = -p;
-    sum = sum + p / (double)(2 * n + 1);
+    double ns = sum + p * inv;
+    if (ns == sum) break;
+    sum = ns;
   }
   return 8.0 * sum;
 }

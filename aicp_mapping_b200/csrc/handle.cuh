@@ -71,12 +71,14 @@ struct Handle {
   DevBuf<float4> refc_pts;       // centred points, Morton order
   DevBuf<float4> refc_node;      // centred boxes
   DevBuf<float4> normals;        // Morton order (nx,ny,nz,density)
+  DevBuf<int> knn_pos;           // n x knn neighbour positions (Morton order), scratch of the normals filter
   int64_t n_ref = 0;
   bool ref_ready = false;
   int ref_knn = 0;
 
   // reading side
   DevBuf<float4> read_in, read0, read_out, read_init;
+  SpatialIndex read_ix;          // reading' in Morton order (.w = original reading index): coherent tree walks per warp
   DevBuf<int> match_pos;
   DevBuf<float> d2;
   DevBuf<unsigned int> hist;

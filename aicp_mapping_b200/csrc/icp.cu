@@ -168,7 +168,7 @@ __device__ __forceinline__ void hist_flush(const unsigned int* sh, unsigned int*
 }
 
 __global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __restrict__ read0, int n, DeviceState* st,
-                                               int* __restrict__ match_pos, float* __restrict__ d2out,
+                                               int* match_pos, float* __restrict__ d2out,
                                                unsigned int* hist, int* trace_idx, float ratio) {
   if (ld_int(&st->done)) return;
   __shared__ unsigned int sh[AICP_HIST_BINS];
@@ -181,10 +181,11 @@ __global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __res
     float4 r = __ldg(&read0[i]);
     float3 p = xform_f(sT, r.x, r.y, r.z);
     int pos; float d;
-    nn_search(ix, p.x, p.y, p.z, &pos, &d);
+    const int iter = st->iter;
+    nn_search(ix, p.x, p.y, p.z, &pos, &d, iter > 0 ? match_pos[i] : -1);
     match_pos[i] = pos;
     d2out[i] = d;
-    if (trace_idx) trace_idx[(size_t)st->iter * n + i] = __float_as_int(__ldg(&ix.pts[pos]).w);
+    if (trace_idx) trace_idx[(size_t)iter * n + __float_as_int(r.w)] = __float_as_int(__ldg(&ix.pts[pos]).w);
     if (d2_valid(d)) atomicAdd(&sh[__float_as_uint(d) >> 20], 1u);
   }
   __syncthreads();
@@ -227,7 +228,7 @@ __device__ __forceinline__ void atomic_add_128(unsigned long long* lo, long long
 }
 
 // A.5 solve + pose update, A.7 checkers; one thread
-__device__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read) {
+__device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read) {
   long long hi[AICP_NSUM];
   unsigned long long lo[AICP_NSUM];
   for (int i = 0; i < AICP_NSUM; ++i) {
@@ -258,15 +259,20 @@ __device__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read
   int hn = st->hist_n;
   det_quat_from_T(T, st->quat_hist[hn]);
   st->tr_hist[hn][0] = (double)T[12]; st->tr_hist[hn][1] = (double)T[13]; st->tr_hist[hn][2] = (double)T[14];
+  {
+    // the newest consecutive pair; older pairs were computed by earlier iterations (same values, same order of summation)
+    st->ang_step[hn] = det_quat_angular_distance(st->quat_hist[hn], st->quat_hist[hn - 1]);
+    double dx = st->tr_hist[hn][0] - st->tr_hist[hn - 1][0], dy = st->tr_hist[hn][1] - st->tr_hist[hn - 1][1],
+           dz = st->tr_hist[hn][2] - st->tr_hist[hn - 1][2];
+    st->trn_step[hn] = sqrt((dx * dx + dy * dy) + dz * dz);
+  }
   ++hn;
   st->hist_n = hn;
   if (hn > lp.smooth_length) {
     double re = 0.0, te = 0.0;
     for (int i = hn - 1; i >= hn - lp.smooth_length; --i) {
-      re = re + det_quat_angular_distance(st->quat_hist[i], st->quat_hist[i - 1]);
-      double dx = st->tr_hist[i][0] - st->tr_hist[i - 1][0], dy = st->tr_hist[i][1] - st->tr_hist[i - 1][1],
-             dz = st->tr_hist[i][2] - st->tr_hist[i - 1][2];
-      te = te + sqrt((dx * dx + dy * dy) + dz * dz);
+      re = re + st->ang_step[i];
+      te = te + st->trn_step[i];
     }
     re = re / (double)lp.smooth_length;
     te = te / (double)lp.smooth_length;
@@ -279,7 +285,7 @@ __device__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read
   if (!iterate) *(volatile int*)&st->done = 1;
 }
 
-__global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
+__global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
                                                     const float4* __restrict__ read0, const int* __restrict__ match_pos,
                                                     const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp) {
   if (ld_int(&st->done)) return;
@@ -488,6 +494,10 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   const int blocks = (n_read + 255) / 256;
   k_read_prepare<<<blocks, 256, 0, s>>>(h->read_in.p, n_read, h->st, h->read0.p, read_init);
   h->launches += 2;
+  // Morton-order the reading so that the 32 queries of a warp walk the same part of the reference tree
+  rc = build_index(h, h->read_ix, h->read0.p, n_read);
+  if (rc) return rc;
+  const float4* read_s = h->read_ix.pts.p;
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
 
   IndexView cix{h->refc_pts.p, h->refc_node.p, h->ref_ix.n, h->ref_ix.first_leaf};
@@ -495,12 +505,12 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
   for (int it = 0; it < cfg.max_iterations; ++it) {
     mark(3 + 4 * (size_t)it);
-    k_match<<<blocks, 256, 0, s>>>(cix, h->read0.p, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio);
+    k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio);
     mark(4 + 4 * (size_t)it);
     k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 2, cfg.ratio);
     k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 3, cfg.ratio);
     mark(5 + 4 * (size_t)it);
-    k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, h->read0.p, h->match_pos.p, h->d2.p, n_read, h->st, lp);
+    k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp);
     mark(6 + 4 * (size_t)it);
   }
   h->launches += 4 * cfg.max_iterations;

@@ -141,6 +141,7 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64)
   cudaStream_t s = h->stream;
   int leaves = (n + AICP_LEAF - 1) / AICP_LEAF;
   int first_leaf = next_pow2(leaves);
+  if (first_leaf < 4) first_leaf = 4;          // the warp k-NN walks 32-point chunks = nodes two levels above the leaves
   int n_pad = first_leaf * AICP_LEAF;
   if (!ix.meta) CUDA_TRY(cudaMalloc((void**)&ix.meta, sizeof(IndexMeta)));
   CUDA_TRY(ix.pts.reserve((size_t)n_pad));

@@ -5,38 +5,127 @@
 // included, ordered by (d2, index)), C = sum (p - mean)(p - mean)^T, normal = eigenvector of the smallest
 // eigenvalue, density = knn / (4/3 pi r_max^3).
 //
-// One thread per point, Morton order (neighbouring threads walk the same tree nodes, so the traversal is served by
-// L1/L2); the candidate list lives in shared memory, strided by thread; covariance and the 3x3 Jacobi eigen-solver run
-// in float64 registers in list order, which makes the result independent of the index shape.
+// Two kernels:
+//   k_knn_warp          one WARP per query point.  The sorted candidate list (32 entries, the first knn matter) lives
+//                       one entry per lane; candidates arrive 32 at a time as a coalesced 512-byte chunk of the
+//                       Morton-ordered cloud, each lane evaluates one, and accepted ones are inserted with a ballot +
+//                       shuffle-up (warp-shuffle top-k).  The walk over the index is warp-uniform: it descends the
+//                       implicit binary tree five levels at a time, the 32 lanes testing the 32 descendant boxes of a
+//                       node in one coalesced 1 KiB load, nearest box first, pruning against the current k-th distance.
+//   k_normals_from_knn  one THREAD per point: gathers the neighbours in list order and runs covariance + cyclic Jacobi
+//                       in float64 registers (sequential in list order, so the result does not depend on the index).
+// Algorithmic HBM bytes per point: 16 (query) + 4*knn (neighbour ids written) + 4*knn (read back) + 16 (normal written).
 #include "detmath.cuh"
 #include "handle.cuh"
 
 namespace aicp {
 
-__global__ void __launch_bounds__(128) k_surface_normals(IndexView ix, int k, float4* __restrict__ normals_morton,
-                                                         int* __restrict__ knn_out_orig) {
-  extern __shared__ unsigned char smem_raw[];
-  const int nt = blockDim.x;
-  float* s_d2 = reinterpret_cast<float*>(smem_raw);
-  int* s_id = reinterpret_cast<int*>(s_d2 + (size_t)k * nt);
-  int* s_pos = s_id + (size_t)k * nt;
-  int i = blockIdx.x * nt + threadIdx.x;
-  if (i >= ix.n) return;
-  KnnList L{s_d2 + threadIdx.x, s_id + threadIdx.x, s_pos + threadIdx.x, nt, k};
-  float4 q = __ldg(&ix.pts[i]);
-  knn_search(ix, q.x, q.y, q.z, L);
+struct WarpKnn {
+  float qx, qy, qz;
+  float ld;        // this lane's list entry: squared distance
+  int lid;         // original index
+  int lpos;        // position in the Morton-ordered array
+  float worst_d;   // entry k-1 (uniform)
+  int worst_id;
+  int k;
+  int own_chunk;
+  int lane;
+};
 
+__device__ __forceinline__ void warp_insert(WarpKnn& w, float cd, int cid, int cpos) {
+  bool less = cand_less(cd, cid, w.ld, w.lid);
+  unsigned m = __ballot_sync(0xFFFFFFFFu, less);
+  if (m == 0) return;
+  int p = __ffs(m) - 1;
+  float ud = __shfl_up_sync(0xFFFFFFFFu, w.ld, 1);
+  int uid = __shfl_up_sync(0xFFFFFFFFu, w.lid, 1);
+  int upos = __shfl_up_sync(0xFFFFFFFFu, w.lpos, 1);
+  if (w.lane > p) { w.ld = ud; w.lid = uid; w.lpos = upos; }
+  else if (w.lane == p) { w.ld = cd; w.lid = cid; w.lpos = cpos; }
+  w.worst_d = __shfl_sync(0xFFFFFFFFu, w.ld, w.k - 1);
+  w.worst_id = __shfl_sync(0xFFFFFFFFu, w.lid, w.k - 1);
+}
+
+// 32 consecutive Morton-ordered points: one candidate per lane
+__device__ __forceinline__ void scan_chunk(const IndexView& ix, WarpKnn& w, int chunk) {
+  int pos = chunk * 32 + w.lane;
+  float4 p = __ldg(&ix.pts[pos]);
+  int id = __float_as_int(p.w);
+  float d = d2_f(w.qx, w.qy, w.qz, p.x, p.y, p.z);
+  unsigned m = __ballot_sync(0xFFFFFFFFu, id != 0x7FFFFFFF && cand_less(d, id, w.worst_d, w.worst_id));
+  while (m) {
+    int b = __ffs(m) - 1;
+    m &= m - 1;
+    float cd = __shfl_sync(0xFFFFFFFFu, d, b);
+    int cid = __shfl_sync(0xFFFFFFFFu, id, b);
+    if (cand_less(cd, cid, w.worst_d, w.worst_id)) warp_insert(w, cd, cid, chunk * 32 + b);
+  }
+}
+
+// node at depth `depth`; chunk_depth = depth of the nodes that cover exactly 32 points (two levels above the leaves)
+template <int LEVEL>
+__device__ void knn_visit(const IndexView& ix, WarpKnn& w, int node, int depth, int chunk_depth) {
+  if (depth == chunk_depth) {
+    int chunk = node - (1 << chunk_depth);
+    if (chunk != w.own_chunk) scan_chunk(ix, w, chunk);
+    return;
+  }
+  if constexpr (LEVEL < 6) {
+    int step = min(5, chunk_depth - depth);
+    int base = node << step;
+    float bd = INFINITY;
+    if (w.lane < (1 << step)) bd = node_d2(ix, base + w.lane, w.qx, w.qy, w.qz);
+    unsigned m = __ballot_sync(0xFFFFFFFFu, bd <= w.worst_d && bd < INFINITY);
+    while (m) {
+      // nearest remaining box first
+      unsigned key = ((m >> w.lane) & 1u) ? __float_as_uint(bd) : 0xFFFFFFFFu;
+      unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, key);
+      if (__uint_as_float(kmin) > w.worst_d) break;        // every remaining box is farther than the k-th neighbour
+      unsigned pick = __ballot_sync(0xFFFFFFFFu, key == kmin) & m;
+      int c = __ffs(pick) - 1;
+      m &= ~(1u << c);
+      knn_visit<LEVEL + 1>(ix, w, base + c, depth + step, chunk_depth);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_knn_warp(IndexView ix, int k, int chunk_depth, int* __restrict__ knn_pos,
+                                                  int* __restrict__ knn_out_orig) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // query = Morton position
+  if (i >= ix.n) return;
+  float4 q = __ldg(&ix.pts[i]);
+  WarpKnn w;
+  w.qx = q.x; w.qy = q.y; w.qz = q.z;
+  w.ld = INFINITY; w.lid = 0x7FFFFFFF; w.lpos = -1;
+  w.worst_d = INFINITY; w.worst_id = 0x7FFFFFFF;
+  w.k = k; w.lane = lane;
+  w.own_chunk = -1;
+  scan_chunk(ix, w, i >> 5);          // the query's own chunk first: a tight bound before the tree is touched
+  w.own_chunk = i >> 5;
+  knn_visit<0>(ix, w, 1, 0, chunk_depth);
+  if (lane < k) {
+    knn_pos[(size_t)i * k + lane] = w.lpos;
+    if (knn_out_orig) knn_out_orig[(size_t)__float_as_int(q.w) * k + lane] = w.lid;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_normals_from_knn(IndexView ix, int k, const int* __restrict__ knn_pos,
+                                                          float4* __restrict__ normals_morton) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ix.n) return;
+  const int* nb = knn_pos + (size_t)i * k;
   // mean and covariance in list order, float64
   double mx = 0, my = 0, mz = 0;
   for (int j = 0; j < k; ++j) {
-    float4 p = __ldg(&ix.pts[L.pos[j * nt]]);
+    float4 p = __ldg(&ix.pts[__ldg(&nb[j])]);
     mx = mx + (double)p.x; my = my + (double)p.y; mz = mz + (double)p.z;
   }
   double kd = (double)k;
   mx = mx / kd; my = my / kd; mz = mz / kd;
   double cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0, r2max = 0;
   for (int j = 0; j < k; ++j) {
-    float4 p = __ldg(&ix.pts[L.pos[j * nt]]);
+    float4 p = __ldg(&ix.pts[__ldg(&nb[j])]);
     double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
     cxx = cxx + dx * dx; cxy = cxy + dx * dy; cxz = cxz + dx * dz;
     cyy = cyy + dy * dy; cyz = cyz + dy * dz; czz = czz + dz * dz;
@@ -75,21 +164,20 @@ __global__ void __launch_bounds__(128) k_surface_normals(IndexView ix, int k, fl
   double r = sqrt(r2max);
   double vol = four_thirds_pi * ((r * r) * r);
   normals_morton[i] = make_float4((float)nx, (float)ny, (float)nz, (float)(kd / vol));
-  if (knn_out_orig) {
-    int self = __float_as_int(q.w);
-    for (int j = 0; j < k; ++j) knn_out_orig[(size_t)self * k + j] = L.id[j * nt];
-  }
 }
 
 int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig) {
-  if (knn < 1 || knn > AICP_MAX_KNN) return fail(h, AICP_B200_ERR_BAD_ARG, "knn %d outside [1,%d]", knn, AICP_MAX_KNN);
+  if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "SurfaceNormalDataPointsFilter: knn %d outside [1,32]", knn);
   if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "SurfaceNormalDataPointsFilter: knn %d >= %d points", knn, ix.n);
-  int nt = knn <= 32 ? 128 : 64;
-  size_t smem = (size_t)knn * nt * 12;
-  CUDA_TRY(cudaFuncSetAttribute(k_surface_normals, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  k_surface_normals<<<(ix.n + nt - 1) / nt, nt, smem, h->stream>>>(ix.view(), knn, normals_morton, knn_out_orig);
+  CUDA_TRY(h->knn_pos.reserve((size_t)ix.n * knn));
+  int depth = 0;
+  while ((1 << depth) < ix.first_leaf) ++depth;
+  const int chunk_depth = depth - 2;                   // build_index guarantees at least 4 leaves
+  const long long threads = (long long)ix.n * 32;
+  k_knn_warp<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(ix.view(), knn, chunk_depth, h->knn_pos.p, knn_out_orig);
+  k_normals_from_knn<<<(ix.n + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton);
   CUDA_TRY(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 2;
   return AICP_B200_OK;
 }
 

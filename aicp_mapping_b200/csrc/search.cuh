@@ -33,13 +33,21 @@ __device__ __forceinline__ float node_d2(const IndexView& ix, int node, float qx
 }
 
 // 1-NN: returns position in the Morton-ordered array (so the caller can gather normals) and the squared distance.
-__device__ inline void nn_search(const IndexView& ix, float qx, float qy, float qz, int* out_pos, float* out_d2) {
+// warm_pos >= 0 seeds the search with a known reference point (the previous iteration's match): the bound starts at its
+// distance, so most of the tree is pruned at the root.  The seed is an ordinary candidate, so the result is unchanged.
+__device__ inline void nn_search(const IndexView& ix, float qx, float qy, float qz, int* out_pos, float* out_d2, int warm_pos = -1) {
   int stack_n[AICP_STACK];
   float stack_d[AICP_STACK];
   int sp = 0;
   float best = INFINITY;
   int best_id = 0x7FFFFFFF;
   int best_pos = -1;
+  if (warm_pos >= 0) {
+    float4 p = __ldg(&ix.pts[warm_pos]);
+    best = d2_f(qx, qy, qz, p.x, p.y, p.z);
+    best_id = __float_as_int(p.w);
+    best_pos = warm_pos;
+  }
   int node = 1;
   while (true) {
     if (node >= ix.first_leaf) {

@@ -1,0 +1,218 @@
+// aicp_b200_adapter.hpp -- header-only C++ adapters that plug libaicp_b200.so into aicp_core behind the reference's own
+// plug-in interfaces.  This is the reference-side binding a maintainer adds (INTEGRATION.md shows the two factory lines):
+//
+//   aicp::B200Registration : aicp::AbstractRegistrator     aicp_core/include/aicp_registration/abstract_registrator.hpp:8-19
+//       stands where aicp::PointmatcherRegistration stands   aicp_core/include/aicp_registration/pointmatcher_registration.hpp:22-67
+//   aicp::B200Overlap      : aicp::AbstractOverlapper       aicp_core/include/aicp_overlap/abstract_overlapper.hpp:13-19
+//       stands where aicp::OctreesOverlap stands             aicp_core/include/aicp_overlap/octrees_overlap.hpp:20-58
+//
+// It needs the headers aicp_core already uses (PCL point types, Eigen, octomap) and nothing else; all arithmetic happens
+// on the GPU behind the C ABI of aicp_b200.h.  Error convention: the reference exit(1)s on a bad config or cloud
+// (pointmatcher_registration.cpp:60-64,96-100); the adapter prints the same kind of message to cerr, leaves
+// final_transform = identity and keeps the process alive -- App::runAicpPipeline's own sanity gate on the correction
+// magnitude (app.cpp:366-373) then sees a null correction.
+#ifndef AICP_B200_ADAPTER_HPP_
+#define AICP_B200_ADAPTER_HPP_
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "aicp_b200.h"
+
+#include "aicp_registration/abstract_registrator.hpp"
+#include "aicp_registration/common.hpp"
+#include "aicp_overlap/abstract_overlapper.hpp"
+#include "aicp_overlap/common.hpp"
+
+namespace aicp {
+
+namespace b200_detail {
+
+// pcl::PointXYZ is a 16-byte (x, y, z, pad) record: it is passed to the C ABI in place.  Wider point types are packed.
+template <typename PointT>
+inline const float* as_xyzw(const pcl::PointCloud<PointT>& cloud, std::vector<float>& staging, int64_t* n) {
+  // the reference takes cloud.width as the point count (cloudIO.cpp:83)
+  size_t count = cloud.width;
+  if (count > cloud.points.size()) count = cloud.points.size();
+  *n = (int64_t)count;
+  if (sizeof(PointT) == 16) return reinterpret_cast<const float*>(cloud.points.data());
+  staging.resize(4 * count);
+  for (size_t i = 0; i < count; ++i) {
+    staging[4 * i + 0] = cloud.points[i].x;
+    staging[4 * i + 1] = cloud.points[i].y;
+    staging[4 * i + 2] = cloud.points[i].z;
+    staging[4 * i + 3] = 1.0f;
+  }
+  return staging.data();
+}
+
+inline void to_pcl(const std::vector<float>& xyzw, pcl::PointCloud<pcl::PointXYZ>& out) {
+  // fromDataPointsToPCL, cloudIO.cpp:68-79
+  size_t n = xyzw.size() / 4;
+  out.points.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    out.points[i].x = xyzw[4 * i + 0];
+    out.points[i].y = xyzw[4 * i + 1];
+    out.points[i].z = xyzw[4 * i + 2];
+  }
+  out.width = (uint32_t)n;
+  out.height = 1;
+}
+
+}  // namespace b200_detail
+
+class B200Registration : public AbstractRegistrator {
+ public:
+  B200Registration() : h_(nullptr), n_read_(0) { open(); }
+  explicit B200Registration(const RegistrationParams& params) : params_(params), h_(nullptr), n_read_(0) { open(); }
+  ~B200Registration() { if (h_) aicp_b200_destroy(h_); }
+  B200Registration(const B200Registration&) = delete;
+  B200Registration& operator=(const B200Registration&) = delete;
+
+  virtual void registerClouds(pcl::PointCloud<pcl::PointXYZ>& cloud_ref, pcl::PointCloud<pcl::PointXYZ>& cloud_read,
+                              Eigen::Matrix4f& final_transform) {
+    registerAny(cloud_ref, cloud_read, final_transform);
+  }
+  virtual void registerClouds(pcl::PointCloud<pcl::PointXYZRGB>& cloud_ref, pcl::PointCloud<pcl::PointXYZRGB>& cloud_read,
+                              Eigen::Matrix4f& final_transform) {
+    registerAny(cloud_ref, cloud_read, final_transform);
+  }
+  // an empty no-op in the reference as well (pointmatcher_registration.cpp:36-45)
+  virtual void registerClouds(pcl::PointCloud<pcl::PointXYZRGBNormal>&, pcl::PointCloud<pcl::PointXYZRGBNormal>&, Eigen::Matrix4f&) {}
+
+  virtual void getInitializedReading(pcl::PointCloud<pcl::PointXYZ>& initialized_reading) {
+    if (params_.pointmatcher.initialTransform.empty())
+      std::cout << "[B200] Reading cloud not initialized here." << std::endl;       // pointmatcher_registration.hpp:43
+    fetch(&aicp_b200_get_initialized_reading, initialized_reading);
+  }
+  virtual void getOutputReading(pcl::PointCloud<pcl::PointXYZ>& out_read_cloud) { fetch(&aicp_b200_get_output_reading, out_read_cloud); }
+
+  virtual void updateConfigParams(std::string config_name) {
+    params_.pointmatcher.configFileName = config_name;
+    if (h_) aicp_b200_set_config(h_, config_name.c_str());
+  }
+
+  // conveniences beyond the reference interface
+  const Eigen::Matrix4f& getOutputTransform() const { return last_T_; }
+  float getWeightedPointUsedRatio() const { return stats_.weighted_point_used_ratio; }
+  const aicp_b200_stats& getStats() const { return stats_; }
+  aicp_b200_handle* handle() { return h_; }
+
+ private:
+  void open() {
+    last_T_ = Eigen::Matrix4f::Identity();
+    std::memset(&stats_, 0, sizeof(stats_));
+    const std::string& cfg = params_.pointmatcher.configFileName;
+    if (aicp_b200_create(cfg.empty() ? nullptr : cfg.c_str(), -1, &h_) != AICP_B200_OK) {
+      std::cerr << "[B200] " << aicp_b200_last_error(nullptr) << std::endl;
+      h_ = nullptr;
+    }
+  }
+
+  // "x,y,theta_deg" -> column-major 4x4, parseTransformationDeg (cloudIO.cpp:261-302) + the rigidity check of
+  // applyInitialization (pointmatcher_registration.cpp:71-89)
+  bool initialTransform(float* T) const {
+    std::string s = params_.pointmatcher.initialTransform;
+    if (s.empty()) return false;
+    for (char& c : s) if (c == '[' || c == ']' || c == ',' || c == ';') c = ' ';
+    float v[3];
+    if (std::sscanf(s.c_str(), "%f %f %f", &v[0], &v[1], &v[2]) != 3) {
+      std::cerr << "[Cloud IO] An error occured while trying to parse the initial transformation." << std::endl
+                << "No initial transformation will be used" << std::endl;
+      return false;
+    }
+    const double th = v[2] * 3.14159265358979323846 / 180.0;
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    T[0] = (float)std::cos(th); T[4] = (float)-std::sin(th);
+    T[1] = (float)std::sin(th); T[5] = (float)std::cos(th);
+    T[12] = v[0]; T[13] = v[1];
+    std::cout << "[B200] Initialization: " << params_.pointmatcher.initialTransform << std::endl;
+    return true;
+  }
+
+  template <typename PointT>
+  void registerAny(pcl::PointCloud<PointT>& cloud_ref, pcl::PointCloud<PointT>& cloud_read, Eigen::Matrix4f& final_transform) {
+    final_transform = Eigen::Matrix4f::Identity();
+    if (!h_) { std::cerr << "[B200] no GPU handle; registration skipped." << std::endl; return; }
+    int64_t n_ref = 0, n_read = 0;
+    const float* ref = b200_detail::as_xyzw(cloud_ref, stage_ref_, &n_ref);
+    const float* read = b200_detail::as_xyzw(cloud_read, stage_read_, &n_read);
+    float init[16];
+    const bool have_init = initialTransform(init);
+    float T[16];
+    const int rc = aicp_b200_register(h_, ref, n_ref, read, n_read, have_init ? init : nullptr, T, &stats_);
+    if (rc != AICP_B200_OK) {
+      std::cerr << "[B200] registerClouds failed (" << rc << "): " << aicp_b200_last_error(h_) << std::endl;
+      return;
+    }
+    n_read_ = n_read;
+    std::memcpy(final_transform.data(), T, sizeof(T));       // column-major, like Eigen::Matrix4f
+    last_T_ = final_transform;
+    std::cout << "[B200] Accepted matches (inliers): " << stats_.weighted_point_used_ratio * 100 << " %" << std::endl;   // :114
+  }
+
+  void fetch(int (*getter)(aicp_b200_handle*, float*, int64_t), pcl::PointCloud<pcl::PointXYZ>& out) {
+    std::vector<float> xyzw(4 * (size_t)n_read_);
+    if (!h_ || n_read_ == 0 || getter(h_, xyzw.data(), n_read_) != AICP_B200_OK) xyzw.clear();
+    b200_detail::to_pcl(xyzw, out);
+  }
+
+  RegistrationParams params_;
+  aicp_b200_handle* h_;
+  aicp_b200_stats stats_;
+  Eigen::Matrix4f last_T_;
+  int64_t n_read_;
+  std::vector<float> stage_ref_, stage_read_;
+};
+
+class B200Overlap : public AbstractOverlapper {
+ public:
+  explicit B200Overlap(const OverlapParams& params) : params_(params), h_(nullptr), overlap_(-1.0f) {
+    counts_[0] = counts_[1] = counts_[2] = 0;
+    // the reference hands ColorOcTree pointers back for visualisation only (App ignores them, app.cpp:132-135); the GPU
+    // path does not materialise trees, so callers get an empty tree of the right resolution
+    tree_ = new octomap::ColorOcTree(params_.octree_based.octomapResolution);
+    if (aicp_b200_create(nullptr, -1, &h_) != AICP_B200_OK) {
+      std::cerr << "[B200] " << aicp_b200_last_error(nullptr) << std::endl;
+      h_ = nullptr;
+    }
+  }
+  ~B200Overlap() { if (h_) aicp_b200_destroy(h_); delete tree_; }
+  B200Overlap(const B200Overlap&) = delete;
+  B200Overlap& operator=(const B200Overlap&) = delete;
+
+  virtual octomap::ColorOcTree* computeOverlap(pcl::PointCloud<pcl::PointXYZ>& ref_cloud, pcl::PointCloud<pcl::PointXYZ>& read_cloud,
+                                               Eigen::Isometry3d ref_pose, Eigen::Isometry3d read_pose,
+                                               octomap::ColorOcTree* /*reading_tree*/) {
+    overlap_ = -1.0f;
+    if (!h_) return tree_;
+    // convertPointCloudToScanGraph iterates cloud.points (octrees_overlap.cpp:232-236); only the pose translation is used
+    const double ro[3] = {ref_pose.translation().x(), ref_pose.translation().y(), ref_pose.translation().z()};
+    const double so[3] = {read_pose.translation().x(), read_pose.translation().y(), read_pose.translation().z()};
+    const int rc = aicp_b200_overlap(h_, reinterpret_cast<const float*>(ref_cloud.points.data()), (int64_t)ref_cloud.points.size(), ro,
+                                     reinterpret_cast<const float*>(read_cloud.points.data()), (int64_t)read_cloud.points.size(), so,
+                                     params_.octree_based.octomapResolution, &overlap_, counts_);
+    if (rc != AICP_B200_OK) {
+      std::cerr << "[B200] computeOverlap failed (" << rc << "): " << aicp_b200_last_error(h_) << std::endl;
+      overlap_ = -1.0f;
+    }
+    return tree_;
+  }
+  virtual float getOverlap() { return overlap_; }
+  const int64_t* getCounts() const { return counts_; }      // {overlapping, reference, reading} nodes
+
+ private:
+  OverlapParams params_;
+  aicp_b200_handle* h_;
+  octomap::ColorOcTree* tree_;
+  float overlap_;
+  int64_t counts_[3];
+};
+
+}  // namespace aicp
+
+#endif

@@ -34,21 +34,26 @@ void orc_sincos(double x, double* s, double* c) {
   double kd = floor(x * two_over_pi + 0.5);
   double r = (x - kd * pio2_hi) - kd * pio2_lo;
   double r2 = r * r;
-  /* sin r */
+  /* sin r: forward Taylor sum, factorial ratios applied as reciprocal multiplications; stops once a term no longer
+   * changes the sum (at most 11 terms) */
   double term = r, ss = r;
   for (int n = 1; n <= 11; ++n) {
-    double den = (double)((2 * n) * (2 * n + 1));
-    term = (term * r2) / den;
+    double inv = 1.0 / (double)((2 * n) * (2 * n + 1));
+    term = (term * r2) * inv;
     term = -term;
-    ss = ss + term;
+    double ns = ss + term;
+    if (ns == ss) break;
+    ss = ns;
   }
   /* cos r */
   double cterm = 1.0, cc = 1.0;
   for (int n = 1; n <= 11; ++n) {
-    double den = (double)((2 * n - 1) * (2 * n));
-    cterm = (cterm * r2) / den;
+    double inv = 1.0 / (double)((2 * n - 1) * (2 * n));
+    cterm = (cterm * r2) * inv;
     cterm = -cterm;
-    cc = cc + cterm;
+    double nc = cc + cterm;
+    if (nc == cc) break;
+    cc = nc;
   }
   long long k = (long long)kd;
   int quad = (int)(((k % 4) + 4) % 4);
@@ -66,9 +71,12 @@ static double orc_atan01(double z) {
   for (int h = 0; h < 3; ++h) u = u / (1.0 + sqrt(1.0 + u * u));
   double u2 = u * u, p = u, sum = u;
   for (int n = 1; n <= 11; ++n) {
+    double inv = 1.0 / (double)(2 * n + 1);
     p = p * u2;
     p = -p;
-    sum = sum + p / (double)(2 * n + 1);
+    double ns = sum + p * inv;
+    if (ns == sum) break;
+    sum = ns;
   }
   return 8.0 * sum;
 }
