@@ -121,7 +121,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   cudaSetDevice(h->device);
   if (h->comm) aicp_b200_comm_destroy(hh);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_node.release(); h->normals.release(); h->knn_pos.release();
+  h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_rec.release(); h->normals.release(); h->knn_pos.release();
   h->read_in.release(); h->read_ix.release(); h->read0.release(); h->read_out.release(); h->read_init.release();
   h->match_pos.release(); h->d2.release(); h->hist.release(); h->trace_idx.release();
   h->tmp_ix.release(); h->tmp_a.release(); h->tmp_b.release(); h->tmp_i.release(); h->tmp_f.release();
@@ -278,11 +278,11 @@ int aicp_b200_surface_normals(aicp_b200_handle* hh, const float* xyzw, int64_t n
   int rc = upload_points(h, h->tmp_a, xyzw, n, &pts);
   if (rc) return rc;
   if ((rc = build_index(h, h->tmp_ix, pts, n))) return rc;
-  CUDA_TRY(h->tmp_b.reserve((size_t)h->tmp_ix.n_pad * 2));
+  CUDA_TRY(h->tmp_b.reserve((size_t)h->tmp_ix.n * 2));
   int* knn_dev = nullptr;
   if (out_knn) { CUDA_TRY(h->tmp_i.reserve((size_t)n * knn)); knn_dev = h->tmp_i.p; }
   float4* nm = h->tmp_b.p;              // Morton order
-  float4* no = h->tmp_b.p + h->tmp_ix.n_pad;   // original order
+  float4* no = h->tmp_b.p + h->tmp_ix.n;   // original order
   if ((rc = run_surface_normals(h, h->tmp_ix, knn, nm, knn_dev))) return rc;
   if ((rc = scatter_normals(h, h->tmp_ix.pts.p, nm, h->tmp_ix.n, no))) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -38,15 +38,16 @@ struct IndexMeta {
 // Morton-ordered spatial index over one cloud
 struct SpatialIndex {
   DevBuf<float4> pts;            // Morton order, .w = original index
-  DevBuf<float4> node;           // 2 float4 per heap node
+  DevBuf<float4> rec;            // 4 float4 per internal node of the radix tree (see search.cuh)
+  DevBuf<int4> node_meta;        // (first, split, end, -) per internal node, build-time scratch
   DevBuf<unsigned int> keys, keys_alt, vals, vals_alt;
   DevBuf<int> flags;             // bottom-up refit arrival counters
   DevBuf<unsigned char> sort_tmp;
   IndexMeta* meta = nullptr;     // device
-  int n = 0, n_pad = 0, first_leaf = 1;
-  IndexView view() const { return IndexView{pts.p, node.p, n, first_leaf}; }
+  int n = 0;
+  IndexView view() const { return IndexView{pts.p, rec.p, n}; }
   void release() {
-    pts.release(); node.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release();
+    pts.release(); rec.release(); node_meta.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release();
     flags.release(); sort_tmp.release();
     if (meta) cudaFree(meta);
     meta = nullptr;
@@ -69,7 +70,7 @@ struct Handle {
   DevBuf<float4> ref_in;
   SpatialIndex ref_ix;           // original frame (normals search)
   DevBuf<float4> refc_pts;       // centred points, Morton order
-  DevBuf<float4> refc_node;      // centred boxes
+  DevBuf<float4> refc_rec;       // centred tree records
   DevBuf<float4> normals;        // Morton order (nx,ny,nz,density)
   DevBuf<int> knn_pos;           // n x knn neighbour positions (Morton order), scratch of the normals filter
   int64_t n_ref = 0;

@@ -51,19 +51,19 @@ __global__ void k_loop_init(DeviceState* st, const IndexMeta* __restrict__ meta,
   st->tr_hist[0][0] = st->tr_hist[0][1] = st->tr_hist[0][2] = 0.0;
 }
 
-// reference' = reference - mean: points and node boxes (float subtraction is monotone, so the boxes stay valid)
-__global__ void __launch_bounds__(256) k_centre(const float4* __restrict__ pts, int n_pad, const float4* __restrict__ node,
-                                                int n_node4, const DeviceState* __restrict__ st, float4* __restrict__ pts_c,
-                                                float4* __restrict__ node_c) {
+// reference' = reference - mean: points and tree records (float subtraction is monotone, so the boxes stay valid)
+__global__ void __launch_bounds__(256) k_centre(const float4* __restrict__ pts, int n, const float4* __restrict__ rec,
+                                                int n_rec4, const DeviceState* __restrict__ st, float4* __restrict__ pts_c,
+                                                float4* __restrict__ rec_c) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   float mx = st->mu[0], my = st->mu[1], mz = st->mu[2];
-  if (i < n_pad) {
+  if (i < n) {
     float4 p = __ldg(&pts[i]);
     pts_c[i] = make_float4(__fsub_rn(p.x, mx), __fsub_rn(p.y, my), __fsub_rn(p.z, mz), p.w);
   }
-  if (i < n_node4) {
-    float4 b = __ldg(&node[i]);
-    node_c[i] = make_float4(__fsub_rn(b.x, mx), __fsub_rn(b.y, my), __fsub_rn(b.z, mz), 0.f);
+  if (i < n_rec4) {
+    float4 b = __ldg(&rec[i]);
+    rec_c[i] = make_float4(__fsub_rn(b.x, mx), __fsub_rn(b.y, my), __fsub_rn(b.z, mz), b.w);
   }
 }
 
@@ -450,9 +450,9 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     rc = build_index(h, h->ref_ix, h->ref_in.p, n_ref);
     if (rc) return rc;
     mark(1);
-    CUDA_TRY(h->normals.reserve((size_t)h->ref_ix.n_pad));
-    CUDA_TRY(h->refc_pts.reserve((size_t)h->ref_ix.n_pad));
-    CUDA_TRY(h->refc_node.reserve((size_t)4 * h->ref_ix.first_leaf));
+    CUDA_TRY(h->normals.reserve((size_t)h->ref_ix.n));
+    CUDA_TRY(h->refc_pts.reserve((size_t)h->ref_ix.n));
+    CUDA_TRY(h->refc_rec.reserve((size_t)4 * h->ref_ix.n));
     rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr);
     if (rc) return rc;
     h->ref_knn = cfg.knn_normals;
@@ -462,7 +462,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     // the reference runs the same filter on the reading (icp_autotuned.yaml:9-14); PointToPlane never reads the result
     rc = build_index(h, h->tmp_ix, h->read_in.p, n_read);
     if (rc) return rc;
-    CUDA_TRY(h->tmp_a.reserve((size_t)h->tmp_ix.n_pad));
+    CUDA_TRY(h->tmp_a.reserve((size_t)h->tmp_ix.n));
     rc = run_surface_normals(h, h->tmp_ix, cfg.knn_normals, h->tmp_a.p, nullptr);
     if (rc) return rc;
   }
@@ -472,10 +472,10 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   }
   k_loop_init<<<1, 32, 0, s>>>(h->st, h->ref_ix.meta, (long long)n_ref, init_T_host ? 1 : 0);
   if (rebuild_reference) {
-    int n4 = 4 * h->ref_ix.first_leaf;
-    int m = h->ref_ix.n_pad > n4 ? h->ref_ix.n_pad : n4;
-    k_centre<<<(m + 255) / 256, 256, 0, s>>>(h->ref_ix.pts.p, h->ref_ix.n_pad, h->ref_ix.node.p, n4, h->st, h->refc_pts.p,
-                                            h->refc_node.p);
+    int n4 = 4 * (h->ref_ix.n - 1);
+    int m = h->ref_ix.n > n4 ? h->ref_ix.n : n4;
+    k_centre<<<(m + 255) / 256, 256, 0, s>>>(h->ref_ix.pts.p, h->ref_ix.n, h->ref_ix.rec.p, n4, h->st, h->refc_pts.p,
+                                            h->refc_rec.p);
     h->launches += 1;
   }
   CUDA_TRY(h->read0.reserve((size_t)n_read));
@@ -500,7 +500,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   const float4* read_s = h->read_ix.pts.p;
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
 
-  IndexView cix{h->refc_pts.p, h->refc_node.p, h->ref_ix.n, h->ref_ix.first_leaf};
+  IndexView cix{h->refc_pts.p, h->refc_rec.p, h->ref_ix.n};
   LoopParams lp{cfg.ratio, cfg.max_iterations, cfg.min_diff_rot, cfg.min_diff_trans, cfg.smooth_length};
   const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
   for (int it = 0; it < cfg.max_iterations; ++it) {

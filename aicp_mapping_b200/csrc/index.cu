@@ -4,11 +4,13 @@
 //                   (order independent, so the mean is identical on every GPU count), non-finite flag
 //   k_morton_keys   30-bit Morton key of the isotropically quantised position + identity permutation
 //   radix sort      (key, original index) pairs, 30 significant bits
-//   k_gather        Morton-ordered float4 copy with the original index in .w, padded to whole leaves
-//   k_refit         leaf boxes + bottom-up union to the root in ONE launch (second-arriver rule on atomic counters)
+//   k_gather        Morton-ordered float4 copy with the original index in .w
+//   k_radix_tree    Karras binary radix tree over the sorted keys: one thread per internal node
+//   k_refit         child boxes written into the parents' 64-byte records, bottom-up to the root in ONE launch
+//                   (second-arriver rule on atomic counters)
 //
-// Algorithmic HBM bytes per reference point: read 16 + key/perm 8 written + 8 read by the gather + 16
-// written = 48, plus 4 B/point of node boxes.
+// Algorithmic HBM bytes per point: read 16 + key/perm 8 written + 8 read by the gather + 16 written = 48,
+// plus 64 B of tree record and 16 B of node range per point.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "handle.cuh"
@@ -85,70 +87,93 @@ __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) k_gather(const float4* __restrict__ pts, const unsigned int* __restrict__ perm, int n,
-                                                int n_pad, float4* __restrict__ out) {
+                                                float4* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  float4 o;
-  if (i < n) {
-    unsigned int src = perm[i];
-    float4 p = __ldg(&pts[src]);
-    o = make_float4(p.x, p.y, p.z, __int_as_float((int)src));
-  } else {
-    o = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0x7FFFFFFF));
-  }
-  out[i] = o;
+  if (i >= n) return;
+  unsigned int src = perm[i];
+  float4 p = __ldg(&pts[src]);
+  out[i] = make_float4(p.x, p.y, p.z, __int_as_float((int)src));
 }
 
-// One thread per leaf: compute the leaf box, then climb.  At every parent the first child to arrive stops, the
-// second (which can see both boxes after the fence) writes the union and continues: one launch builds all levels.
-__global__ void __launch_bounds__(256) k_refit(const float4* __restrict__ pts, int n, int first_leaf, float4* node, int* flags) {
-  int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= first_leaf) return;
-  float3 lo = make_float3(INFINITY, INFINITY, INFINITY), hi = make_float3(-INFINITY, -INFINITY, -INFINITY);
-  int base = l * AICP_LEAF;
-  if (base < n) {
-#pragma unroll
-    for (int j = 0; j < AICP_LEAF; ++j) {
-      if (base + j < n) {
-        float4 p = __ldg(&pts[base + j]);
-        lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
-        hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
-      }
-    }
-  }
-  int id = first_leaf + l;
+// ---- binary radix tree over the sorted keys (Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees,
+// and k-d Trees", HPG 2012).  Keys are made unique by appending the sorted position, so equal Morton codes (many
+// points in one 12 cm cell near the sensor) split by position bits.  One thread per internal node, no dependencies.
+__device__ __forceinline__ int delta(const unsigned int* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  unsigned int x = __ldg(&keys[i]) ^ __ldg(&keys[j]);
+  if (x) return __clz(x);
+  return 32 + __clz((unsigned)i ^ (unsigned)j);
+}
+
+__global__ void __launch_bounds__(256) k_radix_tree(const unsigned int* __restrict__ keys, int n, int4* __restrict__ meta,
+                                                    int* __restrict__ parent_int, int* __restrict__ parent_leaf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = delta(keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int first = min(i, j), last = max(i, j);
+  meta[i] = make_int4(first, gamma + 1, last + 1, 0);
+  if (first == gamma) parent_leaf[gamma] = (i << 1); else parent_int[gamma] = (i << 1);
+  if (last == gamma + 1) parent_leaf[gamma + 1] = (i << 1) | 1; else parent_int[gamma + 1] = (i << 1) | 1;
+}
+
+// One thread per point: start from the point's own box and climb.  At every node the first child to arrive stops, the
+// second (which can see both boxes after the fence) continues with the union: one launch fits all levels.  Each child
+// writes its box into the PARENT's 64-byte record, so that a traversal step reads both child boxes with one access.
+__global__ void __launch_bounds__(256) k_refit(const float4* __restrict__ pts, int n, const int4* __restrict__ meta,
+                                               const int* __restrict__ parent_int, const int* __restrict__ parent_leaf,
+                                               float4* rec, int* flags) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float4 q = __ldg(&pts[p]);
+  float3 lo = make_float3(q.x, q.y, q.z), hi = lo;
+  int cur = __ldg(&parent_leaf[p]);
   while (true) {
-    __stcg(&node[2 * id], make_float4(lo.x, lo.y, lo.z, 0.f));
-    __stcg(&node[2 * id + 1], make_float4(hi.x, hi.y, hi.z, 0.f));
-    if (id == 1) break;
+    int i = cur >> 1, side = cur & 1;
+    int4 m = __ldg(&meta[i]);
+    float4* r = rec + 4 * (size_t)i;
+    if (side == 0) {
+      __stcg(r + 0, make_float4(lo.x, lo.y, lo.z, __int_as_float(m.x)));
+      __stcg(r + 1, make_float4(hi.x, hi.y, hi.z, __int_as_float(m.y)));
+    } else {
+      __stcg(r + 2, make_float4(lo.x, lo.y, lo.z, __int_as_float(m.z)));
+      __stcg(r + 3, make_float4(hi.x, hi.y, hi.z, 0.f));
+    }
     __threadfence();
-    int parent = id >> 1;
-    if (atomicAdd(&flags[parent], 1) == 0) break;   // sibling not there yet: it will do the parent
+    if (atomicAdd(&flags[i], 1) == 0) break;        // sibling not there yet: it will carry on
     __threadfence();
-    int sib = id ^ 1;
-    float4 sa = __ldcg(&node[2 * sib]), sb = __ldcg(&node[2 * sib + 1]);
+    float4 sa = __ldcg(r + 2 * (1 - side)), sb = __ldcg(r + 2 * (1 - side) + 1);
     lo.x = fminf(lo.x, sa.x); lo.y = fminf(lo.y, sa.y); lo.z = fminf(lo.z, sa.z);
     hi.x = fmaxf(hi.x, sb.x); hi.y = fmaxf(hi.y, sb.y); hi.z = fmaxf(hi.z, sb.z);
-    id = parent;
+    if (i == 0) break;
+    cur = __ldg(&parent_int[i]);
   }
 }
-
-static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64) {
   if (n64 < 1 || n64 > (1ll << 30)) return fail(h, AICP_B200_ERR_BAD_ARG, "cloud size %lld out of range", (long long)n64);
   int n = (int)n64;
   cudaStream_t s = h->stream;
-  int leaves = (n + AICP_LEAF - 1) / AICP_LEAF;
-  int first_leaf = next_pow2(leaves);
-  if (first_leaf < 4) first_leaf = 4;          // the warp k-NN walks 32-point chunks = nodes two levels above the leaves
-  int n_pad = first_leaf * AICP_LEAF;
   if (!ix.meta) CUDA_TRY(cudaMalloc((void**)&ix.meta, sizeof(IndexMeta)));
-  CUDA_TRY(ix.pts.reserve((size_t)n_pad));
-  CUDA_TRY(ix.node.reserve((size_t)4 * first_leaf));
+  CUDA_TRY(ix.pts.reserve((size_t)n));
+  CUDA_TRY(ix.rec.reserve((size_t)4 * n));
+  CUDA_TRY(ix.node_meta.reserve((size_t)n));
   CUDA_TRY(ix.keys.reserve((size_t)n)); CUDA_TRY(ix.keys_alt.reserve((size_t)n));
   CUDA_TRY(ix.vals.reserve((size_t)n)); CUDA_TRY(ix.vals_alt.reserve((size_t)n));
-  CUDA_TRY(ix.flags.reserve((size_t)first_leaf));
+  CUDA_TRY(ix.flags.reserve((size_t)3 * n));          // arrival counters | parent of internal nodes | parent of points
   size_t tmp_bytes = 0;
   cub::DoubleBuffer<unsigned int> dk(ix.keys.p, ix.keys_alt.p), dv(ix.vals.p, ix.vals_alt.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, 30, s));
@@ -160,12 +185,19 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64)
   k_index_stats<<<stat_blocks, 256, 0, s>>>(pts_dev, n, ix.meta);
   k_morton_keys<<<blocks, 256, 0, s>>>(pts_dev, n, ix.meta, ix.keys.p, ix.vals.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ix.sort_tmp.p, tmp_bytes, dk, dv, n, 0, 30, s));
-  k_gather<<<(n_pad + 255) / 256, 256, 0, s>>>(pts_dev, dv.Current(), n, n_pad, ix.pts.p);
-  CUDA_TRY(cudaMemsetAsync(ix.flags.p, 0, sizeof(int) * (size_t)first_leaf, s));
-  k_refit<<<(first_leaf + 255) / 256, 256, 0, s>>>(ix.pts.p, n, first_leaf, ix.node.p, ix.flags.p);
+  k_gather<<<blocks, 256, 0, s>>>(pts_dev, dv.Current(), n, ix.pts.p);
+  h->launches += 4 + 4;    // own kernels + the radix sort's passes
+  if (n > 1) {
+    int* flags = ix.flags.p;
+    int* parent_int = flags + n;
+    int* parent_leaf = flags + 2 * (size_t)n;
+    CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, s));
+    k_radix_tree<<<blocks, 256, 0, s>>>(dk.Current(), n, ix.node_meta.p, parent_int, parent_leaf);
+    k_refit<<<blocks, 256, 0, s>>>(ix.pts.p, n, ix.node_meta.p, parent_int, parent_leaf, ix.rec.p, flags);
+    h->launches += 2;
+  }
   CUDA_TRY(cudaGetLastError());
-  h->launches += 5 + 4;    // own kernels + the radix sort's passes (upsweep/scan/downsweep or onesweep)
-  ix.n = n; ix.n_pad = n_pad; ix.first_leaf = first_leaf;
+  ix.n = n;
   return AICP_B200_OK;
 }
 

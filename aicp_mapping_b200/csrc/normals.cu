@@ -9,9 +9,10 @@
 //   k_knn_warp          one WARP per query point.  The sorted candidate list (32 entries, the first knn matter) lives
 //                       one entry per lane; candidates arrive 32 at a time as a coalesced 512-byte chunk of the
 //                       Morton-ordered cloud, each lane evaluates one, and accepted ones are inserted with a ballot +
-//                       shuffle-up (warp-shuffle top-k).  The walk over the index is warp-uniform: it descends the
-//                       implicit binary tree five levels at a time, the 32 lanes testing the 32 descendant boxes of a
-//                       node in one coalesced 1 KiB load, nearest box first, pruning against the current k-th distance.
+//                       shuffle-up (warp-shuffle top-k).  The walk over the radix tree is warp-uniform (every lane reads
+//                       the same 64-byte node record, a broadcast access), nearest child first, pruning against the
+//                       current k-th distance; subtrees of <= 32 points are scanned as one chunk.  The 32 Morton
+//                       neighbours of the query are scanned first, so the bound is tight before the tree is touched.
 //   k_normals_from_knn  one THREAD per point: gathers the neighbours in list order and runs covariance + cyclic Jacobi
 //                       in float64 registers (sequential in list order, so the result does not depend on the index).
 // Algorithmic HBM bytes per point: 16 (query) + 4*knn (neighbour ids written) + 4*knn (read back) + 16 (normal written).
@@ -28,7 +29,7 @@ struct WarpKnn {
   float worst_d;   // entry k-1 (uniform)
   int worst_id;
   int k;
-  int own_chunk;
+  int pre_lo, pre_hi;   // positions already offered by the pre-scan (never offered twice)
   int lane;
 };
 
@@ -46,64 +47,86 @@ __device__ __forceinline__ void warp_insert(WarpKnn& w, float cd, int cid, int c
   w.worst_id = __shfl_sync(0xFFFFFFFFu, w.lid, w.k - 1);
 }
 
-// 32 consecutive Morton-ordered points: one candidate per lane
-__device__ __forceinline__ void scan_chunk(const IndexView& ix, WarpKnn& w, int chunk) {
-  int pos = chunk * 32 + w.lane;
-  float4 p = __ldg(&ix.pts[pos]);
-  int id = __float_as_int(p.w);
-  float d = d2_f(w.qx, w.qy, w.qz, p.x, p.y, p.z);
-  unsigned m = __ballot_sync(0xFFFFFFFFu, id != 0x7FFFFFFF && cand_less(d, id, w.worst_d, w.worst_id));
+// up to 32 consecutive Morton-ordered points [first, first+cnt): one candidate per lane, one coalesced load
+__device__ __forceinline__ void scan_range(const IndexView& ix, WarpKnn& w, int first, int cnt, bool exclude_pre) {
+  int pos = first + w.lane;
+  float d = INFINITY;
+  int id = 0x7FFFFFFF;
+  bool ok = w.lane < cnt && !(exclude_pre && pos >= w.pre_lo && pos < w.pre_hi);
+  if (ok) {
+    float4 p = __ldg(&ix.pts[pos]);
+    id = __float_as_int(p.w);
+    d = d2_f(w.qx, w.qy, w.qz, p.x, p.y, p.z);
+  }
+  unsigned m = __ballot_sync(0xFFFFFFFFu, ok && cand_less(d, id, w.worst_d, w.worst_id));
   while (m) {
     int b = __ffs(m) - 1;
     m &= m - 1;
     float cd = __shfl_sync(0xFFFFFFFFu, d, b);
     int cid = __shfl_sync(0xFFFFFFFFu, id, b);
-    if (cand_less(cd, cid, w.worst_d, w.worst_id)) warp_insert(w, cd, cid, chunk * 32 + b);
+    if (cand_less(cd, cid, w.worst_d, w.worst_id)) warp_insert(w, cd, cid, first + b);
   }
 }
 
-// node at depth `depth`; chunk_depth = depth of the nodes that cover exactly 32 points (two levels above the leaves)
-template <int LEVEL>
-__device__ void knn_visit(const IndexView& ix, WarpKnn& w, int node, int depth, int chunk_depth) {
-  if (depth == chunk_depth) {
-    int chunk = node - (1 << chunk_depth);
-    if (chunk != w.own_chunk) scan_chunk(ix, w, chunk);
-    return;
-  }
-  if constexpr (LEVEL < 6) {
-    int step = min(5, chunk_depth - depth);
-    int base = node << step;
-    float bd = INFINITY;
-    if (w.lane < (1 << step)) bd = node_d2(ix, base + w.lane, w.qx, w.qy, w.qz);
-    unsigned m = __ballot_sync(0xFFFFFFFFu, bd <= w.worst_d && bd < INFINITY);
-    while (m) {
-      // nearest remaining box first
-      unsigned key = ((m >> w.lane) & 1u) ? __float_as_uint(bd) : 0xFFFFFFFFu;
-      unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, key);
-      if (__uint_as_float(kmin) > w.worst_d) break;        // every remaining box is farther than the k-th neighbour
-      unsigned pick = __ballot_sync(0xFFFFFFFFu, key == kmin) & m;
-      int c = __ffs(pick) - 1;
-      m &= ~(1u << c);
-      knn_visit<LEVEL + 1>(ix, w, base + c, depth + step, chunk_depth);
-    }
-  }
-}
+#define KNN_WARPS 8
+#define KNN_LEAF 32
 
-__global__ void __launch_bounds__(256) k_knn_warp(IndexView ix, int k, int chunk_depth, int* __restrict__ knn_pos,
-                                                  int* __restrict__ knn_out_orig) {
-  const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // query = Morton position
+__global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k, int* __restrict__ knn_pos,
+                                                             int* __restrict__ knn_out_orig) {
+  __shared__ int s_a[KNN_WARPS][AICP_STACK];
+  __shared__ int s_b[KNN_WARPS][AICP_STACK];
+  __shared__ float s_d[KNN_WARPS][AICP_STACK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int i = blockIdx.x * KNN_WARPS + wid;      // query = Morton position
   if (i >= ix.n) return;
+  int* st_a = s_a[wid]; int* st_b = s_b[wid]; float* st_d = s_d[wid];
   float4 q = __ldg(&ix.pts[i]);
   WarpKnn w;
   w.qx = q.x; w.qy = q.y; w.qz = q.z;
   w.ld = INFINITY; w.lid = 0x7FFFFFFF; w.lpos = -1;
   w.worst_d = INFINITY; w.worst_id = 0x7FFFFFFF;
   w.k = k; w.lane = lane;
-  w.own_chunk = -1;
-  scan_chunk(ix, w, i >> 5);          // the query's own chunk first: a tight bound before the tree is touched
-  w.own_chunk = i >> 5;
-  knn_visit<0>(ix, w, 1, 0, chunk_depth);
+  // pre-scan: the 32 Morton neighbours of the query (itself included) give a tight bound before the tree is touched
+  int pre_lo = i - 16;
+  if (pre_lo > ix.n - 32) pre_lo = ix.n - 32;
+  if (pre_lo < 0) pre_lo = 0;
+  int pre_hi = pre_lo + 32 < ix.n ? pre_lo + 32 : ix.n;
+  w.pre_lo = pre_lo; w.pre_hi = pre_hi;
+  scan_range(ix, w, pre_lo, pre_hi - pre_lo, false);
+  if (ix.n > KNN_LEAF) {
+    int sp = 0;
+    int code = 0, cnt = ix.n;
+    while (true) {
+      if (code < 0) {
+        scan_range(ix, w, ~code, cnt, true);
+      } else {
+        const float4* r = ix.rec + 4 * (size_t)code;          // same address in every lane: one broadcast access
+        float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+        int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w);
+        float dl = box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), w.qx, w.qy, w.qz);
+        float dr = box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), w.qx, w.qy, w.qz);
+        int cl = split - first, cr = end - split;
+        // ranges entirely inside the pre-scan window have nothing new to offer
+        if (first >= pre_lo && split <= pre_hi) dl = INFINITY;
+        if (split >= pre_lo && end <= pre_hi) dr = INFINITY;
+        int code_l = cl <= KNN_LEAF ? ~first : split - 1;
+        int code_r = cr <= KNN_LEAF ? ~split : split;
+        bool swap = dr < dl;
+        int code_n = swap ? code_r : code_l, cnt_n = swap ? cr : cl;
+        int code_f = swap ? code_l : code_r, cnt_f = swap ? cl : cr;
+        float dn = swap ? dr : dl, df = swap ? dl : dr;
+        if (df <= w.worst_d && df < INFINITY) { st_a[sp] = code_f; st_b[sp] = cnt_f; st_d[sp] = df; ++sp; }
+        if (dn <= w.worst_d && dn < INFINITY) { code = code_n; cnt = cnt_n; continue; }
+      }
+      bool found = false;
+      __syncwarp();
+      while (sp > 0) {
+        --sp;
+        if (st_d[sp] <= w.worst_d) { code = st_a[sp]; cnt = st_b[sp]; found = true; break; }
+      }
+      if (!found) break;
+    }
+  }
   if (lane < k) {
     knn_pos[(size_t)i * k + lane] = w.lpos;
     if (knn_out_orig) knn_out_orig[(size_t)__float_as_int(q.w) * k + lane] = w.lid;
@@ -170,11 +193,7 @@ int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* norm
   if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "SurfaceNormalDataPointsFilter: knn %d outside [1,32]", knn);
   if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "SurfaceNormalDataPointsFilter: knn %d >= %d points", knn, ix.n);
   CUDA_TRY(h->knn_pos.reserve((size_t)ix.n * knn));
-  int depth = 0;
-  while ((1 << depth) < ix.first_leaf) ++depth;
-  const int chunk_depth = depth - 2;                   // build_index guarantees at least 4 leaves
-  const long long threads = (long long)ix.n * 32;
-  k_knn_warp<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(ix.view(), knn, chunk_depth, h->knn_pos.p, knn_out_orig);
+  k_knn_warp<<<(unsigned)((ix.n + KNN_WARPS - 1) / KNN_WARPS), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
   k_normals_from_knn<<<(ix.n + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
