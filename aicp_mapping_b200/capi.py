@@ -91,7 +91,7 @@ def lib():
         L.aicp_b200_autotune_ratio.argtypes = [C.c_float]
         L.aicp_b200_autotune_ratio.restype = C.c_float
         L.aicp_b200_register_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_void_p),
-                                               C.POINTER(i64), fp, fp, C.POINTER(Stats)]
+                                               C.POINTER(i64), fp, C.c_int, fp, C.POINTER(Stats), C.POINTER(C.c_int32), fp]
         L.aicp_b200_comm_unique_id.argtypes = [C.c_void_p]
         L.aicp_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.aicp_b200_comm_destroy.argtypes = [C.c_void_p]

@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <atomic>
 #include <string>
+#include <thread>
 
 #include "handle.cuh"
 
@@ -120,6 +122,10 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   if (!h) return AICP_B200_OK;
   cudaSetDevice(h->device);
   if (h->comm) aicp_b200_comm_destroy(hh);
+  for (Handle* w : h->workers) aicp_b200_destroy(reinterpret_cast<aicp_b200_handle*>(w));
+  h->workers.clear();
+  if (h->done_ev) cudaEventDestroy(h->done_ev);
+  for (int i = 0; i < 2; ++i) if (h->batch_ev[i]) cudaEventDestroy(h->batch_ev[i]);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_rec.release(); h->normals.release(); h->knn_pos.release();
   h->read_in.release(); h->read_ix.release(); h->read0.release(); h->read_out.release(); h->read_init.release();
@@ -349,24 +355,69 @@ float aicp_b200_autotune_ratio(float overlap_pct) {
 }
 
 int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
-                             const float* const* read_xyzw, const int64_t* n_read, const float* ratios, float* out_T,
-                             aicp_b200_stats* stats) {
+                             const float* const* read_xyzw, const int64_t* n_read, const float* ratios, int streams,
+                             float* out_T, aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   H_CHECK(h);
   if (n_pairs < 0 || (n_pairs > 0 && (!ref_xyzw || !n_ref || !read_xyzw || !n_read || !out_T)))
     return fail(h, AICP_B200_ERR_BAD_ARG, "register_batch: bad arguments");
-  int rc = load_config(h);
+  if (batch_ms) *batch_ms = 0.f;
+  if (n_pairs == 0) return AICP_B200_OK;
+  int rc = load_config(h);     // one parse for the whole batch
   if (rc) return rc;
-  bool from_file = h->cfg_from_file;
-  h->cfg_from_file = false;                 // one parse for the whole batch
-  const float base_ratio = h->cfg.ratio;
-  for (int64_t i = 0; i < n_pairs && rc == AICP_B200_OK; ++i) {
-    if (ratios) h->cfg.ratio = ratios[i];
-    rc = aicp_b200_register(hh, ref_xyzw[i], n_ref[i], read_xyzw[i], n_read[i], nullptr, out_T + 16 * i, stats ? stats + i : nullptr);
+  if (streams <= 0) streams = 4;
+  if (streams > 32) streams = 32;
+  if ((int64_t)streams > n_pairs) streams = (int)n_pairs;
+  while ((int)h->workers.size() < streams) {
+    aicp_b200_handle* w = nullptr;
+    rc = aicp_b200_create(nullptr, h->device, &w);
+    if (rc) return fail(h, rc, "register_batch: cannot create worker: %s", aicp_b200_last_error(nullptr));
+    Handle* wh = reinterpret_cast<Handle*>(w);
+    if (cudaEventCreate(&wh->done_ev) != cudaSuccess) return fail(h, AICP_B200_ERR_CUDA, "register_batch: event creation failed");
+    h->workers.push_back(wh);
   }
-  h->cfg.ratio = base_ratio;
-  h->cfg_from_file = from_file;
-  return rc;
+  if (!h->batch_ev[0]) { CUDA_TRY(cudaEventCreate(&h->batch_ev[0])); CUDA_TRY(cudaEventCreate(&h->batch_ev[1])); }
+  // device-side span: every worker stream starts after batch_ev[0]; the master stream ends after every worker
+  CUDA_TRY(cudaEventRecord(h->batch_ev[0], h->stream));
+  for (int w = 0; w < streams; ++w) {
+    Handle* wh = h->workers[w];
+    wh->cfg = h->cfg; wh->cfg_from_file = false;
+    wh->profiling = h->profiling; wh->trace_matches = false;
+    CUDA_TRY(cudaStreamWaitEvent(wh->stream, h->batch_ev[0], 0));
+  }
+  std::atomic<int64_t> next(0);
+  std::atomic<int> first_err(0);
+  std::vector<std::string> errs((size_t)streams);
+  auto work = [&](int w) {
+    Handle* wh = h->workers[w];
+    cudaSetDevice(wh->device);
+    for (;;) {
+      int64_t i = next.fetch_add(1);
+      if (i >= n_pairs) break;
+      if (ratios) wh->cfg.ratio = ratios[i];
+      int r = aicp_b200_register(reinterpret_cast<aicp_b200_handle*>(wh), ref_xyzw[i], n_ref[i], read_xyzw[i], n_read[i], nullptr,
+                                 out_T + 16 * i, stats ? stats + i : nullptr);
+      if (status) status[i] = r;
+      if (r) {
+        int expected = 0;
+        if (first_err.compare_exchange_strong(expected, r)) errs[(size_t)w] = wh->last_error;
+      }
+    }
+    cudaEventRecord(wh->done_ev, wh->stream);
+  };
+  std::vector<std::thread> threads;
+  for (int w = 1; w < streams; ++w) threads.emplace_back(work, w);
+  work(0);
+  for (auto& t : threads) t.join();
+  for (int w = 0; w < streams; ++w) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->workers[w]->done_ev, 0));
+  CUDA_TRY(cudaEventRecord(h->batch_ev[1], h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (batch_ms) CUDA_TRY(cudaEventElapsedTime(batch_ms, h->batch_ev[0], h->batch_ev[1]));
+  if (first_err.load()) {
+    for (const std::string& e : errs) if (!e.empty()) { h->last_error = "register_batch: " + e; break; }
+    return first_err.load();
+  }
+  return AICP_B200_OK;
 }
 
 }  // extern "C"

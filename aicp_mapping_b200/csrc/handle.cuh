@@ -104,6 +104,12 @@ struct Handle {
   DevBuf<unsigned long long> ovl_counts;
 
   Comm* comm = nullptr;
+
+  // batch workers: one child handle (own stream + buffers) per concurrent registration
+  std::vector<Handle*> workers;
+  cudaEvent_t batch_ev[2] = {nullptr, nullptr};
+  cudaEvent_t wait_ev = nullptr;     // set while a batch runs: the worker's first stream op waits on it
+  cudaEvent_t done_ev = nullptr;
 };
 
 // ---- index.cu

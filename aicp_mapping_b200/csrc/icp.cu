@@ -409,7 +409,10 @@ static int ensure_state(Handle* h) {
     CUDA_TRY(cudaMemsetAsync(h->st, 0, sizeof(DeviceState), h->stream));
   }
   if (!h->st_host) CUDA_TRY(cudaMallocHost((void**)&h->st_host, sizeof(DeviceState)));
-  CUDA_TRY(h->hist.reserve(AICP_HIST_BINS));
+  if (h->hist.cap < AICP_HIST_BINS) {
+    CUDA_TRY(h->hist.reserve(AICP_HIST_BINS));
+    CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * h->hist.cap, h->stream));   // cudaMalloc does not zero
+  }
   static_assert(AICP_HIST_BINS == 2048, "select_pick assumes 256 threads x 8 bins");
   return AICP_B200_OK;
 }
@@ -470,6 +473,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     memcpy(h->st_host->T_init, init_T_host, 16 * sizeof(float));
     CUDA_TRY(cudaMemcpyAsync(h->st->T_init, h->st_host->T_init, 16 * sizeof(float), cudaMemcpyHostToDevice, s));
   }
+  CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * AICP_HIST_BINS, s));
   k_loop_init<<<1, 32, 0, s>>>(h->st, h->ref_ix.meta, (long long)n_ref, init_T_host ? 1 : 0);
   if (rebuild_reference) {
     int n4 = 4 * (h->ref_ix.n - 1);

@@ -199,6 +199,29 @@ class B200Registration:
         pq, nq, keep_q = capi.ptr_and_count(cloud_read)
         return self._register(pr, nr, pq, nq, init_T)
 
+    def registerBatch(self, pairs, ratios=None, streams=0):
+        """aicp_b200_register_batch: `pairs` is a list of (cloud_ref, cloud_read); independent pairs are registered
+        concurrently on `streams` CUDA streams.  Returns (T [n,4,4], stats list, status array, batch_ms)."""
+        n = len(pairs)
+        keep, refs, reads = [], (C.c_void_p * n)(), (C.c_void_p * n)()
+        n_ref, n_read = (C.c_int64 * n)(), (C.c_int64 * n)()
+        for i, (r, q) in enumerate(pairs):
+            pr, nr, kr = capi.ptr_and_count(r)
+            pq, nq, kq = capi.ptr_and_count(q)
+            refs[i], reads[i], n_ref[i], n_read[i] = pr, pq, nr, nq
+            keep.append((kr, kq))
+        T = np.zeros((n, 16), dtype=np.float32)
+        stats = (capi.Stats * n)()
+        status = np.zeros(n, dtype=np.int32)
+        ms = C.c_float()
+        rat = np.ascontiguousarray(ratios, dtype=np.float32) if ratios is not None else None
+        rc = self._lib.aicp_b200_register_batch(self._h, n, refs, n_ref, reads, n_read,
+                                                rat.ctypes.data_as(C.POINTER(C.c_float)) if rat is not None else None,
+                                                int(streams), T.ctypes.data_as(C.POINTER(C.c_float)), stats,
+                                                status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
+        self._check(rc)
+        return np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4), stats, status, float(ms.value)
+
     def getReferenceNormals(self):
         n = int(self.stats.n_ref)
         out = np.zeros((n, 4), dtype=np.float32)

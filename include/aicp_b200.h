@@ -164,10 +164,18 @@ int aicp_b200_overlap(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref,
 float aicp_b200_autotune_ratio(float overlap_pct);
 
 /* ---- batched registration (BASELINE.json config 5: independent pairs, no communication) --------------------------
- * pairs share one configuration; ref/read arrays hold n_pairs pointers; out_T: n_pairs x 16; stats nullable array. */
+ * replaces the bash sweeps that call the pairwise tool once per pair (bash/run_registration_validation.sh:7-21,
+ * bash/run_registration.sh:8-36) and KITTI-sequence style frame-to-frame runs.
+ * The pairs are independent, so they are registered CONCURRENTLY on `streams` CUDA streams of the handle's device (one
+ * worker handle + host thread per stream; a single 128k-point registration does not fill a B200).
+ * All pairs share the handle's configuration except the trimmed ratio, which may be given per pair (auto-tuned from each
+ * pair's overlap).  ref/read arrays hold n_pairs pointers (host or device); out_T: n_pairs x 16; stats: nullable array
+ * of n_pairs; status: nullable array of n_pairs per-pair return codes (a failing pair does not stop the batch; the
+ * function returns the first non-zero code).  batch_ms (nullable): device time from the first kernel of the batch to
+ * the last, measured with CUDA events across all streams.  streams <= 0 selects the default (4). */
 int aicp_b200_register_batch(aicp_b200_handle* h, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
                              const float* const* read_xyzw, const int64_t* n_read, const float* ratios /*nullable*/,
-                             float* out_T, aicp_b200_stats* stats /*nullable, n_pairs*/);
+                             int streams, float* out_T, aicp_b200_stats* stats, int32_t* status, float* batch_ms);
 
 /* ---- multi-GPU single registration (BASELINE.json config 4: reading sharded, reference replicated) ---------------
  * nccl_unique_id: the 128-byte ncclUniqueId obtained on rank 0 with aicp_b200_comm_unique_id and broadcast by the

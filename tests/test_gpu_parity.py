@@ -253,6 +253,28 @@ def test_device_pointers_are_used_in_place(reg, orc):
     assert np.array_equal(u32(T_host), u32(T_dev))
 
 
+def test_register_batch_concurrent_streams_equals_sequential(reg, orc):
+    """Independent pairs registered concurrently on 3 streams give bit-identical transforms to one-by-one calls, and a
+    failing pair (identical clouds -> ConvergenceError) does not stop the others."""
+    pairs = [synth.make_pair(5, t, 4000 + 500 * t) for t in range(5)]
+    ratios = [0.7, 0.6, 0.5, 0.65, 0.7]
+    reg.setConfig(max_iterations=20)
+    seq = []
+    for p, r in zip(pairs, ratios):
+        reg.setConfig(ratio=r)
+        seq.append(reg.registerClouds(p["ref"], p["read"]))
+    reg.setConfig(ratio=0.7)
+    T, stats, status, ms = reg.registerBatch([(p["ref"], p["read"]) for p in pairs], ratios=ratios, streams=3)
+    assert ms > 0 and not status.any()
+    for a, b in zip(seq, T):
+        assert np.array_equal(u32(a), u32(b))
+    o = orc.icp(pairs[2]["ref"], pairs[2]["read"], orc.default_config(ratio=0.5, threads=NCPU))
+    assert stats[2].iterations == o.iterations and np.array_equal(u32(T[2]), u32(o.T))
+    bad = [(pairs[0]["ref"], pairs[0]["read"]), (pairs[1]["ref"], pairs[1]["ref"]), (pairs[2]["ref"], pairs[2]["read"])]
+    with pytest.raises(capi.AicpError, match="NO_VALID_MATCH"):
+        reg.registerBatch(bad, ratios=ratios[:3], streams=2)
+
+
 # ---- overlap -------------------------------------------------------------------------------------------------------
 def test_overlap_parity(orc, pair_cache):
     ov = ab.B200Overlap()
