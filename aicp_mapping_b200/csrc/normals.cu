@@ -6,10 +6,12 @@
 // eigenvalue, density = knn / (4/3 pi r_max^3).
 //
 // Two kernels:
-//   k_knn_warp          one WARP per query point.  The sorted candidate list (32 entries, the first knn matter) lives
-//                       one entry per lane; candidates arrive 32 at a time as a coalesced 512-byte chunk of the
-//                       Morton-ordered cloud, each lane evaluates one, and accepted ones are inserted with a ballot +
-//                       shuffle-up (warp-shuffle top-k).  The walk over the radix tree is warp-uniform (every lane reads
+//   k_knn_warp          one WARP per run of 16 consecutive (Morton-ordered) query points, one query at a time; the list
+//                       of a query seeds the next one, whose neighbourhood is almost the same, so the pruning bound is
+//                       near-final before the tree is touched.  The k best candidates live one per lane; candidates arrive 32 at a
+//                       time as a coalesced 512-byte chunk of the Morton-ordered cloud, each lane evaluates one, and
+//                       an accepted one replaces the current worst entry, which is re-located with warp reductions
+//                       (warp-shuffle top-k); a 15-round bitonic shuffle sort orders the list at the end.  The walk over the radix tree is warp-uniform (every lane reads
 //                       the same 64-byte node record, a broadcast access), nearest child first, pruning against the
 //                       current k-th distance; subtrees of <= 32 points are scanned as one chunk.  The 32 Morton
 //                       neighbours of the query are scanned first, so the bound is tight before the tree is touched.
@@ -28,33 +30,44 @@ struct WarpKnn {
   int lpos;        // position in the Morton-ordered array
   float worst_d;   // entry k-1 (uniform)
   int worst_id;
+  int worst_lane;
   int k;
-  int pre_lo, pre_hi;   // positions already offered by the pre-scan (never offered twice)
   int lane;
 };
 
-__device__ __forceinline__ void warp_insert(WarpKnn& w, float cd, int cid, int cpos) {
-  bool less = cand_less(cd, cid, w.ld, w.lid);
-  unsigned m = __ballot_sync(0xFFFFFFFFu, less);
-  if (m == 0) return;
-  int p = __ffs(m) - 1;
-  float ud = __shfl_up_sync(0xFFFFFFFFu, w.ld, 1);
-  int uid = __shfl_up_sync(0xFFFFFFFFu, w.lid, 1);
-  int upos = __shfl_up_sync(0xFFFFFFFFu, w.lpos, 1);
-  if (w.lane > p) { w.ld = ud; w.lid = uid; w.lpos = upos; }
-  else if (w.lane == p) { w.ld = cd; w.lid = cid; w.lpos = cpos; }
-  w.worst_d = __shfl_sync(0xFFFFFFFFu, w.ld, w.k - 1);
-  w.worst_id = __shfl_sync(0xFFFFFFFFu, w.lid, w.k - 1);
+// The k live entries sit UNSORTED in lanes 0..k-1; only the worst one (largest (d2, id)) is tracked.  An accepted
+// candidate replaces the worst entry, then the new worst is found with two warp reductions: ~15 instructions per
+// insertion instead of a shuffle-up insertion into a sorted list.  The list is sorted once, at the end.
+__device__ __forceinline__ void find_worst(WarpKnn& w) {
+  const bool live = w.lane < w.k;
+  unsigned key = live ? __float_as_uint(w.ld) : 0u;           // d2 >= 0: the bit pattern orders like the value
+  unsigned kmax = __reduce_max_sync(0xFFFFFFFFu, key);
+  unsigned tie = __ballot_sync(0xFFFFFFFFu, live && key == kmax);
+  w.worst_d = __uint_as_float(kmax);
+  if ((tie & (tie - 1)) == 0) {                                // the usual case: a single farthest entry
+    w.worst_lane = __ffs(tie) - 1;
+    w.worst_id = __shfl_sync(0xFFFFFFFFu, w.lid, w.worst_lane);
+  } else {                                                     // equal distances: the largest index is the worst
+    int idkey = ((tie >> w.lane) & 1u) ? w.lid : -1;
+    w.worst_id = __reduce_max_sync(0xFFFFFFFFu, idkey);
+    w.worst_lane = __ffs(__ballot_sync(0xFFFFFFFFu, idkey == w.worst_id)) - 1;
+  }
 }
 
-// up to 32 consecutive Morton-ordered points [first, first+cnt): one candidate per lane, one coalesced load
-__device__ __forceinline__ void scan_range(const IndexView& ix, WarpKnn& w, int first, int cnt, bool exclude_pre) {
-  int pos = first + w.lane;
+__device__ __forceinline__ void warp_insert(WarpKnn& w, float cd, int cid, int cpos) {
+  if (w.lane == w.worst_lane) { w.ld = cd; w.lid = cid; w.lpos = cpos; }
+  find_worst(w);
+}
+
+// up to 32 consecutive Morton-ordered points [first, first+cnt): one candidate per lane, one coalesced load.
+// A candidate that beats the current worst entry is inserted unless it is already in the list (the list is seeded with
+// points that the walk meets again: the Morton window of the first query of a run, the previous query's neighbours after).
+__device__ __forceinline__ void scan_range(const IndexView& ix, WarpKnn& w, int first, int cnt) {
   float d = INFINITY;
   int id = 0x7FFFFFFF;
-  bool ok = w.lane < cnt && !(exclude_pre && pos >= w.pre_lo && pos < w.pre_hi);
+  const bool ok = w.lane < cnt;
   if (ok) {
-    float4 p = __ldg(&ix.pts[pos]);
+    float4 p = __ldg(&ix.pts[first + w.lane]);
     id = __float_as_int(p.w);
     d = d2_f(w.qx, w.qy, w.qz, p.x, p.y, p.z);
   }
@@ -64,12 +77,34 @@ __device__ __forceinline__ void scan_range(const IndexView& ix, WarpKnn& w, int 
     m &= m - 1;
     float cd = __shfl_sync(0xFFFFFFFFu, d, b);
     int cid = __shfl_sync(0xFFFFFFFFu, id, b);
-    if (cand_less(cd, cid, w.worst_d, w.worst_id)) warp_insert(w, cd, cid, first + b);
+    if (!cand_less(cd, cid, w.worst_d, w.worst_id)) continue;
+    if (__any_sync(0xFFFFFFFFu, w.lane < w.k && w.lid == cid)) continue;      // already a neighbour
+    warp_insert(w, cd, cid, first + b);
   }
+}
+
+// ascending bitonic sort of one (d2, id, pos) entry per lane.  (d2, id) is packed into one 64-bit key -- d2 >= 0, so
+// its bit pattern orders like the value -- which makes a compare-exchange round 3 shuffles + one 64-bit compare.
+// ids are unique, so the order is total (padding entries are all (inf, INT_MAX) and never swap among themselves).
+__device__ __forceinline__ void warp_sort(WarpKnn& w) {
+  unsigned long long key = ((unsigned long long)__float_as_uint(w.ld) << 32) | (unsigned)w.lid;
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long pk = __shfl_xor_sync(0xFFFFFFFFu, key, j);
+      int ppos = __shfl_xor_sync(0xFFFFFFFFu, w.lpos, j);
+      bool keep_min = ((w.lane & k) == 0) == ((w.lane & j) == 0);
+      if (keep_min ? (pk < key) : (pk > key)) { key = pk; w.lpos = ppos; }
+    }
+  }
+  w.ld = __uint_as_float((unsigned)(key >> 32));
+  w.lid = (int)(unsigned)key;
 }
 
 #define KNN_WARPS 8
 #define KNN_LEAF 32
+#define KNN_RUN 16        // consecutive Morton-ordered queries handled by one warp
 
 __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k, int* __restrict__ knn_pos,
                                                              int* __restrict__ knn_out_orig) {
@@ -77,59 +112,75 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k
   __shared__ int s_b[KNN_WARPS][AICP_STACK];
   __shared__ float s_d[KNN_WARPS][AICP_STACK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int i = blockIdx.x * KNN_WARPS + wid;      // query = Morton position
-  if (i >= ix.n) return;
+  const int run = blockIdx.x * KNN_WARPS + wid;
+  const int i0 = run * KNN_RUN;
+  if (i0 >= ix.n) return;
+  const int i1 = i0 + KNN_RUN < ix.n ? i0 + KNN_RUN : ix.n;
   int* st_a = s_a[wid]; int* st_b = s_b[wid]; float* st_d = s_d[wid];
-  float4 q = __ldg(&ix.pts[i]);
   WarpKnn w;
-  w.qx = q.x; w.qy = q.y; w.qz = q.z;
-  w.ld = INFINITY; w.lid = 0x7FFFFFFF; w.lpos = -1;
-  w.worst_d = INFINITY; w.worst_id = 0x7FFFFFFF;
   w.k = k; w.lane = lane;
-  // pre-scan: the 32 Morton neighbours of the query (itself included) give a tight bound before the tree is touched
-  int pre_lo = i - 16;
-  if (pre_lo > ix.n - 32) pre_lo = ix.n - 32;
-  if (pre_lo < 0) pre_lo = 0;
-  int pre_hi = pre_lo + 32 < ix.n ? pre_lo + 32 : ix.n;
-  w.pre_lo = pre_lo; w.pre_hi = pre_hi;
-  scan_range(ix, w, pre_lo, pre_hi - pre_lo, false);
-  if (ix.n > KNN_LEAF) {
-    int sp = 0;
-    int code = 0, cnt = ix.n;
-    while (true) {
-      if (code < 0) {
-        scan_range(ix, w, ~code, cnt, true);
-      } else {
-        const float4* r = ix.rec + 4 * (size_t)code;          // same address in every lane: one broadcast access
-        float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
-        int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w);
-        float dl = box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), w.qx, w.qy, w.qz);
-        float dr = box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), w.qx, w.qy, w.qz);
-        int cl = split - first, cr = end - split;
-        // ranges entirely inside the pre-scan window have nothing new to offer
-        if (first >= pre_lo && split <= pre_hi) dl = INFINITY;
-        if (split >= pre_lo && end <= pre_hi) dr = INFINITY;
-        int code_l = cl <= KNN_LEAF ? ~first : split - 1;
-        int code_r = cr <= KNN_LEAF ? ~split : split;
-        bool swap = dr < dl;
-        int code_n = swap ? code_r : code_l, cnt_n = swap ? cr : cl;
-        int code_f = swap ? code_l : code_r, cnt_f = swap ? cl : cr;
-        float dn = swap ? dr : dl, df = swap ? dl : dr;
-        if (df <= w.worst_d && df < INFINITY) { st_a[sp] = code_f; st_b[sp] = cnt_f; st_d[sp] = df; ++sp; }
-        if (dn <= w.worst_d && dn < INFINITY) { code = code_n; cnt = cnt_n; continue; }
+  w.ld = INFINITY; w.lid = 0x7FFFFFFF; w.lpos = -1;
+  for (int i = i0; i < i1; ++i) {
+    float4 q = __ldg(&ix.pts[i]);
+    w.qx = q.x; w.qy = q.y; w.qz = q.z;
+    if (i == i0) {
+      // first query of the run: seed with the 32 Morton neighbours of the query (itself included) and keep the k nearest
+      int pre_lo = i - 16;
+      if (pre_lo > ix.n - 32) pre_lo = ix.n - 32;
+      if (pre_lo < 0) pre_lo = 0;
+      int pre_hi = pre_lo + 32 < ix.n ? pre_lo + 32 : ix.n;
+      if (pre_lo + lane < pre_hi) {
+        float4 p = __ldg(&ix.pts[pre_lo + lane]);
+        w.lid = __float_as_int(p.w);
+        w.lpos = pre_lo + lane;
+        w.ld = d2_f(w.qx, w.qy, w.qz, p.x, p.y, p.z);
       }
-      bool found = false;
-      __syncwarp();
-      while (sp > 0) {
-        --sp;
-        if (st_d[sp] <= w.worst_d) { code = st_a[sp]; cnt = st_b[sp]; found = true; break; }
-      }
-      if (!found) break;
+      warp_sort(w);
+    } else if (lane < k) {
+      // next query of the run: its neighbourhood is almost the previous one, so the previous list re-measured from the
+      // new query is a near-final bound before the tree is touched
+      float4 p = __ldg(&ix.pts[w.lpos]);
+      w.ld = d2_f(w.qx, w.qy, w.qz, p.x, p.y, p.z);
     }
-  }
-  if (lane < k) {
-    knn_pos[(size_t)i * k + lane] = w.lpos;
-    if (knn_out_orig) knn_out_orig[(size_t)__float_as_int(q.w) * k + lane] = w.lid;
+    if (lane >= k) { w.ld = INFINITY; w.lid = 0x7FFFFFFF; w.lpos = -1; }
+    find_worst(w);
+    if (ix.n > KNN_LEAF) {
+      int sp = 0;
+      int code = 0, cnt = ix.n;
+      while (true) {
+        if (code < 0) {
+          scan_range(ix, w, ~code, cnt);
+        } else {
+          const float4* r = ix.rec + 4 * (size_t)code;          // same address in every lane: one broadcast access
+          float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+          int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w);
+          float dl = box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), w.qx, w.qy, w.qz);
+          float dr = box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), w.qx, w.qy, w.qz);
+          int cl = split - first, cr = end - split;
+          int code_l = cl <= KNN_LEAF ? ~first : split - 1;
+          int code_r = cr <= KNN_LEAF ? ~split : split;
+          bool swap = dr < dl;
+          int code_n = swap ? code_r : code_l, cnt_n = swap ? cr : cl;
+          int code_f = swap ? code_l : code_r, cnt_f = swap ? cl : cr;
+          float dn = swap ? dr : dl, df = swap ? dl : dr;
+          if (df <= w.worst_d) { st_a[sp] = code_f; st_b[sp] = cnt_f; st_d[sp] = df; ++sp; }
+          if (dn <= w.worst_d) { code = code_n; cnt = cnt_n; continue; }
+        }
+        bool found = false;
+        while (sp > 0) {
+          --sp;
+          if (st_d[sp] <= w.worst_d) { code = st_a[sp]; cnt = st_b[sp]; found = true; break; }
+        }
+        if (!found) break;
+      }
+    } else {
+      scan_range(ix, w, 0, ix.n);
+    }
+    warp_sort(w);                        // neighbours are reported in (d2, id) order
+    if (lane < k) {
+      knn_pos[(size_t)i * k + lane] = w.lpos;
+      if (knn_out_orig) knn_out_orig[(size_t)__float_as_int(q.w) * k + lane] = w.lid;
+    }
   }
 }
 
@@ -193,7 +244,7 @@ int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* norm
   if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "SurfaceNormalDataPointsFilter: knn %d outside [1,32]", knn);
   if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "SurfaceNormalDataPointsFilter: knn %d >= %d points", knn, ix.n);
   CUDA_TRY(h->knn_pos.reserve((size_t)ix.n * knn));
-  k_knn_warp<<<(unsigned)((ix.n + KNN_WARPS - 1) / KNN_WARPS), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
+  k_knn_warp<<<(unsigned)((ix.n + KNN_WARPS * KNN_RUN - 1) / (KNN_WARPS * KNN_RUN)), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
   k_normals_from_knn<<<(ix.n + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;
