@@ -124,6 +124,12 @@ int run_trim_stage(Handle* h, const float* d2_dev, int64_t n, float ratio, float
 // ---- overlap.cu
 int run_overlap(Handle* h, const float4* ref, int64_t n_ref, const double* ref_origin, const float4* read, int64_t n_read,
                 const double* read_origin, double resolution, float* overlap_pct, int64_t* counts);
+// ---- comm.cu (sharded registration; NCCL is loaded at run time, the library has no link-time dependency on it)
+int comm_allreduce_u32(Handle* h, unsigned int* buf, size_t count);
+int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count);
+unsigned long long* comm_limbs(Handle* h);
+long long comm_total_reading(Handle* h);
+int comm_begin_registration(Handle* h, long long n_read_local);
 // ---- config_yaml.cpp
 int parse_icp_yaml(const char* path, aicp_b200_icp_config* cfg, std::string* err);
 void default_icp_config(aicp_b200_icp_config* cfg);

