@@ -275,6 +275,23 @@ def test_register_batch_concurrent_streams_equals_sequential(reg, orc):
         reg.registerBatch(bad, ratios=ratios[:3], streams=2)
 
 
+def test_cpp_adapter_demo():
+    """The C++ adapters (include/aicp_b200_adapter.hpp) compiled against the reference's own abstract plug-in headers:
+    overlap -> updateConfigParams -> registerClouds -> getOutputReading through the factories, as App::runAicpPipeline does.
+    The binary is built in the build container (tests/stubs/build_demo.sh needs the reference's headers) and travels."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs", "build", "adapter_demo")
+    if not os.path.exists(exe):
+        pytest.skip("tests/stubs/build/adapter_demo was not built (needs the reference headers at build time)")
+    r = subprocess.run([exe, os.path.join(GOLDEN, "icp_autotuned_default.yaml"), "40"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("OK ")][0]
+    T = np.array([float(x) for x in line.split("T=")[1].split()]).reshape(4, 4).T
+    assert 4 <= int(line.split("iterations=")[1].split()[0]) <= 20
+    # the demo's reading is the reference rotated by 0.02 rad about z and shifted by (0.05, -0.03): T undoes it
+    assert abs(np.arctan2(T[1, 0], T[0, 0]) + 0.02) < 2e-3 and np.abs(T[:2, 3] - [-0.0506, 0.0290]).max() < 5e-3
+
+
 # ---- overlap -------------------------------------------------------------------------------------------------------
 def test_overlap_parity(orc, pair_cache):
     ov = ab.B200Overlap()
