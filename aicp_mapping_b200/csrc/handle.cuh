@@ -27,28 +27,22 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// per-index reduction results (device)
-struct IndexMeta {
-  int bmin[3], bmax[3];          // ordered-int encoded bounding box
-  long long csum[3];             // sum of round(coord * 2^16)
-  int nonfinite;
-  int pad;
-};
-
 // Morton-ordered spatial index over one cloud
 struct SpatialIndex {
   DevBuf<float4> pts;            // Morton order, .w = original index
   DevBuf<float4> rec;            // 4 float4 per internal node of the radix tree (see search.cuh)
   DevBuf<int4> node_meta;        // (first, split, end, -) per internal node, build-time scratch
   DevBuf<unsigned int> keys, keys_alt, vals, vals_alt;
-  DevBuf<int> flags;             // bottom-up refit arrival counters
+  DevBuf<int> flags;             // bottom-up refit arrival counters, parent links
+  DevBuf<int> owner;             // per point: lowest node with > 8 (first n) resp. > 32 (next n) points above it
+  DevBuf<int2> cell;             // per internal node: (a Morton key of the node, common-prefix length in clz units)
   DevBuf<unsigned char> sort_tmp;
   IndexMeta* meta = nullptr;     // device
   int n = 0;
-  IndexView view() const { return IndexView{pts.p, rec.p, n}; }
+  IndexView view() const { return IndexView{pts.p, rec.p, owner.p, owner.p + n, cell.p, meta, nullptr, n}; }
   void release() {
     pts.release(); rec.release(); node_meta.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release();
-    flags.release(); sort_tmp.release();
+    flags.release(); owner.release(); cell.release(); sort_tmp.release();
     if (meta) cudaFree(meta);
     meta = nullptr;
   }

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __res
     float3 p = xform_f(sT, r.x, r.y, r.z);
     int pos; float d;
     const int iter = st->iter;
-    nn_search(ix, p.x, p.y, p.z, &pos, &d, iter > 0 ? match_pos[i] : -1);
+    if (iter > 0) nn_search_up(ix, p.x, p.y, p.z, match_pos[i], &pos, &d);
+    else nn_search(ix, p.x, p.y, p.z, &pos, &d);
     match_pos[i] = pos;
     d2out[i] = d;
     if (trace_idx) trace_idx[(size_t)iter * n + __float_as_int(r.w)] = __float_as_int(__ldg(&ix.pts[pos]).w);
@@ -545,7 +546,8 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
 
   if (h->comm && (rc = comm_begin_registration(h, n_read))) return rc;
-  IndexView cix{h->refc_pts.p, h->refc_rec.p, h->ref_ix.n};
+  IndexView cix{h->refc_pts.p, h->refc_rec.p, h->ref_ix.owner.p, h->ref_ix.owner.p + h->ref_ix.n, h->ref_ix.cell.p, h->ref_ix.meta,
+                h->st->mu, h->ref_ix.n};      // queries are in the centred frame: + mu reaches the frame of the keys
   LoopParams lp{cfg.ratio, cfg.max_iterations, cfg.min_diff_rot, cfg.min_diff_trans, cfg.smooth_length};
   const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
   for (int it = 0; it < cfg.max_iterations; ++it) {

@@ -62,27 +62,23 @@ __global__ void __launch_bounds__(256) k_index_stats(const float4* __restrict__ 
   }
 }
 
-__device__ __forceinline__ unsigned int spread10(unsigned int v) {
-  v = (v | (v << 16)) & 0x030000FFu;
-  v = (v | (v << 8)) & 0x0300F00Fu;
-  v = (v | (v << 4)) & 0x030C30C3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
+// quantisation parameters from the bounding box (one thread; the searches read them back from meta)
+__global__ void k_quant_params(IndexMeta* m) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float lx = ordered_to_float(m->bmin[0]), ly = ordered_to_float(m->bmin[1]), lz = ordered_to_float(m->bmin[2]);
+  float ex = ordered_to_float(m->bmax[0]) - lx, ey = ordered_to_float(m->bmax[1]) - ly, ez = ordered_to_float(m->bmax[2]) - lz;
+  float ext = fmaxf(ex, fmaxf(ey, ez));
+  m->qlo[0] = lx; m->qlo[1] = ly; m->qlo[2] = lz;
+  m->qscale = ext > 0.f ? 1023.0f / ext : 0.f;
 }
 
 __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ pts, int n, const IndexMeta* __restrict__ m,
                                                      unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float lx = ordered_to_float(m->bmin[0]), ly = ordered_to_float(m->bmin[1]), lz = ordered_to_float(m->bmin[2]);
-  float ex = ordered_to_float(m->bmax[0]) - lx, ey = ordered_to_float(m->bmax[1]) - ly, ez = ordered_to_float(m->bmax[2]) - lz;
-  float ext = fmaxf(ex, fmaxf(ey, ez));
-  float scale = ext > 0.f ? 1023.0f / ext : 0.f;
+  const float lx = m->qlo[0], ly = m->qlo[1], lz = m->qlo[2], scale = m->qscale;
   float4 p = __ldg(&pts[i]);
-  int qx = min(1023, max(0, (int)((p.x - lx) * scale)));
-  int qy = min(1023, max(0, (int)((p.y - ly) * scale)));
-  int qz = min(1023, max(0, (int)((p.z - lz) * scale)));
-  keys[i] = spread10((unsigned)qx) | (spread10((unsigned)qy) << 1) | (spread10((unsigned)qz) << 2);
+  keys[i] = morton_key(morton_quant(p.x, lx, scale), morton_quant(p.y, ly, scale), morton_quant(p.z, lz, scale));
   vals[i] = (unsigned)i;
 }
 
@@ -106,7 +102,8 @@ __device__ __forceinline__ int delta(const unsigned int* __restrict__ keys, int 
 }
 
 __global__ void __launch_bounds__(256) k_radix_tree(const unsigned int* __restrict__ keys, int n, int4* __restrict__ meta,
-                                                    int* __restrict__ parent_int, int* __restrict__ parent_leaf) {
+                                                    int* __restrict__ parent_int, int* __restrict__ parent_leaf,
+                                                    int* __restrict__ owner8, int* __restrict__ owner32, int2* __restrict__ cell) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -125,9 +122,24 @@ __global__ void __launch_bounds__(256) k_radix_tree(const unsigned int* __restri
   } while (t > 1);
   int gamma = i + s * d + min(d, 0);
   int first = min(i, j), last = max(i, j);
-  meta[i] = make_int4(first, gamma + 1, last + 1, 0);
+  // dnode < 32: the node is a Morton cell (all keys sharing a prefix of the 30 key bits) -- the property the bottom-up
+  // searches rely on to stop early; dnode >= 32 means the split is among equal keys (position bits) and proves nothing
+  meta[i] = make_int4(first, gamma + 1, last + 1, dnode < 32 ? 1 : 0);
+  cell[i] = make_int2((int)__ldg(&keys[first]), dnode);
   if (first == gamma) parent_leaf[gamma] = (i << 1); else parent_int[gamma] = (i << 1);
   if (last == gamma + 1) parent_leaf[gamma + 1] = (i << 1) | 1; else parent_int[gamma + 1] = (i << 1) | 1;
+  // owner of a point = the lowest node with MORE than LEAF points above it (code = node << 1 | side): where the
+  // bottom-up searches start.  Written by that node for each child that is small enough to be scanned directly.
+  const int split = gamma + 1, end = last + 1, count = end - first;
+  const int cl = split - first, cr = end - split;
+  if (count > AICP_LEAF) {
+    if (cl <= AICP_LEAF) for (int p = first; p < split; ++p) owner8[p] = (i << 1);
+    if (cr <= AICP_LEAF) for (int p = split; p < end; ++p) owner8[p] = (i << 1) | 1;
+  }
+  if (count > 32) {
+    if (cl <= 32) for (int p = first; p < split; ++p) owner32[p] = (i << 1);
+    if (cr <= 32) for (int p = split; p < end; ++p) owner32[p] = (i << 1) | 1;
+  }
 }
 
 // One thread per point: start from the point's own box and climb.  At every node the first child to arrive stops, the
@@ -149,8 +161,10 @@ __global__ void __launch_bounds__(256) k_refit(const float4* __restrict__ pts, i
       __stcg(r + 0, make_float4(lo.x, lo.y, lo.z, __int_as_float(m.x)));
       __stcg(r + 1, make_float4(hi.x, hi.y, hi.z, __int_as_float(m.y)));
     } else {
+      // up-link for the bottom-up searches: (parent << 2 | side-in-parent << 1 | this-node-is-a-Morton-cell), -1 at the root
+      int up = i == 0 ? -1 : ((__ldg(&parent_int[i]) << 1) | m.w);
       __stcg(r + 2, make_float4(lo.x, lo.y, lo.z, __int_as_float(m.z)));
-      __stcg(r + 3, make_float4(hi.x, hi.y, hi.z, 0.f));
+      __stcg(r + 3, make_float4(hi.x, hi.y, hi.z, __int_as_float(up)));
     }
     __threadfence();
     if (atomicAdd(&flags[i], 1) == 0) break;        // sibling not there yet: it will carry on
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(256) k_refit(const float4* __restrict__ pts, i
 }
 
 int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64) {
-  if (n64 < 1 || n64 > (1ll << 30)) return fail(h, AICP_B200_ERR_BAD_ARG, "cloud size %lld out of range", (long long)n64);
+  if (n64 < 1 || n64 > (1ll << 28)) return fail(h, AICP_B200_ERR_BAD_ARG, "cloud size %lld out of range [1, 2^28]", (long long)n64);
   int n = (int)n64;
   cudaStream_t s = h->stream;
   if (!ix.meta) CUDA_TRY(cudaMalloc((void**)&ix.meta, sizeof(IndexMeta)));
@@ -174,6 +188,8 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64)
   CUDA_TRY(ix.keys.reserve((size_t)n)); CUDA_TRY(ix.keys_alt.reserve((size_t)n));
   CUDA_TRY(ix.vals.reserve((size_t)n)); CUDA_TRY(ix.vals_alt.reserve((size_t)n));
   CUDA_TRY(ix.flags.reserve((size_t)3 * n));          // arrival counters | parent of internal nodes | parent of points
+  CUDA_TRY(ix.owner.reserve((size_t)2 * n));          // owner8 | owner32
+  CUDA_TRY(ix.cell.reserve((size_t)n));
   size_t tmp_bytes = 0;
   cub::DoubleBuffer<unsigned int> dk(ix.keys.p, ix.keys_alt.p), dv(ix.vals.p, ix.vals_alt.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, 30, s));
@@ -183,16 +199,17 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64)
   int blocks = (n + 255) / 256;
   int stat_blocks = blocks < 148 * 4 ? blocks : 148 * 4;
   k_index_stats<<<stat_blocks, 256, 0, s>>>(pts_dev, n, ix.meta);
+  k_quant_params<<<1, 32, 0, s>>>(ix.meta);
   k_morton_keys<<<blocks, 256, 0, s>>>(pts_dev, n, ix.meta, ix.keys.p, ix.vals.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ix.sort_tmp.p, tmp_bytes, dk, dv, n, 0, 30, s));
   k_gather<<<blocks, 256, 0, s>>>(pts_dev, dv.Current(), n, ix.pts.p);
-  h->launches += 4 + 4;    // own kernels + the radix sort's passes
+  h->launches += 5 + 4;    // own kernels + the radix sort's passes
   if (n > 1) {
     int* flags = ix.flags.p;
     int* parent_int = flags + n;
     int* parent_leaf = flags + 2 * (size_t)n;
     CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, s));
-    k_radix_tree<<<blocks, 256, 0, s>>>(dk.Current(), n, ix.node_meta.p, parent_int, parent_leaf);
+    k_radix_tree<<<blocks, 256, 0, s>>>(dk.Current(), n, ix.node_meta.p, parent_int, parent_leaf, ix.owner.p, ix.owner.p + n, ix.cell.p);
     k_refit<<<blocks, 256, 0, s>>>(ix.pts.p, n, ix.node_meta.p, parent_int, parent_leaf, ix.rec.p, flags);
     h->launches += 2;
   }

@@ -72,14 +72,16 @@ __device__ __forceinline__ void scan_range(const IndexView& ix, WarpKnn& w, int 
     d = d2_f(w.qx, w.qy, w.qz, p.x, p.y, p.z);
   }
   unsigned m = __ballot_sync(0xFFFFFFFFu, ok && cand_less(d, id, w.worst_d, w.worst_id));
+  // points of this chunk that are already in the list (the list is seeded with points the walk meets again): one
+  // warp-wide OR of their position bits removes them all at once
+  unsigned off = (unsigned)(w.lpos - first);
+  m &= ~__reduce_or_sync(0xFFFFFFFFu, (w.lane < w.k && off < 32u) ? (1u << off) : 0u);
   while (m) {
     int b = __ffs(m) - 1;
     m &= m - 1;
     float cd = __shfl_sync(0xFFFFFFFFu, d, b);
     int cid = __shfl_sync(0xFFFFFFFFu, id, b);
-    if (!cand_less(cd, cid, w.worst_d, w.worst_id)) continue;
-    if (__any_sync(0xFFFFFFFFu, w.lane < w.k && w.lid == cid)) continue;      // already a neighbour
-    warp_insert(w, cd, cid, first + b);
+    if (cand_less(cd, cid, w.worst_d, w.worst_id)) warp_insert(w, cd, cid, first + b);
   }
 }
 
@@ -104,6 +106,37 @@ __device__ __forceinline__ void warp_sort(WarpKnn& w) {
 
 #define KNN_WARPS 8
 #define KNN_LEAF 32
+
+// warp-uniform top-down walk of one subtree (code >= 0: internal node, code < 0: chunk [~code, ~code + cnt))
+__device__ __forceinline__ void knn_descend(const IndexView& ix, WarpKnn& w, int code, int cnt, int* st_a, int* st_b, float* st_d) {
+  int sp = 0;
+  while (true) {
+    if (code < 0) {
+      scan_range(ix, w, ~code, cnt);
+    } else {
+      const float4* r = ix.rec + 4 * (size_t)code;          // same address in every lane: one broadcast access
+      float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+      int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w);
+      float dl = box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), w.qx, w.qy, w.qz);
+      float dr = box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), w.qx, w.qy, w.qz);
+      int cl = split - first, cr = end - split;
+      int code_l = cl <= KNN_LEAF ? ~first : split - 1;
+      int code_r = cr <= KNN_LEAF ? ~split : split;
+      bool swap = dr < dl;
+      int code_n = swap ? code_r : code_l, cnt_n = swap ? cr : cl;
+      int code_f = swap ? code_l : code_r, cnt_f = swap ? cl : cr;
+      float dn = swap ? dr : dl, df = swap ? dl : dr;
+      if (df <= w.worst_d) { st_a[sp] = code_f; st_b[sp] = cnt_f; st_d[sp] = df; ++sp; }
+      if (dn <= w.worst_d) { code = code_n; cnt = cnt_n; continue; }
+    }
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      if (st_d[sp] <= w.worst_d) { code = st_a[sp]; cnt = st_b[sp]; found = true; break; }
+    }
+    if (!found) break;
+  }
+}
 #define KNN_RUN 16        // consecutive Morton-ordered queries handled by one warp
 
 __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k, int* __restrict__ knn_pos,
@@ -145,33 +178,32 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k
     if (lane >= k) { w.ld = INFINITY; w.lid = 0x7FFFFFFF; w.lpos = -1; }
     find_worst(w);
     if (ix.n > KNN_LEAF) {
-      int sp = 0;
-      int code = 0, cnt = ix.n;
+      // bottom-up: the query is a point of the cloud, so start at its own chunk and climb; a sibling subtree is entered
+      // only if its box can still hold one of the k nearest, and the climb stops once the ball (q, k-th distance) lies
+      // inside an ancestor that is a Morton cell (same argument as nn_search_up in search.cuh)
+      int own = __ldg(&ix.owner32[i]);
+      int node = own >> 1, side = own & 1;
+      bool first_level = true;
+      BallKeys bk; bk.d2 = -1.f;
       while (true) {
-        if (code < 0) {
-          scan_range(ix, w, ~code, cnt);
-        } else {
-          const float4* r = ix.rec + 4 * (size_t)code;          // same address in every lane: one broadcast access
-          float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
-          int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w);
-          float dl = box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), w.qx, w.qy, w.qz);
-          float dr = box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), w.qx, w.qy, w.qz);
-          int cl = split - first, cr = end - split;
-          int code_l = cl <= KNN_LEAF ? ~first : split - 1;
-          int code_r = cr <= KNN_LEAF ? ~split : split;
-          bool swap = dr < dl;
-          int code_n = swap ? code_r : code_l, cnt_n = swap ? cr : cl;
-          int code_f = swap ? code_l : code_r, cnt_f = swap ? cl : cr;
-          float dn = swap ? dr : dl, df = swap ? dl : dr;
-          if (df <= w.worst_d) { st_a[sp] = code_f; st_b[sp] = cnt_f; st_d[sp] = df; ++sp; }
-          if (dn <= w.worst_d) { code = code_n; cnt = cnt_n; continue; }
+        const float4* r = ix.rec + 4 * (size_t)node;            // same address in every lane: one broadcast access
+        float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+        int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w), up = __float_as_int(r3.w);
+        if (first_level) {
+          if (side == 0) scan_range(ix, w, first, split - first); else scan_range(ix, w, split, end - split);
+          first_level = false;
         }
-        bool found = false;
-        while (sp > 0) {
-          --sp;
-          if (st_d[sp] <= w.worst_d) { code = st_a[sp]; cnt = st_b[sp]; found = true; break; }
+        float ds = side == 0 ? box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), w.qx, w.qy, w.qz)
+                             : box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), w.qx, w.qy, w.qz);
+        if (ds <= w.worst_d) {
+          int sf = side == 0 ? split : first, sc = side == 0 ? end - split : split - first;
+          int scode = sc <= KNN_LEAF ? ~sf : (side == 0 ? split : split - 1);
+          knn_descend(ix, w, scode, sc, st_a, st_b, st_d);
         }
-        if (!found) break;
+        if (up < 0) break;
+        if (ball_inside_node(ix, node, w.qx, w.qy, w.qz, w.worst_d, bk)) break;
+        side = (up >> 1) & 1;
+        node = up >> 2;
       }
     } else {
       scan_range(ix, w, 0, ix.n);

@@ -32,7 +32,7 @@ __device__ __forceinline__ double key_to_coord(int key, double res) { return ((d
 __global__ void k_bounds_init(KeyBounds* kb, unsigned long long* counts) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int d = 0; d < 3; ++d) { kb->lo[d] = 0x7FFFFFFF; kb->hi[d] = (int)0x80000000; }
-    counts[0] = counts[1] = counts[2] = 0;
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
   }
 }
 
@@ -63,7 +63,11 @@ __global__ void __launch_bounds__(256) k_key_bounds(const float4* __restrict__ p
 
 struct Grid { int lo[3]; int dim[3]; };
 
-__device__ __forceinline__ void mark(unsigned int* bits, const Grid& g, int kx, int ky, int kz) {
+// The DDA may step past the end voxel before its length guard fires (octomap's "accumulating discretization errors"
+// case), so the bitmap box carries a 2-voxel margin; a key outside even that raises a flag instead of being dropped.
+__device__ __forceinline__ void mark(unsigned int* bits, const Grid& g, int kx, int ky, int kz, unsigned long long* oob) {
+  if ((unsigned)(kx - g.lo[0]) >= (unsigned)g.dim[0] || (unsigned)(ky - g.lo[1]) >= (unsigned)g.dim[1] ||
+      (unsigned)(kz - g.lo[2]) >= (unsigned)g.dim[2]) { atomicAdd(oob, 1ull); return; }
   unsigned long long idx = ((unsigned long long)(kx - g.lo[0]) * (unsigned)g.dim[1] + (unsigned)(ky - g.lo[1])) * (unsigned)g.dim[2] +
                            (unsigned)(kz - g.lo[2]);
   unsigned int* w = bits + (idx >> 5);
@@ -73,7 +77,7 @@ __device__ __forceinline__ void mark(unsigned int* bits, const Grid& g, int kx, 
 
 // OccupancyOcTreeBase::computeUpdate for one point: computeRayKeys(origin, p) -> free cells, key(p) -> occupied cell
 __global__ void __launch_bounds__(128) k_ray_mark(const float4* __restrict__ pts, int n, float ox, float oy, float oz, double res,
-                                                  double res_factor, Grid g, unsigned int* bits) {
+                                                  double res_factor, Grid g, unsigned int* bits, unsigned long long* oob) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(&pts[i]);
@@ -85,10 +89,10 @@ __global__ void __launch_bounds__(128) k_ray_mark(const float4* __restrict__ pts
               coord_to_key(origin[2], res_factor, &ko[2]);
   bool ok_e = coord_to_key(end[0], res_factor, &ke[0]) && coord_to_key(end[1], res_factor, &ke[1]) &&
               coord_to_key(end[2], res_factor, &ke[2]);
-  if (ok_e) mark(bits, g, ke[0], ke[1], ke[2]);
+  if (ok_e) mark(bits, g, ke[0], ke[1], ke[2], oob);
   if (!ok_o || !ok_e) return;
   if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return;
-  mark(bits, g, ko[0], ko[1], ko[2]);
+  mark(bits, g, ko[0], ko[1], ko[2], oob);
   float dir[3] = {__fsub_rn(end[0], origin[0]), __fsub_rn(end[1], origin[1]), __fsub_rn(end[2], origin[2])};
   float nsq = __fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1]));
   nsq = __fadd_rn(nsq, __fmul_rn(dir[2], dir[2]));
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(128) k_ray_mark(const float4* __restrict__ pts
     if (tMax[2] < dmin) dmin = tMax[2];
     if (dmin > (double)length) break;
     if ((unsigned)cur[0] >= 65536u || (unsigned)cur[1] >= 65536u || (unsigned)cur[2] >= 65536u) break;
-    mark(bits, g, cur[0], cur[1], cur[2]);
+    mark(bits, g, cur[0], cur[1], cur[2], oob);
   }
 }
 
@@ -153,7 +157,7 @@ int run_overlap(Handle* h, const float4* ref, int64_t n_ref, const double* ref_o
   const float ro[3] = {(float)ref_origin[0], (float)ref_origin[1], (float)ref_origin[2]};
   const float so[3] = {(float)read_origin[0], (float)read_origin[1], (float)read_origin[2]};
   CUDA_TRY(h->ovl_counts.reserve(16));
-  KeyBounds* kb = reinterpret_cast<KeyBounds*>(h->ovl_counts.p + 4);
+  KeyBounds* kb = reinterpret_cast<KeyBounds*>(h->ovl_counts.p + 8);
   unsigned long long* dcounts = h->ovl_counts.p;
   k_bounds_init<<<1, 32, 0, s>>>(kb, dcounts);
   auto nblk = [](int64_t n) { int64_t b = (n + 1 + 255) / 256; return (unsigned)(b < 148 * 4 ? b : 148 * 4); };
@@ -163,25 +167,26 @@ int run_overlap(Handle* h, const float4* ref, int64_t n_ref, const double* ref_o
   CUDA_TRY(cudaMemcpyAsync(&hb, kb, sizeof(hb), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   h->launches += 3;
-  unsigned long long hc[3] = {0, 0, 0};
+  unsigned long long hc[4] = {0, 0, 0, 0};
   if (hb.lo[0] <= hb.hi[0]) {
     Grid g;
     unsigned long long n_bits = 1;
-    for (int d = 0; d < 3; ++d) { g.lo[d] = hb.lo[d]; g.dim[d] = hb.hi[d] - hb.lo[d] + 1; n_bits *= (unsigned long long)g.dim[d]; }
+    for (int d = 0; d < 3; ++d) { g.lo[d] = hb.lo[d] - 2; g.dim[d] = hb.hi[d] - hb.lo[d] + 5; n_bits *= (unsigned long long)g.dim[d]; }
     if (n_bits > (1ull << 35)) return fail(h, AICP_B200_ERR_EXTENT, "overlap key box %d x %d x %d voxels exceeds the 4 GiB bitmap limit", g.dim[0], g.dim[1], g.dim[2]);
     unsigned long long n_words = (n_bits + 31) / 32;
     CUDA_TRY(h->ovl_bits_a.reserve((size_t)n_words));
     CUDA_TRY(h->ovl_bits_b.reserve((size_t)n_words));
     CUDA_TRY(cudaMemsetAsync(h->ovl_bits_a.p, 0, n_words * 4, s));
     CUDA_TRY(cudaMemsetAsync(h->ovl_bits_b.p, 0, n_words * 4, s));
-    k_ray_mark<<<(unsigned)((n_ref + 127) / 128), 128, 0, s>>>(ref, (int)n_ref, ro[0], ro[1], ro[2], resolution, res_factor, g, h->ovl_bits_a.p);
-    k_ray_mark<<<(unsigned)((n_read + 127) / 128), 128, 0, s>>>(read, (int)n_read, so[0], so[1], so[2], resolution, res_factor, g, h->ovl_bits_b.p);
+    k_ray_mark<<<(unsigned)((n_ref + 127) / 128), 128, 0, s>>>(ref, (int)n_ref, ro[0], ro[1], ro[2], resolution, res_factor, g, h->ovl_bits_a.p, dcounts + 3);
+    k_ray_mark<<<(unsigned)((n_read + 127) / 128), 128, 0, s>>>(read, (int)n_read, so[0], so[1], so[2], resolution, res_factor, g, h->ovl_bits_b.p, dcounts + 3);
     unsigned long long pb = (n_words + 255) / 256;
     k_popcount<<<(unsigned)(pb < 148 * 8 ? pb : 148 * 8), 256, 0, s>>>(h->ovl_bits_a.p, h->ovl_bits_b.p, n_words, dcounts);
     CUDA_TRY(cudaMemcpyAsync(hc, dcounts, sizeof(hc), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     CUDA_TRY(cudaGetLastError());
     h->launches += 3;
+    if (hc[3]) return fail(h, AICP_B200_ERR_EXTENT, "overlap: %llu ray voxels fell outside the occupancy box", hc[3]);
   }
   // octrees_overlap.cpp:47-53
   float treeA = (float)(long long)hc[0] / (float)(long long)hc[1];

@@ -11,6 +11,8 @@
 //                          left child = node `split-1` over [first, split), right child = node `split` over [split, end).
 //                          A child with <= LEAF points is scanned directly instead of being entered, so the per-thread
 //                          1-NN walk (LEAF 8) and the warp k-NN walk (LEAF 32) share one tree.
+//                          rec[4i+3].w is the up-link (parent << 2 | side in parent << 1 | node-is-a-Morton-cell), -1 at
+//                          the root: searches that start from a known nearby point climb instead of descending.
 //
 // Exactness: box_d2_f(child) <= d2_f(p) for every point p stored below it, in float arithmetic, because float
 // subtraction, multiplication and addition are monotone and both sides use the same operation order.  A subtree is
@@ -22,11 +24,79 @@
 
 namespace aicp {
 
+// per-index reduction results and quantisation parameters (device memory, written by index.cu)
+struct IndexMeta {
+  int bmin[3], bmax[3];          // ordered-int encoded bounding box
+  long long csum[3];             // sum of round(coord * 2^16)
+  int nonfinite;
+  int pad;
+  float qlo[3];                  // Morton quantisation: cell = (int)((x - qlo) * qscale), clamped to [0, 1023]
+  float qscale;
+};
+
 struct IndexView {
   const float4* __restrict__ pts;
   const float4* __restrict__ rec;
+  const int* __restrict__ owner8;     // per point: (node << 1 | side) of the lowest node with more than 8 points above it
+  const int* __restrict__ owner32;    // same for 32 points (warp k-NN chunks)
+  const int2* __restrict__ cell;      // per internal node: (a Morton key inside the node, common-prefix length = clz(first ^ last))
+  const IndexMeta* __restrict__ meta;
+  const float* __restrict__ shift;    // added to query coordinates to reach the frame the keys were built in (nullptr: none)
   int n;
 };
+
+__device__ __forceinline__ unsigned int morton_spread10(unsigned int v) {
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// the quantisation of index.cu's k_morton_keys: monotone non-decreasing in x
+__device__ __forceinline__ int morton_quant(float x, float lo, float scale) {
+  return min(1023, max(0, (int)((x - lo) * scale)));
+}
+__device__ __forceinline__ unsigned int morton_key(int qx, int qy, int qz) {
+  return morton_spread10((unsigned)qx) | (morton_spread10((unsigned)qy) << 1) | (morton_spread10((unsigned)qz) << 2);
+}
+
+// Stop test of the bottom-up searches: "can the ball (q, sqrt(d2)) reach outside node c?"
+// A node whose keys share exactly `len` leading bits (clz units of the 32-bit key word; the key uses bits 29..0) and that
+// is a Morton cell holds ALL indexed points whose key carries that prefix.  Every indexed point within the ball has a key
+// whose per-axis cell lies between the cells of the two extreme corners of a box around the ball (the quantisation is
+// monotone), so if both corner keys carry the node's prefix, no point outside the node is in the ball.
+// Slack: the query may live in a shifted frame (one extra rounding) and sqrt / subtraction round, so the radius is
+// inflated by a relative 2^-18 plus 1 % of a cell -- far more than any of those roundings.
+// The corner keys are cached and recomputed only when the bound changed; a node whose cell is narrower than the ball is
+// rejected before any key arithmetic.
+struct BallKeys {
+  unsigned int lo, hi;
+  float d2;          // bound the keys were computed for (-1: none yet)
+  float diam_cells;  // ball diameter in quantisation cells
+};
+
+__device__ __forceinline__ void ball_keys_update(const IndexView& ix, float qx, float qy, float qz, float d2, BallKeys& k) {
+  const float lx = ix.meta->qlo[0], ly = ix.meta->qlo[1], lz = ix.meta->qlo[2], sc = ix.meta->qscale;
+  if (ix.shift) { qx += ix.shift[0]; qy += ix.shift[1]; qz += ix.shift[2]; }
+  float r = sqrtf(d2);
+  r = r * 1.000004f + 0.01f / fmaxf(sc, 1e-30f) + 4e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+  k.lo = morton_key(morton_quant(qx - r, lx, sc), morton_quant(qy - r, ly, sc), morton_quant(qz - r, lz, sc));
+  k.hi = morton_key(morton_quant(qx + r, lx, sc), morton_quant(qy + r, ly, sc), morton_quant(qz + r, lz, sc));
+  k.d2 = d2;
+  k.diam_cells = 2.f * r * sc;
+}
+
+__device__ __forceinline__ bool ball_inside_node(const IndexView& ix, int node, float qx, float qy, float qz, float d2, BallKeys& k) {
+  int2 c = __ldg(&ix.cell[node]);
+  if (c.y >= 32) return false;                       // split among equal keys: not a Morton cell
+  // narrowest side of the node's cell, in quantisation cells: prefix of (c.y - 2) key bits = floor/ceil of a third per axis
+  int bits = c.y - 2;
+  int side_log2 = 10 - (bits + 2) / 3;
+  if (k.d2 != d2) ball_keys_update(ix, qx, qy, qz, d2, k);
+  if (k.diam_cells > (float)(1 << side_log2)) return false;
+  return __clz((int)(k.lo ^ (unsigned)c.x)) >= c.y && __clz((int)(k.hi ^ (unsigned)c.x)) >= c.y;
+}
 
 #define AICP_STACK 64
 
@@ -34,34 +104,30 @@ __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) 
   return d2a < d2b || (d2a == d2b && ia < ib);
 }
 
-// 1-NN: returns position in the Morton-ordered array (so the caller can gather normals) and the squared distance.
-// warm_pos >= 0 seeds the search with a known reference point (the previous iteration's match): the bound starts at its
-// distance, so most of the tree is pruned at the root.  The seed is an ordinary candidate, so the result is unchanged.
-__device__ inline void nn_search(const IndexView& ix, float qx, float qy, float qz, int* out_pos, float* out_d2, int warm_pos = -1) {
+struct NnBest {
+  float d;
+  int id;
+  int pos;
+};
+
+__device__ __forceinline__ void nn_scan(const IndexView& ix, float qx, float qy, float qz, int first, int cnt, NnBest& b) {
+  for (int j = 0; j < cnt; ++j) {
+    float4 p = __ldg(&ix.pts[first + j]);
+    float d = d2_f(qx, qy, qz, p.x, p.y, p.z);
+    int id = __float_as_int(p.w);
+    if (d < b.d || (d == b.d && id < b.id)) { b.d = d; b.id = id; b.pos = first + j; }
+  }
+}
+
+// top-down walk of one subtree (code >= 0: internal node, code < 0: scan range [~code, ~code + cnt))
+__device__ inline void nn_descend(const IndexView& ix, float qx, float qy, float qz, int code, int cnt, NnBest& b) {
   int st_a[AICP_STACK];      // internal node index, or ~first for a scan range
   int st_b[AICP_STACK];      // point count of a scan range
   float st_d[AICP_STACK];
   int sp = 0;
-  float best = INFINITY;
-  int best_id = 0x7FFFFFFF;
-  int best_pos = -1;
-  if (warm_pos >= 0) {
-    float4 p = __ldg(&ix.pts[warm_pos]);
-    best = d2_f(qx, qy, qz, p.x, p.y, p.z);
-    best_id = __float_as_int(p.w);
-    best_pos = warm_pos;
-  }
-  int code = (ix.n <= AICP_LEAF) ? ~0 : 0;      // start at the root, or scan everything when the cloud is one leaf
-  int cnt = ix.n;
   while (true) {
     if (code < 0) {
-      int first = ~code;
-      for (int j = 0; j < cnt; ++j) {
-        float4 p = __ldg(&ix.pts[first + j]);
-        float d = d2_f(qx, qy, qz, p.x, p.y, p.z);
-        int id = __float_as_int(p.w);
-        if (d < best || (d == best && id < best_id)) { best = d; best_id = id; best_pos = first + j; }
-      }
+      nn_scan(ix, qx, qy, qz, ~code, cnt, b);
     } else {
       const float4* r = ix.rec + 4 * (size_t)code;
       float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
@@ -76,19 +142,69 @@ __device__ inline void nn_search(const IndexView& ix, float qx, float qy, float 
       int code_n = swap ? code_r : code_l, cnt_n = swap ? cr : cl;
       int code_f = swap ? code_l : code_r, cnt_f = swap ? cl : cr;
       float dn = swap ? dr : dl, df = swap ? dl : dr;
-      if (df <= best) { st_a[sp] = code_f; st_b[sp] = cnt_f; st_d[sp] = df; ++sp; }
-      if (dn <= best) { code = code_n; cnt = cnt_n; continue; }
+      if (df <= b.d) { st_a[sp] = code_f; st_b[sp] = cnt_f; st_d[sp] = df; ++sp; }
+      if (dn <= b.d) { code = code_n; cnt = cnt_n; continue; }
     }
     // pop the next subtree that can still improve on (best, best_id)
     bool found = false;
     while (sp > 0) {
       --sp;
-      if (st_d[sp] <= best) { code = st_a[sp]; cnt = st_b[sp]; found = true; break; }
+      if (st_d[sp] <= b.d) { code = st_a[sp]; cnt = st_b[sp]; found = true; break; }
     }
     if (!found) break;
   }
-  *out_pos = best_pos;
-  *out_d2 = best;
+}
+
+// 1-NN from the root: returns position in the Morton-ordered array (so the caller can gather normals) and d2.
+__device__ inline void nn_search(const IndexView& ix, float qx, float qy, float qz, int* out_pos, float* out_d2) {
+  NnBest b{INFINITY, 0x7FFFFFFF, -1};
+  if (ix.n <= AICP_LEAF) nn_scan(ix, qx, qy, qz, 0, ix.n, b);
+  else nn_descend(ix, qx, qy, qz, 0, ix.n, b);
+  *out_pos = b.pos;
+  *out_d2 = b.d;
+}
+
+// 1-NN seeded with a reference point known to be near (the previous ICP iteration's match).  The walk starts at the
+// seed's leaf and CLIMBS: at every ancestor the sibling subtree is entered only if its box can still beat the bound, and
+// the climb stops as soon as the ball (q, best) lies inside an ancestor that is a Morton cell -- every point outside that
+// ancestor has a key outside the cell, hence (monotone quantisation) lies outside the ball.  Once ICP has pulled the
+// clouds together the ball is a few centimetres wide and the climb ends 3-5 levels above the leaf instead of walking a
+// root-to-leaf path; the result is identical to nn_search (the same candidates can win).
+__device__ inline void nn_search_up(const IndexView& ix, float qx, float qy, float qz, int seed_pos, int* out_pos, float* out_d2) {
+  NnBest b{INFINITY, 0x7FFFFFFF, -1};
+  if (ix.n <= AICP_LEAF) {
+    nn_scan(ix, qx, qy, qz, 0, ix.n, b);
+  } else {
+    int own = __ldg(&ix.owner8[seed_pos]);
+    int node = own >> 1, side = own & 1;
+    bool first_level = true;
+    BallKeys bk; bk.d2 = -1.f;
+    while (true) {
+      const float4* r = ix.rec + 4 * (size_t)node;
+      float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+      int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w), up = __float_as_int(r3.w);
+      if (first_level) {
+        // the seed's own small range first: it holds the seed, so the bound is at most the seed's distance afterwards
+        if (side == 0) nn_scan(ix, qx, qy, qz, first, split - first, b); else nn_scan(ix, qx, qy, qz, split, end - split, b);
+        first_level = false;
+      }
+      // sibling subtree of the side we came from
+      float ds = side == 0 ? box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), qx, qy, qz)
+                           : box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), qx, qy, qz);
+      if (ds <= b.d) {
+        int sf = side == 0 ? split : first, sc = side == 0 ? end - split : split - first;
+        int scode = sc <= AICP_LEAF ? ~sf : (side == 0 ? split : split - 1);
+        nn_descend(ix, qx, qy, qz, scode, sc, b);
+      }
+      if (up < 0) break;                                   // root done
+      // stop once the ball (q, best) cannot reach outside this node (see ball_inside_node)
+      if (ball_inside_node(ix, node, qx, qy, qz, b.d, bk)) break;
+      side = (up >> 1) & 1;
+      node = up >> 2;
+    }
+  }
+  *out_pos = b.pos;
+  *out_d2 = b.d;
 }
 
 }  // namespace aicp

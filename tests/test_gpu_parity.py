@@ -301,6 +301,15 @@ def test_overlap_parity(orc, pair_cache):
         o_ov, o_counts = orc.overlap(pair["ref"], pair["ref_origin"], pair["read"], pair["read_origin"])
         assert counts == o_counts, pair["name"]
         assert abs(float(ov.getOverlap()) - float(o_ov)) <= 1e-4 and u32([ov.getOverlap()])[0] == u32([o_ov])[0]
+    # lattice points exactly on voxel boundaries, origin inside the cloud: the DDA overshoots its end voxels here
+    t = (np.arange(40, dtype=np.float32) * np.float32(0.1) - np.float32(2.0))
+    g = np.stack(np.meshgrid(t, t, indexing="ij"), -1).reshape(-1, 2)
+    lattice = np.concatenate([np.c_[g, np.full(len(g), v)] for v in (-2.0, 2.0)] + [np.c_[np.full(len(g), v), g] for v in (-2.0, 2.0)] +
+                             [np.c_[g[:, 0], np.full(len(g), v), g[:, 1]] for v in (-2.0, 2.0)]).astype(np.float32)
+    shifted = lattice + np.float32([0.05, -0.03, 0.0007])
+    counts = ov.computeOverlap(lattice, shifted, [0, 0, 0], [0, 0, 0])
+    o_ov, o_counts = orc.overlap(lattice, [0, 0, 0], shifted, [0, 0, 0])
+    assert counts == o_counts and u32([ov.getOverlap()])[0] == u32([o_ov])[0]
     # identical clouds -> 100 %, disjoint -> 0 %
     a = cases[0]["ref"]
     ov.computeOverlap(a, a, [0, 0, 0.6], [0, 0, 0.6])
