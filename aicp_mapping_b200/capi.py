@@ -43,7 +43,8 @@ class Stats(C.Structure):
                 ("mean_ref", C.c_float * 3), ("n_ref", C.c_int64), ("n_read", C.c_int64), ("ms_total", C.c_float),
                 ("ms_setup", C.c_float), ("ms_iterations", C.c_float), ("gpu_launches", C.c_int32),
                 ("profiled", C.c_int32), ("ms_index", C.c_float), ("ms_normals", C.c_float), ("ms_match", C.c_float),
-                ("ms_select", C.c_float), ("ms_accumulate", C.c_float), ("trace", IterTrace * MAX_ITERS)]
+                ("ms_select", C.c_float), ("ms_accumulate", C.c_float), ("ms_tail_pick", C.c_float), ("ms_tail_select", C.c_float),
+                ("ms_tail_solve", C.c_float), ("trace", IterTrace * MAX_ITERS)]
 
 
 class AicpError(RuntimeError):

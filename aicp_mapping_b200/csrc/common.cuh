@@ -48,6 +48,8 @@ struct DeviceState {
   unsigned long long n_valid;
   float limit;
   unsigned int ticket[4];
+  unsigned int cand_n;              // candidate keys appended by k_select23
+  unsigned long long tail_ns[3];    // time spent in the single-block tails: digit-1 pick, digits 2+3, solve + checkers
   // normal equations, 128-bit two's complement fixed point
   unsigned long long sum_lo[AICP_NSUM];
   long long sum_hi[AICP_NSUM];

@@ -18,6 +18,17 @@
 
 namespace aicp {
 
+// correctly rounded reciprocals of the series denominators (compile-time constants: the same values a run-time IEEE
+// division produces, which is what the oracle executes)
+#define AICP_R(x) (1.0 / (double)(x))
+__device__ static const double kInvSin[12] = {0.0, AICP_R(2 * 3), AICP_R(4 * 5), AICP_R(6 * 7), AICP_R(8 * 9), AICP_R(10 * 11), AICP_R(12 * 13),
+                                     AICP_R(14 * 15), AICP_R(16 * 17), AICP_R(18 * 19), AICP_R(20 * 21), AICP_R(22 * 23)};
+__device__ static const double kInvCos[12] = {0.0, AICP_R(1 * 2), AICP_R(3 * 4), AICP_R(5 * 6), AICP_R(7 * 8), AICP_R(9 * 10), AICP_R(11 * 12),
+                                     AICP_R(13 * 14), AICP_R(15 * 16), AICP_R(17 * 18), AICP_R(19 * 20), AICP_R(21 * 22)};
+__device__ static const double kInvOdd[12] = {0.0, AICP_R(3), AICP_R(5), AICP_R(7), AICP_R(9), AICP_R(11), AICP_R(13), AICP_R(15), AICP_R(17),
+                                     AICP_R(19), AICP_R(21), AICP_R(23)};
+#undef AICP_R
+
 __device__ inline void det_sincos(double x, double* s, double* c) {
   const double two_over_pi = 0.63661977236758138;
   const double pio2_hi = 1.5707963267341256;
@@ -27,7 +38,7 @@ __device__ inline void det_sincos(double x, double* s, double* c) {
   double r2 = r * r;
   double term = r, ss = r;
   for (int n = 1; n <= 11; ++n) {
-    double inv = 1.0 / (double)((2 * n) * (2 * n + 1));
+    double inv = kInvSin[n];
     term = (term * r2) * inv;
     term = -term;
     double ns = ss + term;
@@ -36,7 +47,7 @@ __device__ inline void det_sincos(double x, double* s, double* c) {
   }
   double cterm = 1.0, cc = 1.0;
   for (int n = 1; n <= 11; ++n) {
-    double inv = 1.0 / (double)((2 * n - 1) * (2 * n));
+    double inv = kInvCos[n];
     cterm = (cterm * r2) * inv;
     cterm = -cterm;
     double nc = cc + cterm;
@@ -56,7 +67,7 @@ __device__ inline double det_atan01(double z) {
   for (int h = 0; h < 3; ++h) u = u / (1.0 + sqrt(1.0 + u * u));
   double u2 = u * u, p = u, sum = u;
   for (int n = 1; n <= 11; ++n) {
-    double inv = 1.0 / (double)(2 * n + 1);
+    double inv = kInvOdd[n];
     p = p * u2;
     p = -p;
     double ns = sum + p * inv;

@@ -77,12 +77,15 @@ struct Handle {
   DevBuf<int> match_pos;
   DevBuf<float> d2;
   DevBuf<unsigned int> hist;
+  DevBuf<unsigned int> cand;     // d2 keys of the quantile's first-digit bin (k_select23)
   int64_t n_read = 0;
   bool has_init_reading = false;
 
   // loop state
   DeviceState* st = nullptr;     // device
   DeviceState* st_host = nullptr;  // pinned
+  volatile int* progress_host = nullptr;   // mapped pinned: [0] iterations completed, [1] loop finished (written by the device)
+  int* progress_dev = nullptr;             // the same two words, device address
   DevBuf<int> trace_idx;
   bool trace_matches = false;
   bool profiling = false;
@@ -107,7 +110,8 @@ struct Handle {
 };
 
 // ---- index.cu
-int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n);
+// with_tree = false: Morton order only (pts), no radix tree -- enough to make the queries of a warp spatially coherent
+int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n, bool with_tree = true);
 // ---- normals.cu
 int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig);
 // ---- icp.cu

@@ -5,20 +5,43 @@
 //   KDTreeMatcher{knn 1, epsilon 0}  ->  TrimmedDistOutlierFilter{ratio}  ->  PointToPlaneErrorMinimizer
 //   ->  CounterTransformationChecker + DifferentialTransformationChecker.
 //
-// One iteration = four launches on one stream, no host synchronisation anywhere in the loop:
+// One iteration = three launches on one stream, no host synchronisation anywhere in the loop:
 //   k_match       reading' -> T_iter * reading' (float, fixed order), exact NN in the centred reference index,
 //                 writes (position, d2), builds the first radix-select histogram; its last block picks the digit
-//   k_select x2   digits 2 and 3 of the radix select over the float bit pattern of d2 -> exact k-th order statistic
+//   k_select23    compacts the d2 keys that carry that digit (a few thousand) into a candidate list; its last block
+//                 finishes the radix select (digits 2 and 3) over the list in shared memory -> exact k-th order statistic
 //   k_accumulate  weights (d2 <= limit), F = [p x n; n], exact fixed-point sums of F F^T and F (delta.n) reduced
 //                 with a transposed warp shuffle and 128-bit integer atomics; its last block solves the 6x6 system in
 //                 float64, updates T_iter and evaluates both transformation checkers (-> st->done)
-// Every kernel returns immediately once st->done is set, so the host can enqueue max_iterations iterations blindly.
+// Every kernel returns immediately once st->done is set.  The host enqueues the first smoothLength iterations blindly (the
+// differential checker cannot stop earlier) and then stays at most two iterations ahead of the device, reading the
+// iteration counter the solve publishes in mapped pinned memory -- a registration that converges after 8 of 20
+// iterations does not pay for 36 empty launches.
 #include "detmath.cuh"
 #include "handle.cuh"
 
 namespace aicp {
 
 __device__ __forceinline__ int ld_int(const int* p) { return *(const volatile int*)p; }
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// loop progress for the host (mapped pinned memory): [0] = iterations completed, [1] = loop finished
+__device__ __forceinline__ void publish_progress(volatile int* progress, int iter, int done) {
+  if (!progress) return;
+  progress[0] = iter;
+  if (done) progress[1] = 1;
+  __threadfence_system();
+}
+
+// early-exit path of the loop kernels: the loop is over (converged, counter, or a status was raised)
+__device__ __forceinline__ void publish_done(volatile int* progress) {
+  if (progress && blockIdx.x == 0 && threadIdx.x == 0) { progress[1] = 1; __threadfence_system(); }
+}
 
 __device__ __forceinline__ void raise_status(DeviceState* st, int code) {
   atomicCAS(&st->status, 0, code);
@@ -31,6 +54,8 @@ __global__ void k_loop_init(DeviceState* st, const IndexMeta* __restrict__ meta,
   st->status = 0; st->done = 0; st->stop_reason = 0; st->iter = 0; st->hist_n = 1;
   st->prefix = 0; st->k_rem = 0; st->n_valid = 0; st->limit = 0.f; st->n_used_last = 0;
   for (int i = 0; i < 4; ++i) st->ticket[i] = 0;
+  st->cand_n = 0;
+  for (int i = 0; i < 3; ++i) st->tail_ns[i] = 0;
   for (int i = 0; i < AICP_NSUM; ++i) { st->sum_lo[i] = 0; st->sum_hi[i] = 0; }
   if (meta->nonfinite) { st->status = AICP_B200_ERR_NONFINITE_INPUT; st->done = 1; }
   // A.1 step 2: centre on the mean of the (filtered) reference; exact fixed-point sum -> order independent
@@ -90,16 +115,18 @@ __global__ void __launch_bounds__(256) k_read_prepare(const float4* __restrict__
 // digit 1 = bits 30..20, digit 2 = bits 19..9, digit 3 = bits 8..0
 __device__ __forceinline__ bool d2_valid(float d) { return d > 0.f && d < INFINITY; }   // Matches::getDistsQuantile filter
 
-// executed by all 256 threads of the last block of a histogram pass
-__device__ void select_pick(DeviceState* st, unsigned int* hist, int pass, float ratio) {
+// Rank search in a 2048-bin histogram held 8 consecutive bins per thread (256 threads): the bin that holds rank
+// `target`, the rank inside that bin, and the histogram total.  pass 1 derives the target from the total (A.4):
+// index = size_t(float(n_valid) * ratio), clamped to n_valid - 1; ratio == 1 -> the maximum.
+__device__ __forceinline__ void block_pick(const unsigned int (&h)[8], int pass, float ratio, unsigned long long k_rem_in,
+                                           unsigned int* out_bin, unsigned long long* out_rem, unsigned long long* out_total) {
   __shared__ unsigned long long s_warp[8];
-  __shared__ unsigned long long s_target;
+  __shared__ unsigned long long s_target, s_rem, s_total;
+  __shared__ unsigned int s_bin;
   const int t = threadIdx.x;
-  unsigned int h[8];
   unsigned long long local = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { h[j] = __ldcg(&hist[t * 8 + j]); local += h[j]; }
-  // block exclusive scan of `local`
+  for (int j = 0; j < 8; ++j) local += h[j];
   unsigned long long incl = local;
   const int lane = t & 31, w = t >> 5;
 #pragma unroll
@@ -108,15 +135,16 @@ __device__ void select_pick(DeviceState* st, unsigned int* hist, int pass, float
     if (lane >= off) incl += o;
   }
   if (lane == 31) s_warp[w] = incl;
+  if (t == 0) { s_bin = 0; s_rem = 0; }
   __syncthreads();
   unsigned long long base = 0, total = 0;
+#pragma unroll
   for (int i = 0; i < 8; ++i) { if (i < w) base += s_warp[i]; total += s_warp[i]; }
-  unsigned long long excl = base + incl - local;
+  const unsigned long long excl = base + incl - local;
   if (t == 0) {
     unsigned long long target;
     if (pass == 1) {
-      st->n_valid = total;
-      if (total == 0) { raise_status(st, AICP_B200_ERR_NO_VALID_MATCH); target = 0; }
+      if (total == 0) target = 0;
       else if (ratio == 1.0f) target = total - 1;
       else {
         float fi = __fmul_rn(__ull2float_rn(total), ratio);      // size_t * float in float32, truncated (A.4)
@@ -124,27 +152,40 @@ __device__ void select_pick(DeviceState* st, unsigned int* hist, int pass, float
         if (target > total - 1) target = total - 1;
       }
     } else {
-      target = st->k_rem;
+      target = k_rem_in;
     }
-    s_target = target;
+    s_target = target; s_total = total;
   }
   __syncthreads();
-  unsigned long long target = s_target;
+  const unsigned long long target = s_target;
   unsigned long long cum = excl;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    if (h[j] != 0 && cum <= target && target < cum + h[j]) {
-      unsigned int bin = (unsigned)(t * 8 + j);
-      st->k_rem = target - cum;
-      if (pass == 1) st->prefix = bin;
-      else if (pass == 2) st->prefix = (st->prefix << 11) | bin;
-      else {
-        unsigned int key = (st->prefix << 9) | bin;
-        st->limit = __uint_as_float(key);
-      }
-    }
+    if (h[j] != 0 && cum <= target && target < cum + h[j]) { s_bin = (unsigned)(t * 8 + j); s_rem = target - cum; }
     cum += h[j];
-    hist[t * 8 + j] = 0;
+  }
+  __syncthreads();
+  *out_bin = s_bin; *out_rem = s_rem; *out_total = s_total;
+  __syncthreads();                                       // the scratch is reused by the next call
+}
+
+// executed by all 256 threads of the last block of a histogram pass over the GLOBAL histogram (which it zeroes again)
+__device__ void select_pick(DeviceState* st, unsigned int* hist, int pass, float ratio) {
+  const int t = threadIdx.x;
+  unsigned int h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { h[j] = __ldcg(&hist[t * 8 + j]); hist[t * 8 + j] = 0; }
+  unsigned int bin; unsigned long long rem, total;
+  block_pick(h, pass, ratio, st->k_rem, &bin, &rem, &total);
+  if (t == 0) {
+    if (pass == 1) {
+      st->n_valid = total;
+      if (total == 0) raise_status(st, AICP_B200_ERR_NO_VALID_MATCH);
+    }
+    st->k_rem = rem;
+    if (pass == 1) st->prefix = bin;
+    else if (pass == 2) st->prefix = (st->prefix << 11) | bin;
+    else st->limit = __uint_as_float((st->prefix << 9) | bin);
   }
 }
 
@@ -169,8 +210,9 @@ __device__ __forceinline__ void hist_flush(const unsigned int* sh, unsigned int*
 
 __global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __restrict__ read0, int n, DeviceState* st,
                                                int* match_pos, float* __restrict__ d2out,
-                                               unsigned int* hist, int* trace_idx, float ratio, int tail) {
-  if (ld_int(&st->done)) return;
+                                               unsigned int* hist, int* trace_idx, float ratio, int tail,
+                                               volatile int* progress) {
+  if (ld_int(&st->done)) { publish_done(progress); return; }
   __shared__ unsigned int sh[AICP_HIST_BINS];
   __shared__ float sT[16];
   for (int b = threadIdx.x; b < AICP_HIST_BINS; b += blockDim.x) sh[b] = 0;
@@ -191,7 +233,72 @@ __global__ void __launch_bounds__(256) k_match(IndexView ix, const float4* __res
   }
   __syncthreads();
   hist_flush(sh, hist);
-  if (tail && block_is_last(&st->ticket[0])) select_pick(st, hist, 1, ratio);
+  if (tail && block_is_last(&st->ticket[0])) {
+    const unsigned long long t0 = global_ns();
+    select_pick(st, hist, 1, ratio);
+    if (threadIdx.x == 0) st->tail_ns[0] += global_ns() - t0;
+  }
+}
+
+// Digits 2 and 3 of the trimmed quantile in ONE launch.  Grid: every d2 key whose first digit is the one k_match picked
+// (typically a few thousand of the n keys) is appended to `cand` (warp-aggregated atomics).  Last block: radix select of
+// the remaining 20 bits over the candidate list with shared-memory histograms -> st->limit, the exact k-th smallest.
+__global__ void __launch_bounds__(256) k_select23(const float* __restrict__ d2, int n, DeviceState* st, unsigned int* cand,
+                                                  volatile int* progress) {
+  if (ld_int(&st->done)) { publish_done(progress); return; }
+  __shared__ unsigned int sh[AICP_HIST_BINS];
+  const unsigned int prefix = st->prefix;
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {     // warp-uniform trip count
+    const int i = base + threadIdx.x;
+    unsigned int key = 0;
+    bool hit = false;
+    if (i < n) {
+      float d = __ldg(&d2[i]);
+      key = __float_as_uint(d);
+      hit = d2_valid(d) && (key >> 20) == prefix;
+    }
+    const unsigned int m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned int off = 0;
+      if (lane == leader) off = atomicAdd(&st->cand_n, (unsigned)__popc(m));
+      off = __shfl_sync(0xFFFFFFFFu, off, leader);
+      if (hit) cand[off + __popc(m & ((1u << lane) - 1u))] = key;
+    }
+  }
+  if (!block_is_last(&st->ticket[1])) return;
+  const unsigned long long t0 = global_ns();
+  const int t = threadIdx.x;
+  const unsigned int c = *(volatile unsigned int*)&st->cand_n;
+  unsigned int h[8], bin; unsigned long long rem, total;
+  // digit 2
+  for (int b = t; b < AICP_HIST_BINS; b += 256) sh[b] = 0;
+  __syncthreads();
+  for (unsigned int j = t; j < c; j += 256) atomicAdd(&sh[(__ldcg(&cand[j]) >> 9) & 2047u], 1u);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = sh[t * 8 + j];
+  block_pick(h, 2, 0.f, st->k_rem, &bin, &rem, &total);
+  const unsigned int prefix22 = (prefix << 11) | bin;
+  // digit 3
+  for (int b = t; b < AICP_HIST_BINS; b += 256) sh[b] = 0;
+  __syncthreads();
+  for (unsigned int j = t; j < c; j += 256) {
+    unsigned int key = __ldcg(&cand[j]);
+    if ((key >> 9) == prefix22) atomicAdd(&sh[key & 511u], 1u);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = sh[t * 8 + j];
+  block_pick(h, 3, 0.f, rem, &bin, &rem, &total);
+  if (t == 0) {
+    st->prefix = prefix22;
+    st->k_rem = rem;
+    st->limit = __uint_as_float((prefix22 << 9) | bin);
+    st->cand_n = 0;
+    st->tail_ns[1] += global_ns() - t0;
+  }
 }
 
 // pass 1: plain histogram of digit 1 (stage entry point); pass 2 / 3: next digits among keys matching the prefix
@@ -297,8 +404,9 @@ __device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams l
 
 __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
                                                     const float4* __restrict__ read0, const int* __restrict__ match_pos,
-                                                    const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp, int tail) {
-  if (ld_int(&st->done)) return;
+                                                    const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp, int tail,
+                                                    volatile int* progress) {
+  if (ld_int(&st->done)) { publish_done(progress); return; }
   __shared__ float sT[16];
   __shared__ long long s_part[8][32];
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T_iter[threadIdx.x];
@@ -357,7 +465,12 @@ __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict_
     if (lane < AICP_NSUM && tot != 0) atomic_add_128(&st->sum_lo[lane], &st->sum_hi[lane], tot);
   }
   if (tail && block_is_last(&st->ticket[2])) {
-    if (threadIdx.x == 0) solve_and_check(st, lp, n);
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = global_ns();
+      solve_and_check(st, lp, n);
+      st->tail_ns[2] += global_ns() - t0;
+      publish_progress(progress, st->iter, *(volatile int*)&st->done);
+    }
   }
 }
 
@@ -450,6 +563,11 @@ static int ensure_state(Handle* h) {
     CUDA_TRY(cudaMemsetAsync(h->st, 0, sizeof(DeviceState), h->stream));
   }
   if (!h->st_host) CUDA_TRY(cudaMallocHost((void**)&h->st_host, sizeof(DeviceState)));
+  if (!h->progress_host) {
+    CUDA_TRY(cudaHostAlloc((void**)&h->progress_host, 2 * sizeof(int), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&h->progress_dev, (void*)h->progress_host, 0));
+    h->progress_host[0] = 0; h->progress_host[1] = 0;
+  }
   if (h->hist.cap < AICP_HIST_BINS) {
     CUDA_TRY(h->hist.reserve(AICP_HIST_BINS));
     CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * h->hist.cap, h->stream));   // cudaMalloc does not zero
@@ -540,7 +658,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   k_read_prepare<<<blocks, 256, 0, s>>>(h->read_in.p, n_read, h->st, h->read0.p, read_init);
   h->launches += 2;
   // Morton-order the reading so that the 32 queries of a warp walk the same part of the reference tree
-  rc = build_index(h, h->read_ix, h->read0.p, n_read);
+  rc = build_index(h, h->read_ix, h->read0.p, n_read, false);
   if (rc) return rc;
   const float4* read_s = h->read_ix.pts.p;
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
@@ -550,20 +668,39 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
                 h->st->mu, h->ref_ix.n};      // queries are in the centred frame: + mu reaches the frame of the keys
   LoopParams lp{cfg.ratio, cfg.max_iterations, cfg.min_diff_rot, cfg.min_diff_trans, cfg.smooth_length};
   const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
+  CUDA_TRY(h->cand.reserve((size_t)n_read));
+  // Loop control lives on the device.  The host enqueues the iterations the differential checker cannot stop before
+  // (smoothLength) blindly, then stays at most LOOKAHEAD iterations ahead of the device by watching the iteration
+  // counter that the solve publishes in mapped pinned memory; iterations enqueued after convergence return at once.
+  const int LOOKAHEAD = 2;
+  volatile int* prog = h->progress_host;
+  int* prog_dev = h->comm ? nullptr : h->progress_dev;
+  prog[0] = 0; prog[1] = 0;           // the stream is idle here: every earlier call ended with a synchronisation
+  int enqueued = 0;
   for (int it = 0; it < cfg.max_iterations; ++it) {
+    if (!h->comm && it >= cfg.smooth_length && it >= LOOKAHEAD) {
+      unsigned spins = 0;
+      while (prog[1] == 0 && prog[0] < it - LOOKAHEAD + 1) {
+        if ((++spins & 0x3FFu) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;   // stream drained or failed: stop waiting
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      if (prog[1] != 0) break;
+    }
     mark(3 + 4 * (size_t)it);
     if (!h->comm) {
-      k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 1);
+      k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 1, prog_dev);
       mark(4 + 4 * (size_t)it);
-      k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 2, cfg.ratio, 1);
-      k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, 3, cfg.ratio, 1);
+      k_select23<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->cand.p, prog_dev);
       mark(5 + 4 * (size_t)it);
-      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1);
+      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1, prog_dev);
       mark(6 + 4 * (size_t)it);
+      h->launches += 3;
     } else {
       // reading sharded over the ranks: the trimmed quantile is GLOBAL, so each radix-select digit is
       // picked from the all-reduced histogram; then the 27 normal-equation partials (+ count) are all-reduced
-      k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 0);
+      k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 0, nullptr);
       if ((rc = comm_allreduce_u32(h, h->hist.p, AICP_HIST_BINS))) return rc;
       k_pick<<<1, 256, 0, s>>>(h->st, h->hist.p, 1, cfg.ratio);
       mark(4 + 4 * (size_t)it);
@@ -573,16 +710,16 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
         k_pick<<<1, 256, 0, s>>>(h->st, h->hist.p, pass, cfg.ratio);
       }
       mark(5 + 4 * (size_t)it);
-      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 0);
+      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 0, nullptr);
       unsigned long long* limbs = comm_limbs(h);
       k_sums_to_limbs<<<1, 32, 0, s>>>(h->st, limbs);
       if ((rc = comm_allreduce_u64(h, limbs, 4 * AICP_NSUM + 1))) return rc;
       k_limbs_solve<<<1, 32, 0, s>>>(h->st, limbs, lp, n_read);
       mark(6 + 4 * (size_t)it);
-      h->launches += 5;
+      h->launches += 9;
     }
+    ++enqueued;
   }
-  h->launches += 4 * cfg.max_iterations;
   CUDA_TRY(cudaEventRecord(h->ev[2], s));
   k_finalize<<<1, 32, 0, s>>>(h->st);
   k_transform_out<<<blocks, 256, 0, s>>>(h->read_in.p, n_read, h->st, h->read_out.p);
@@ -609,12 +746,15 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
       float ms = 0.f;
       cudaEventElapsedTime(&stats->ms_index, h->prof_ev[0], h->prof_ev[1]);
       cudaEventElapsedTime(&stats->ms_normals, h->prof_ev[1], h->prof_ev[2]);
-      for (int it = 0; it < hs->iter && it < cfg.max_iterations; ++it) {
+      for (int it = 0; it < hs->iter && it < enqueued; ++it) {
         cudaEventElapsedTime(&ms, h->prof_ev[3 + 4 * it], h->prof_ev[4 + 4 * it]); stats->ms_match += ms;
         cudaEventElapsedTime(&ms, h->prof_ev[4 + 4 * it], h->prof_ev[5 + 4 * it]); stats->ms_select += ms;
         cudaEventElapsedTime(&ms, h->prof_ev[5 + 4 * it], h->prof_ev[6 + 4 * it]); stats->ms_accumulate += ms;
       }
     }
+    stats->ms_tail_pick = (float)((double)hs->tail_ns[0] * 1e-6);
+    stats->ms_tail_select = (float)((double)hs->tail_ns[1] * 1e-6);
+    stats->ms_tail_solve = (float)((double)hs->tail_ns[2] * 1e-6);
     int nt = hs->iter < AICP_B200_MAX_ITERS ? hs->iter : AICP_B200_MAX_ITERS;
     memcpy(stats->trace, hs->trace, sizeof(aicp_b200_iter_trace) * (size_t)nt);
   }

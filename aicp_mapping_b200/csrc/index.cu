@@ -40,25 +40,37 @@ __global__ void __launch_bounds__(256) k_index_stats(const float4* __restrict__ 
       cs[d] += __double2ll_rn((double)c[d] * AICP_CENTROID_SCALE);
     }
   }
-  // warp reduce
+  // warp reduce (integer min / max / add: order independent), then one set of atomics per BLOCK
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = __reduce_min_sync(0xFFFFFFFFu, lo[d]);
+    hi[d] = __reduce_max_sync(0xFFFFFFFFu, hi[d]);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      lo[d] = min(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], off));
-      hi[d] = max(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], off));
-      cs[d] += __shfl_xor_sync(0xFFFFFFFFu, cs[d], off);
-    }
-    bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, off);
+    for (int off = 16; off > 0; off >>= 1) cs[d] += __shfl_xor_sync(0xFFFFFFFFu, cs[d], off);
   }
-  if ((threadIdx.x & 31) == 0) {
+  bad = __any_sync(0xFFFFFFFFu, bad);
+  __shared__ int s_lo[8][3], s_hi[8][3], s_bad[8];
+  __shared__ long long s_cs[8][3];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      atomicMin(&m->bmin[d], lo[d]);
-      atomicMax(&m->bmax[d], hi[d]);
-      atomicAdd((unsigned long long*)&m->csum[d], (unsigned long long)cs[d]);
-    }
-    if (bad) atomicOr(&m->nonfinite, 1);
+    for (int d = 0; d < 3; ++d) { s_lo[w][d] = lo[d]; s_hi[w][d] = hi[d]; s_cs[w][d] = cs[d]; }
+    s_bad[w] = bad;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int d = threadIdx.x;
+    int l = s_lo[0][d], h = s_hi[0][d];
+    long long c = s_cs[0][d];
+    for (int k = 1; k < 8; ++k) { l = min(l, s_lo[k][d]); h = max(h, s_hi[k][d]); c += s_cs[k][d]; }
+    atomicMin(&m->bmin[d], l);
+    atomicMax(&m->bmax[d], h);
+    atomicAdd((unsigned long long*)&m->csum[d], (unsigned long long)c);
+  }
+  if (threadIdx.x == 3) {
+    int b = 0;
+    for (int k = 0; k < 8; ++k) b |= s_bad[k];
+    if (b) atomicOr(&m->nonfinite, 1);
   }
 }
 
@@ -177,19 +189,21 @@ __global__ void __launch_bounds__(256) k_refit(const float4* __restrict__ pts, i
   }
 }
 
-int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64) {
+int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64, bool with_tree) {
   if (n64 < 1 || n64 > (1ll << 28)) return fail(h, AICP_B200_ERR_BAD_ARG, "cloud size %lld out of range [1, 2^28]", (long long)n64);
   int n = (int)n64;
   cudaStream_t s = h->stream;
   if (!ix.meta) CUDA_TRY(cudaMalloc((void**)&ix.meta, sizeof(IndexMeta)));
   CUDA_TRY(ix.pts.reserve((size_t)n));
-  CUDA_TRY(ix.rec.reserve((size_t)4 * n));
-  CUDA_TRY(ix.node_meta.reserve((size_t)n));
+  if (with_tree) {
+    CUDA_TRY(ix.rec.reserve((size_t)4 * n));
+    CUDA_TRY(ix.node_meta.reserve((size_t)n));
+    CUDA_TRY(ix.flags.reserve((size_t)3 * n));          // arrival counters | parent of internal nodes | parent of points
+    CUDA_TRY(ix.owner.reserve((size_t)2 * n));          // owner8 | owner32
+    CUDA_TRY(ix.cell.reserve((size_t)n));
+  }
   CUDA_TRY(ix.keys.reserve((size_t)n)); CUDA_TRY(ix.keys_alt.reserve((size_t)n));
   CUDA_TRY(ix.vals.reserve((size_t)n)); CUDA_TRY(ix.vals_alt.reserve((size_t)n));
-  CUDA_TRY(ix.flags.reserve((size_t)3 * n));          // arrival counters | parent of internal nodes | parent of points
-  CUDA_TRY(ix.owner.reserve((size_t)2 * n));          // owner8 | owner32
-  CUDA_TRY(ix.cell.reserve((size_t)n));
   size_t tmp_bytes = 0;
   cub::DoubleBuffer<unsigned int> dk(ix.keys.p, ix.keys_alt.p), dv(ix.vals.p, ix.vals_alt.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, 30, s));
@@ -197,14 +211,14 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64)
 
   k_meta_init<<<1, 32, 0, s>>>(ix.meta);
   int blocks = (n + 255) / 256;
-  int stat_blocks = blocks < 148 * 4 ? blocks : 148 * 4;
+  int stat_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
   k_index_stats<<<stat_blocks, 256, 0, s>>>(pts_dev, n, ix.meta);
   k_quant_params<<<1, 32, 0, s>>>(ix.meta);
   k_morton_keys<<<blocks, 256, 0, s>>>(pts_dev, n, ix.meta, ix.keys.p, ix.vals.p);
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(ix.sort_tmp.p, tmp_bytes, dk, dv, n, 0, 30, s));
   k_gather<<<blocks, 256, 0, s>>>(pts_dev, dv.Current(), n, ix.pts.p);
   h->launches += 5 + 4;    // own kernels + the radix sort's passes
-  if (n > 1) {
+  if (n > 1 && with_tree) {
     int* flags = ix.flags.p;
     int* parent_int = flags + n;
     int* parent_leaf = flags + 2 * (size_t)n;

@@ -194,11 +194,14 @@ def run_b200(args, rank, world, local_rank):
         flush.zero_()
         torch.cuda.synchronize()
         T, stats, status, ms = reg.registerBatch(host_batch if use_host else dev_batch, ratios=batch_ratios, streams=S)
-        agg = dict(match=0.0, select=0.0, accumulate=0.0, index=0.0, normals=0.0, iters=0, launches=0, reg_ms=0.0)
+        agg = dict(match=0.0, select=0.0, accumulate=0.0, index=0.0, normals=0.0, iters=0, launches=0, reg_ms=0.0,
+                   tail_pick=0.0, tail_select=0.0, tail_solve=0.0, setup=0.0, loop=0.0)
         for s in stats:
             agg["match"] += s.ms_match; agg["select"] += s.ms_select; agg["accumulate"] += s.ms_accumulate
             agg["index"] += s.ms_index; agg["normals"] += s.ms_normals
             agg["iters"] += s.iterations; agg["launches"] += s.gpu_launches; agg["reg_ms"] += s.ms_total
+            agg["tail_pick"] += s.ms_tail_pick; agg["tail_select"] += s.ms_tail_select; agg["tail_solve"] += s.ms_tail_solve
+            agg["setup"] += s.ms_setup; agg["loop"] += s.ms_iterations
         return ms, agg
 
     def barrier():
@@ -281,7 +284,8 @@ def run_b200(args, rank, world, local_rank):
                 "roofline_registration": {"algorithmic_bytes": b_reg, "iterations_mean": I, "ms": reg_ms,
                                           "achieved": b_reg / (reg_ms * 1e-3) / 1e9, "frac": b_reg / (reg_ms * 1e-3) / 1e9 / peak,
                                           "unit": "GB/s"},
-                "stage_ms_per_registration": {k: agg[k] / (P * args.steps) for k in ("index", "normals", "match", "select", "accumulate")},
+                "stage_ms_per_registration": {k: agg[k] / (P * args.steps) for k in ("index", "normals", "match", "select", "accumulate", "tail_pick", "tail_select",
+                                                                                       "tail_solve", "setup", "loop", "reg_ms")},
                 "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(P * 2 * N_POINTS * 16),
                         "d2h_bytes_per_step": int(P * 64)},
                 "gpu_launches": int(agg["launches"]), "clocks": clocks, "wall_s": wall_s, "ratios": ratios}

@@ -79,7 +79,8 @@ typedef struct {
    * the iterations that actually ran */
   int32_t profiled;
   float   ms_index, ms_normals;       /* setup: Morton index build, SurfaceNormal filter */
-  float   ms_match, ms_select, ms_accumulate;   /* loop: k_match, 2 x k_select, k_accumulate(+solve) */
+  float   ms_match, ms_select, ms_accumulate;   /* loop: k_match, k_select23, k_accumulate(+solve) */
+  float   ms_tail_pick, ms_tail_select, ms_tail_solve;   /* of which: single-block tails (device globaltimer) */
   aicp_b200_iter_trace trace[AICP_B200_MAX_ITERS];
 } aicp_b200_stats;
 
