@@ -127,9 +127,9 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   for (int i = 0; i < 2; ++i) if (h->batch_ev[i]) cudaEventDestroy(h->batch_ev[i]);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_rec.release(); h->normals.release(); h->knn_pos.release();
+  h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_rec.release(); h->refc_cell.release(); h->normals.release(); h->knn_pos.release();
   h->read_in.release(); h->read_ix.release(); h->read0.release(); h->read_out.release(); h->read_init.release();
-  h->match_pos.release(); h->d2.release(); h->hist.release(); h->cand.release(); h->trace_idx.release();
+  h->match_pos.release(); h->d2.release(); h->hist.release(); h->cand.release(); h->acc_slots.release(); h->trace_idx.release();
   if (h->progress_host) cudaFreeHost((void*)h->progress_host);
   h->tmp_ix.release(); h->tmp_a.release(); h->tmp_b.release(); h->tmp_i.release(); h->tmp_f.release();
   h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release();

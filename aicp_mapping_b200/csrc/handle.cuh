@@ -35,14 +35,14 @@ struct SpatialIndex {
   DevBuf<unsigned int> keys, keys_alt, vals, vals_alt;
   DevBuf<int> flags;             // bottom-up refit arrival counters, parent links
   DevBuf<int> owner;             // per point: lowest node with > 8 (first n) resp. > 32 (next n) points above it
-  DevBuf<int2> cell;             // per internal node: (a Morton key of the node, common-prefix length in clz units)
+  DevBuf<float4> cellbox;        // per internal node: shrunk float box of the node's Morton cell (lo, hi), see search.cuh
   DevBuf<unsigned char> sort_tmp;
   IndexMeta* meta = nullptr;     // device
   int n = 0;
-  IndexView view() const { return IndexView{pts.p, rec.p, owner.p, owner.p + n, cell.p, meta, nullptr, n}; }
+  IndexView view() const { return IndexView{pts.p, rec.p, owner.p, owner.p + n, cellbox.p, n}; }
   void release() {
     pts.release(); rec.release(); node_meta.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release();
-    flags.release(); owner.release(); cell.release(); sort_tmp.release();
+    flags.release(); owner.release(); cellbox.release(); sort_tmp.release();
     if (meta) cudaFree(meta);
     meta = nullptr;
   }
@@ -65,6 +65,7 @@ struct Handle {
   SpatialIndex ref_ix;           // original frame (normals search)
   DevBuf<float4> refc_pts;       // centred points, Morton order
   DevBuf<float4> refc_rec;       // centred tree records
+  DevBuf<float4> refc_cell;      // centred cell boxes
   DevBuf<float4> normals;        // Morton order (nx,ny,nz,density)
   DevBuf<int> knn_pos;           // n x knn neighbour positions (Morton order), scratch of the normals filter
   int64_t n_ref = 0;
@@ -77,6 +78,7 @@ struct Handle {
   DevBuf<int> match_pos;
   DevBuf<float> d2;
   DevBuf<unsigned int> hist;
+  DevBuf<unsigned long long> acc_slots;   // normal-equation partial sums: ACC_SLOTS x 32 x (lo, hi), all zero between launches
   DevBuf<unsigned int> cand;     // d2 keys of the quantile's first-digit bin (k_select23)
   int64_t n_read = 0;
   bool has_init_reading = false;

@@ -78,8 +78,8 @@ __global__ void k_loop_init(DeviceState* st, const IndexMeta* __restrict__ meta,
 
 // reference' = reference - mean: points and tree records (float subtraction is monotone, so the boxes stay valid)
 __global__ void __launch_bounds__(256) k_centre(const float4* __restrict__ pts, int n, const float4* __restrict__ rec,
-                                                int n_rec4, const DeviceState* __restrict__ st, float4* __restrict__ pts_c,
-                                                float4* __restrict__ rec_c) {
+                                                int n_rec4, const float4* __restrict__ cell, const DeviceState* __restrict__ st,
+                                                float4* __restrict__ pts_c, float4* __restrict__ rec_c, float4* __restrict__ cell_c) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   float mx = st->mu[0], my = st->mu[1], mz = st->mu[2];
   if (i < n) {
@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(256) k_centre(const float4* __restrict__ pts, 
   if (i < n_rec4) {
     float4 b = __ldg(&rec[i]);
     rec_c[i] = make_float4(__fsub_rn(b.x, mx), __fsub_rn(b.y, my), __fsub_rn(b.z, mz), b.w);
+  }
+  if (i < n_rec4 / 2) {                                    // cell boxes: 2 float4 per node; infinite sides stay infinite
+    float4 b = __ldg(&cell[i]);
+    cell_c[i] = make_float4(__fsub_rn(b.x, mx), __fsub_rn(b.y, my), __fsub_rn(b.z, mz), b.w);
   }
 }
 
@@ -402,45 +406,59 @@ __device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams l
   if (!iterate) *(volatile int*)&st->done = 1;
 }
 
+#define ACC_SLOTS 64          // partial-sum slots: block b adds into slot b % ACC_SLOTS, the last block folds the slots
+#define ACC_PTS 2             // reading points per thread
+
 __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
                                                     const float4* __restrict__ read0, const int* __restrict__ match_pos,
                                                     const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp, int tail,
-                                                    volatile int* progress) {
+                                                    volatile int* progress, unsigned long long* slots) {
   if (ld_int(&st->done)) { publish_done(progress); return; }
   __shared__ float sT[16];
   __shared__ long long s_part[8][32];
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T_iter[threadIdx.x];
   __syncthreads();
   const float limit = st->limit;
+  // all independent loads first (distance, reading point, match), then the two gathers of the inliers: two memory
+  // round trips per thread instead of four
+  float d[ACC_PTS]; float4 r[ACC_PTS]; int pos[ACC_PTS]; bool in[ACC_PTS];
+#pragma unroll
+  for (int u = 0; u < ACC_PTS; ++u) {
+    const int i = blockIdx.x * (256 * ACC_PTS) + u * 256 + threadIdx.x;
+    d[u] = INFINITY; pos[u] = 0; r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) { d[u] = __ldg(&d2[i]); pos[u] = __ldg(&match_pos[i]); r[u] = __ldg(&read0[i]); }
+  }
+  float4 q[ACC_PTS], nr[ACC_PTS];
+#pragma unroll
+  for (int u = 0; u < ACC_PTS; ++u) {
+    in[u] = d[u] <= limit;                                     // TrimmedDist weight (A.4); false for NaN and padding
+    q[u] = nr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in[u]) { q[u] = __ldg(&refc[pos[u]]); nr[u] = __ldg(&normals[pos[u]]); }
+  }
   long long v[32];
 #pragma unroll
   for (int s = 0; s < 32; ++s) v[s] = 0;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    float d = __ldg(&d2[i]);
-    if (d <= limit) {                                        // TrimmedDist weight (A.4)
-      float4 r = __ldg(&read0[i]);
-      float3 p = xform_f(sT, r.x, r.y, r.z);
-      int pos = __ldg(&match_pos[i]);
-      float4 q = __ldg(&refc[pos]);
-      float4 nr = __ldg(&normals[pos]);
+#pragma unroll
+  for (int u = 0; u < ACC_PTS; ++u) {
+    if (in[u]) {
+      float3 p = xform_f(sT, r[u].x, r[u].y, r[u].z);
       float F[6];
-      F[0] = __fsub_rn(__fmul_rn(p.y, nr.z), __fmul_rn(p.z, nr.y));      // c = p x n
-      F[1] = __fsub_rn(__fmul_rn(p.z, nr.x), __fmul_rn(p.x, nr.z));
-      F[2] = __fsub_rn(__fmul_rn(p.x, nr.y), __fmul_rn(p.y, nr.x));
-      F[3] = nr.x; F[4] = nr.y; F[5] = nr.z;
-      float ddx = __fsub_rn(p.x, q.x), ddy = __fsub_rn(p.y, q.y), ddz = __fsub_rn(p.z, q.z);
-      float res = __fmul_rn(ddx, nr.x);
-      res = __fadd_rn(res, __fmul_rn(ddy, nr.y));
-      res = __fadd_rn(res, __fmul_rn(ddz, nr.z));
+      F[0] = __fsub_rn(__fmul_rn(p.y, nr[u].z), __fmul_rn(p.z, nr[u].y));      // c = p x n
+      F[1] = __fsub_rn(__fmul_rn(p.z, nr[u].x), __fmul_rn(p.x, nr[u].z));
+      F[2] = __fsub_rn(__fmul_rn(p.x, nr[u].y), __fmul_rn(p.y, nr[u].x));
+      F[3] = nr[u].x; F[4] = nr[u].y; F[5] = nr[u].z;
+      float ddx = __fsub_rn(p.x, q[u].x), ddy = __fsub_rn(p.y, q[u].y), ddz = __fsub_rn(p.z, q[u].z);
+      float res = __fmul_rn(ddx, nr[u].x);
+      res = __fadd_rn(res, __fmul_rn(ddy, nr[u].y));
+      res = __fadd_rn(res, __fmul_rn(ddz, nr[u].z));
       int s = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int b = a; b < 6; ++b) v[s++] = fixed_term(F[a], F[b]);
+        for (int b = a; b < 6; ++b) v[s++] += fixed_term(F[a], F[b]);
 #pragma unroll
-      for (int a = 0; a < 6; ++a) v[s++] = fixed_term(F[a], res);
-      v[27] = 1;
+      for (int a = 0; a < 6; ++a) v[s++] += fixed_term(F[a], res);
+      v[27] += 1;
     }
   }
   // transposed warp reduction: after 5 exchange rounds lane L holds the warp total of slot L (31 shuffles, not 32*5)
@@ -459,18 +477,50 @@ __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict_
   s_part[w][lane] = v[0];
   __syncthreads();
   if (w == 0) {
+    // |term| < 2^52 and a block holds 512 points, so the block total fits in 64 bits; the slots are 128-bit
     long long tot = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tot += s_part[k][lane];
-    if (lane < AICP_NSUM && tot != 0) atomic_add_128(&st->sum_lo[lane], &st->sum_hi[lane], tot);
+    unsigned long long* slot = slots + ((size_t)(blockIdx.x % ACC_SLOTS) * 32 + lane) * 2;
+    if (lane < AICP_NSUM && tot != 0) atomic_add_128(slot, (long long*)(slot + 1), tot);
   }
-  if (tail && block_is_last(&st->ticket[2])) {
-    if (threadIdx.x == 0) {
-      const unsigned long long t0 = global_ns();
-      solve_and_check(st, lp, n);
-      st->tail_ns[2] += global_ns() - t0;
-      publish_progress(progress, st->iter, *(volatile int*)&st->done);
+  if (!block_is_last(&st->ticket[2])) return;
+  // last block: fold the slots (and zero them for the next launch) into st->sum_*, then solve
+  const unsigned long long t0 = global_ns();
+  __shared__ unsigned long long s_lo[8][32];
+  __shared__ long long s_hi[8][32];
+  {
+    const int nslots = gridDim.x < ACC_SLOTS ? (int)gridDim.x : ACC_SLOTS;
+    unsigned long long lo = 0; long long hi = 0;
+    if (lane < AICP_NSUM) {
+      for (int g = w; g < nslots; g += 8) {
+        unsigned long long* slot = slots + ((size_t)g * 32 + lane) * 2;
+        unsigned long long l = __ldcg(slot); long long hh = (long long)__ldcg(slot + 1);
+        slot[0] = 0; slot[1] = 0;
+        unsigned long long nl = lo + l;
+        hi = hi + hh + (nl < lo ? 1 : 0);
+        lo = nl;
+      }
     }
+    s_lo[w][lane] = lo; s_hi[w][lane] = hi;
+  }
+  __syncthreads();
+  if (w == 0 && lane < AICP_NSUM) {
+    unsigned long long lo = 0; long long hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      unsigned long long nl = lo + s_lo[k][lane];
+      hi = hi + s_hi[k][lane] + (nl < lo ? 1 : 0);
+      lo = nl;
+    }
+    st->sum_lo[lane] = lo; st->sum_hi[lane] = hi;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tail && threadIdx.x == 0) {
+    solve_and_check(st, lp, n);
+    st->tail_ns[2] += global_ns() - t0;
+    publish_progress(progress, st->iter, *(volatile int*)&st->done);
   }
 }
 
@@ -572,6 +622,10 @@ static int ensure_state(Handle* h) {
     CUDA_TRY(h->hist.reserve(AICP_HIST_BINS));
     CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * h->hist.cap, h->stream));   // cudaMalloc does not zero
   }
+  if (h->acc_slots.cap < (size_t)ACC_SLOTS * 64) {
+    CUDA_TRY(h->acc_slots.reserve((size_t)ACC_SLOTS * 64));
+    CUDA_TRY(cudaMemsetAsync(h->acc_slots.p, 0, sizeof(unsigned long long) * h->acc_slots.cap, h->stream));
+  }
   static_assert(AICP_HIST_BINS == 2048, "select_pick assumes 256 threads x 8 bins");
   return AICP_B200_OK;
 }
@@ -615,6 +669,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     CUDA_TRY(h->normals.reserve((size_t)h->ref_ix.n));
     CUDA_TRY(h->refc_pts.reserve((size_t)h->ref_ix.n));
     CUDA_TRY(h->refc_rec.reserve((size_t)4 * h->ref_ix.n));
+    CUDA_TRY(h->refc_cell.reserve((size_t)2 * h->ref_ix.n));
     rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr);
     if (rc) return rc;
     h->ref_knn = cfg.knn_normals;
@@ -637,8 +692,8 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   if (rebuild_reference) {
     int n4 = 4 * (h->ref_ix.n - 1);
     int m = h->ref_ix.n > n4 ? h->ref_ix.n : n4;
-    k_centre<<<(m + 255) / 256, 256, 0, s>>>(h->ref_ix.pts.p, h->ref_ix.n, h->ref_ix.rec.p, n4, h->st, h->refc_pts.p,
-                                            h->refc_rec.p);
+    k_centre<<<(m + 255) / 256, 256, 0, s>>>(h->ref_ix.pts.p, h->ref_ix.n, h->ref_ix.rec.p, n4, h->ref_ix.cellbox.p, h->st,
+                                            h->refc_pts.p, h->refc_rec.p, h->refc_cell.p);
     h->launches += 1;
   }
   CUDA_TRY(h->read0.reserve((size_t)n_read));
@@ -664,10 +719,10 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
 
   if (h->comm && (rc = comm_begin_registration(h, n_read))) return rc;
-  IndexView cix{h->refc_pts.p, h->refc_rec.p, h->ref_ix.owner.p, h->ref_ix.owner.p + h->ref_ix.n, h->ref_ix.cell.p, h->ref_ix.meta,
-                h->st->mu, h->ref_ix.n};      // queries are in the centred frame: + mu reaches the frame of the keys
+  IndexView cix{h->refc_pts.p, h->refc_rec.p, h->ref_ix.owner.p, h->ref_ix.owner.p + h->ref_ix.n, h->refc_cell.p, h->ref_ix.n};
   LoopParams lp{cfg.ratio, cfg.max_iterations, cfg.min_diff_rot, cfg.min_diff_trans, cfg.smooth_length};
   const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
+  const int acc_blocks = (n_read + 256 * ACC_PTS - 1) / (256 * ACC_PTS);
   CUDA_TRY(h->cand.reserve((size_t)n_read));
   // Loop control lives on the device.  The host enqueues the iterations the differential checker cannot stop before
   // (smoothLength) blindly, then stays at most LOOKAHEAD iterations ahead of the device by watching the iteration
@@ -694,7 +749,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
       mark(4 + 4 * (size_t)it);
       k_select23<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->cand.p, prog_dev);
       mark(5 + 4 * (size_t)it);
-      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1, prog_dev);
+      k_accumulate<<<acc_blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1, prog_dev, h->acc_slots.p);
       mark(6 + 4 * (size_t)it);
       h->launches += 3;
     } else {
@@ -710,7 +765,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
         k_pick<<<1, 256, 0, s>>>(h->st, h->hist.p, pass, cfg.ratio);
       }
       mark(5 + 4 * (size_t)it);
-      k_accumulate<<<blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 0, nullptr);
+      k_accumulate<<<acc_blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 0, nullptr, h->acc_slots.p);
       unsigned long long* limbs = comm_limbs(h);
       k_sums_to_limbs<<<1, 32, 0, s>>>(h->st, limbs);
       if ((rc = comm_allreduce_u64(h, limbs, 4 * AICP_NSUM + 1))) return rc;

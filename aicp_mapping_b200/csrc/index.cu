@@ -82,6 +82,11 @@ __global__ void k_quant_params(IndexMeta* m) {
   float ext = fmaxf(ex, fmaxf(ey, ez));
   m->qlo[0] = lx; m->qlo[1] = ly; m->qlo[2] = lz;
   m->qscale = ext > 0.f ? 1023.0f / ext : 0.f;
+  // margin by which the per-node cell boxes are shrunk (search.cuh, ball_inside_node): 1 % of a cell + 1e-5 of the
+  // largest coordinate magnitude in either frame (the centred frame lies within the bounding box)
+  float amax = 0.f;
+  for (int d = 0; d < 3; ++d) amax = fmaxf(amax, fmaxf(fabsf(ordered_to_float(m->bmin[d])), fabsf(ordered_to_float(m->bmax[d]))));
+  m->cell_margin = (ext > 0.f ? 0.01f * ext / 1023.0f : 0.f) + 1e-5f * (amax + ext);
 }
 
 __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ pts, int n, const IndexMeta* __restrict__ m,
@@ -115,7 +120,8 @@ __device__ __forceinline__ int delta(const unsigned int* __restrict__ keys, int 
 
 __global__ void __launch_bounds__(256) k_radix_tree(const unsigned int* __restrict__ keys, int n, int4* __restrict__ meta,
                                                     int* __restrict__ parent_int, int* __restrict__ parent_leaf,
-                                                    int* __restrict__ owner8, int* __restrict__ owner32, int2* __restrict__ cell) {
+                                                    int* __restrict__ owner8, int* __restrict__ owner32,
+                                                    const IndexMeta* __restrict__ im, float4* __restrict__ cellbox) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -137,7 +143,29 @@ __global__ void __launch_bounds__(256) k_radix_tree(const unsigned int* __restri
   // dnode < 32: the node is a Morton cell (all keys sharing a prefix of the 30 key bits) -- the property the bottom-up
   // searches rely on to stop early; dnode >= 32 means the split is among equal keys (position bits) and proves nothing
   meta[i] = make_int4(first, gamma + 1, last + 1, dnode < 32 ? 1 : 0);
-  cell[i] = make_int2((int)__ldg(&keys[first]), dnode);
+  {
+    // float box of the node's Morton cell, shrunk by the margin (empty when the node splits equal keys)
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (dnode < 32) {
+      const int P = dnode - 2;                                   // known leading bits of the 30-bit key
+      const unsigned int key = __ldg(&keys[first]);
+      const float scale = im->qscale, margin = im->cell_margin;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        // bit b of axis a sits at key bit 3b + a; it is known when 3b + a >= 30 - P
+        int bmin = (30 - P - a + 2) / 3;
+        if (bmin < 0) bmin = 0;
+        const int na = bmin > 10 ? 0 : 10 - bmin;
+        const int shift = 10 - na;
+        const int c = (int)morton_compact10(key >> a);
+        const int cmin = (c >> shift) << shift, cmax = cmin + (1 << shift) - 1;
+        lo[a] = cmin <= 0 ? -INFINITY : im->qlo[a] + (float)cmin / scale + margin;
+        hi[a] = cmax >= 1023 ? INFINITY : im->qlo[a] + (float)(cmax + 1) / scale - margin;
+      }
+    }
+    cellbox[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    cellbox[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+  }
   if (first == gamma) parent_leaf[gamma] = (i << 1); else parent_int[gamma] = (i << 1);
   if (last == gamma + 1) parent_leaf[gamma + 1] = (i << 1) | 1; else parent_int[gamma + 1] = (i << 1) | 1;
   // owner of a point = the lowest node with MORE than LEAF points above it (code = node << 1 | side): where the
@@ -200,7 +228,7 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
     CUDA_TRY(ix.node_meta.reserve((size_t)n));
     CUDA_TRY(ix.flags.reserve((size_t)3 * n));          // arrival counters | parent of internal nodes | parent of points
     CUDA_TRY(ix.owner.reserve((size_t)2 * n));          // owner8 | owner32
-    CUDA_TRY(ix.cell.reserve((size_t)n));
+    CUDA_TRY(ix.cellbox.reserve((size_t)2 * n));
   }
   CUDA_TRY(ix.keys.reserve((size_t)n)); CUDA_TRY(ix.keys_alt.reserve((size_t)n));
   CUDA_TRY(ix.vals.reserve((size_t)n)); CUDA_TRY(ix.vals_alt.reserve((size_t)n));
@@ -223,7 +251,7 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
     int* parent_int = flags + n;
     int* parent_leaf = flags + 2 * (size_t)n;
     CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, s));
-    k_radix_tree<<<blocks, 256, 0, s>>>(dk.Current(), n, ix.node_meta.p, parent_int, parent_leaf, ix.owner.p, ix.owner.p + n, ix.cell.p);
+    k_radix_tree<<<blocks, 256, 0, s>>>(dk.Current(), n, ix.node_meta.p, parent_int, parent_leaf, ix.owner.p, ix.owner.p + n, ix.meta, ix.cellbox.p);
     k_refit<<<blocks, 256, 0, s>>>(ix.pts.p, n, ix.node_meta.p, parent_int, parent_leaf, ix.rec.p, flags);
     h->launches += 2;
   }

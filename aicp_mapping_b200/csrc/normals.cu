@@ -184,7 +184,6 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k
       int own = __ldg(&ix.owner32[i]);
       int node = own >> 1, side = own & 1;
       bool first_level = true;
-      BallKeys bk; bk.d2 = -1.f;
       while (true) {
         const float4* r = ix.rec + 4 * (size_t)node;            // same address in every lane: one broadcast access
         float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k
           knn_descend(ix, w, scode, sc, st_a, st_b, st_d);
         }
         if (up < 0) break;
-        if (ball_inside_node(ix, node, w.qx, w.qy, w.qz, w.worst_d, bk)) break;
+        if (ball_inside_node(ix, node, w.qx, w.qy, w.qz, w.worst_d)) break;
         side = (up >> 1) & 1;
         node = up >> 2;
       }

@@ -32,6 +32,7 @@ struct IndexMeta {
   int pad;
   float qlo[3];                  // Morton quantisation: cell = (int)((x - qlo) * qscale), clamped to [0, 1023]
   float qscale;
+  float cell_margin;             // how far the stored cell boxes are shrunk (see ball_inside_node)
 };
 
 struct IndexView {
@@ -39,9 +40,7 @@ struct IndexView {
   const float4* __restrict__ rec;
   const int* __restrict__ owner8;     // per point: (node << 1 | side) of the lowest node with more than 8 points above it
   const int* __restrict__ owner32;    // same for 32 points (warp k-NN chunks)
-  const int2* __restrict__ cell;      // per internal node: (a Morton key inside the node, common-prefix length = clz(first ^ last))
-  const IndexMeta* __restrict__ meta;
-  const float* __restrict__ shift;    // added to query coordinates to reach the frame the keys were built in (nullptr: none)
+  const float4* __restrict__ cellbox; // per internal node: [2i] = lo.xyz, [2i+1] = hi.xyz of the node's Morton cell, shrunk
   int n;
 };
 
@@ -50,6 +49,14 @@ __device__ __forceinline__ unsigned int morton_spread10(unsigned int v) {
   v = (v | (v << 8)) & 0x0300F00Fu;
   v = (v | (v << 4)) & 0x030C30C3u;
   v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__device__ __forceinline__ unsigned int morton_compact10(unsigned int v) {
+  v &= 0x09249249u;
+  v = (v | (v >> 2)) & 0x030C30C3u;
+  v = (v | (v >> 4)) & 0x0300F00Fu;
+  v = (v | (v >> 8)) & 0x030000FFu;
+  v = (v | (v >> 16)) & 0x000003FFu;
   return v;
 }
 
@@ -61,41 +68,20 @@ __device__ __forceinline__ unsigned int morton_key(int qx, int qy, int qz) {
   return morton_spread10((unsigned)qx) | (morton_spread10((unsigned)qy) << 1) | (morton_spread10((unsigned)qz) << 2);
 }
 
-// Stop test of the bottom-up searches: "can the ball (q, sqrt(d2)) reach outside node c?"
-// A node whose keys share exactly `len` leading bits (clz units of the 32-bit key word; the key uses bits 29..0) and that
-// is a Morton cell holds ALL indexed points whose key carries that prefix.  Every indexed point within the ball has a key
-// whose per-axis cell lies between the cells of the two extreme corners of a box around the ball (the quantisation is
-// monotone), so if both corner keys carry the node's prefix, no point outside the node is in the ball.
-// Slack: the query may live in a shifted frame (one extra rounding) and sqrt / subtraction round, so the radius is
-// inflated by a relative 2^-18 plus 1 % of a cell -- far more than any of those roundings.
-// The corner keys are cached and recomputed only when the bound changed; a node whose cell is narrower than the ball is
-// rejected before any key arithmetic.
-struct BallKeys {
-  unsigned int lo, hi;
-  float d2;          // bound the keys were computed for (-1: none yet)
-  float diam_cells;  // ball diameter in quantisation cells
-};
-
-__device__ __forceinline__ void ball_keys_update(const IndexView& ix, float qx, float qy, float qz, float d2, BallKeys& k) {
-  const float lx = ix.meta->qlo[0], ly = ix.meta->qlo[1], lz = ix.meta->qlo[2], sc = ix.meta->qscale;
-  if (ix.shift) { qx += ix.shift[0]; qy += ix.shift[1]; qz += ix.shift[2]; }
-  float r = sqrtf(d2);
-  r = r * 1.000004f + 0.01f / fmaxf(sc, 1e-30f) + 4e-6f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
-  k.lo = morton_key(morton_quant(qx - r, lx, sc), morton_quant(qy - r, ly, sc), morton_quant(qz - r, lz, sc));
-  k.hi = morton_key(morton_quant(qx + r, lx, sc), morton_quant(qy + r, ly, sc), morton_quant(qz + r, lz, sc));
-  k.d2 = d2;
-  k.diam_cells = 2.f * r * sc;
-}
-
-__device__ __forceinline__ bool ball_inside_node(const IndexView& ix, int node, float qx, float qy, float qz, float d2, BallKeys& k) {
-  int2 c = __ldg(&ix.cell[node]);
-  if (c.y >= 32) return false;                       // split among equal keys: not a Morton cell
-  // narrowest side of the node's cell, in quantisation cells: prefix of (c.y - 2) key bits = floor/ceil of a third per axis
-  int bits = c.y - 2;
-  int side_log2 = 10 - (bits + 2) / 3;
-  if (k.d2 != d2) ball_keys_update(ix, qx, qy, qz, d2, k);
-  if (k.diam_cells > (float)(1 << side_log2)) return false;
-  return __clz((int)(k.lo ^ (unsigned)c.x)) >= c.y && __clz((int)(k.hi ^ (unsigned)c.x)) >= c.y;
+// Stop test of the bottom-up searches: "can the ball (q, sqrt(d2)) reach a point outside node c?"
+// A node whose keys share a prefix of the 30 key bits and that is a Morton cell holds ALL indexed points whose key
+// carries that prefix, i.e. all points whose quantised coordinates fall into an axis-aligned range of cells.  index.cu
+// stores that range as a float box per node, shrunk by a margin (1 % of a quantisation cell + 1e-5 of the coordinate
+// magnitude) that exceeds every rounding between a coordinate and its cell (the quantisation, the centring shift of the
+// reference frame): a point whose key lies outside the prefix is strictly outside the stored box.  If the ball, with the
+// radius rounded up and the ends rounded outward, lies inside the box, no point outside the node can beat or tie the
+// current bound.  Sides that coincide with the clamped ends of the quantisation range are infinite; a node that splits
+// equal keys is not a cell and stores an empty box.
+__device__ __forceinline__ bool ball_inside_node(const IndexView& ix, int node, float qx, float qy, float qz, float d2) {
+  const float4 lo = __ldg(&ix.cellbox[2 * (size_t)node]), hi = __ldg(&ix.cellbox[2 * (size_t)node + 1]);
+  const float r = __fsqrt_ru(d2);
+  return __fsub_rd(qx, r) >= lo.x && __fadd_ru(qx, r) <= hi.x && __fsub_rd(qy, r) >= lo.y && __fadd_ru(qy, r) <= hi.y &&
+         __fsub_rd(qz, r) >= lo.z && __fadd_ru(qz, r) <= hi.z;
 }
 
 #define AICP_STACK 64
@@ -178,7 +164,6 @@ __device__ inline void nn_search_up(const IndexView& ix, float qx, float qy, flo
     int own = __ldg(&ix.owner8[seed_pos]);
     int node = own >> 1, side = own & 1;
     bool first_level = true;
-    BallKeys bk; bk.d2 = -1.f;
     while (true) {
       const float4* r = ix.rec + 4 * (size_t)node;
       float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
@@ -198,7 +183,7 @@ __device__ inline void nn_search_up(const IndexView& ix, float qx, float qy, flo
       }
       if (up < 0) break;                                   // root done
       // stop once the ball (q, best) cannot reach outside this node (see ball_inside_node)
-      if (ball_inside_node(ix, node, qx, qy, qz, b.d, bk)) break;
+      if (ball_inside_node(ix, node, qx, qy, qz, b.d)) break;
       side = (up >> 1) & 1;
       node = up >> 2;
     }
