@@ -264,7 +264,7 @@ int aicp_b200_enable_match_trace(aicp_b200_handle* hh, int enable) {
 int aicp_b200_set_profiling(aicp_b200_handle* hh, int enable) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   if (!h) return AICP_B200_ERR_BAD_ARG;
-  h->profiling = enable != 0;
+  h->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   return AICP_B200_OK;
 }
 

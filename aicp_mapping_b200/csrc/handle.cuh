@@ -90,7 +90,7 @@ struct Handle {
   int* progress_dev = nullptr;             // the same two words, device address
   DevBuf<int> trace_idx;
   bool trace_matches = false;
-  bool profiling = false;
+  int profiling = 0;             // 0 off, 1 CUDA events around k_match only, 2 around every stage
   std::vector<cudaEvent_t> prof_ev;   // 3 setup + 4 per iteration
   int64_t trace_iters = 0, trace_n = 0;
 

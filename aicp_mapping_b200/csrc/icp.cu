@@ -652,12 +652,13 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   if (!(cfg.ratio > 0.f) || cfg.ratio > 1.f) return fail(h, AICP_B200_ERR_BAD_ARG, "TrimmedDistOutlierFilter ratio %g outside (0,1]", cfg.ratio);
   const int n_read = (int)h->n_read, n_ref = (int)h->n_ref;
   h->launches = 0;
-  const bool prof = h->profiling;
+  const int prof = h->profiling;
   if (prof) {
     size_t need = 3 + 4 * (size_t)cfg.max_iterations;
     while (h->prof_ev.size() < need) { cudaEvent_t e; CUDA_TRY(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
   }
-  auto mark = [&](size_t i) { if (prof) cudaEventRecord(h->prof_ev[i], s); };
+  auto mark = [&](size_t i) { if (prof >= 2) cudaEventRecord(h->prof_ev[i], s); };
+  auto mark_match = [&](size_t i) { if (prof >= 1) cudaEventRecord(h->prof_ev[i], s); };
   CUDA_TRY(cudaEventRecord(h->ev[0], s));
   mark(0);
 
@@ -743,10 +744,10 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
       }
       if (prog[1] != 0) break;
     }
-    mark(3 + 4 * (size_t)it);
+    mark_match(3 + 4 * (size_t)it);
     if (!h->comm) {
       k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 1, prog_dev);
-      mark(4 + 4 * (size_t)it);
+      mark_match(4 + 4 * (size_t)it);
       k_select23<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->cand.p, prog_dev);
       mark(5 + 4 * (size_t)it);
       k_accumulate<<<acc_blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1, prog_dev, h->acc_slots.p);
@@ -758,7 +759,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
       k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 0, nullptr);
       if ((rc = comm_allreduce_u32(h, h->hist.p, AICP_HIST_BINS))) return rc;
       k_pick<<<1, 256, 0, s>>>(h->st, h->hist.p, 1, cfg.ratio);
-      mark(4 + 4 * (size_t)it);
+      mark_match(4 + 4 * (size_t)it);
       for (int pass = 2; pass <= 3; ++pass) {
         k_select<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->hist.p, pass, cfg.ratio, 0);
         if ((rc = comm_allreduce_u32(h, h->hist.p, AICP_HIST_BINS))) return rc;
@@ -797,12 +798,15 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     cudaEventElapsedTime(&stats->ms_iterations, h->ev[1], h->ev[2]);
     stats->gpu_launches = h->launches;
     if (prof) {
-      stats->profiled = 1;
+      stats->profiled = prof;
       float ms = 0.f;
-      cudaEventElapsedTime(&stats->ms_index, h->prof_ev[0], h->prof_ev[1]);
-      cudaEventElapsedTime(&stats->ms_normals, h->prof_ev[1], h->prof_ev[2]);
+      if (prof >= 2) {
+        cudaEventElapsedTime(&stats->ms_index, h->prof_ev[0], h->prof_ev[1]);
+        cudaEventElapsedTime(&stats->ms_normals, h->prof_ev[1], h->prof_ev[2]);
+      }
       for (int it = 0; it < hs->iter && it < enqueued; ++it) {
         cudaEventElapsedTime(&ms, h->prof_ev[3 + 4 * it], h->prof_ev[4 + 4 * it]); stats->ms_match += ms;
+        if (prof < 2) continue;
         cudaEventElapsedTime(&ms, h->prof_ev[4 + 4 * it], h->prof_ev[5 + 4 * it]); stats->ms_select += ms;
         cudaEventElapsedTime(&ms, h->prof_ev[5 + 4 * it], h->prof_ev[6 + 4 * it]); stats->ms_accumulate += ms;
       }

@@ -240,8 +240,9 @@ class B200Registration:
     def enableMatchTrace(self, enable=True):
         self._check(self._lib.aicp_b200_enable_match_trace(self._h, int(enable)))
 
-    def setProfiling(self, enable=True):
-        self._check(self._lib.aicp_b200_set_profiling(self._h, int(enable)))
+    def setProfiling(self, level=2):
+        """0 off, 1 CUDA events around k_match only, 2 around every stage (stats.ms_*)."""
+        self._check(self._lib.aicp_b200_set_profiling(self._h, int(level)))
 
     def getTraceMatches(self):
         it, n = int(self.stats.iterations), int(self.stats.n_read)

@@ -61,7 +61,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -173,7 +173,7 @@ def run_b200(args, rank, world, local_rank):
     pairs = [load_pair(t) for t in trials]
     reg = ab.B200Registration(device=local_rank)
     ovl = ab.B200Overlap(device=local_rank)
-    reg.setProfiling(True)
+    reg.setProfiling(0 if args.no_profile else 1)     # CUDA events around k_match only inside the timed region
     dev, host, ratios = [], [], []
     for p in pairs:
         ovl.computeOverlap(p["ref"], p["read"], p["ref_origin"], p["read_origin"])
@@ -238,6 +238,16 @@ def run_b200(args, rank, world, local_rank):
         e2e_s += time.perf_counter() - t0
     barrier()
 
+    # per-stage breakdown: a separate, untimed pass with CUDA events around every stage (costs ~5 % throughput)
+    stage = None
+    if not args.profile_run and not args.no_profile:
+        reg.setProfiling(2)
+        for _ in range(2):
+            _, a = one_step(False)
+            stage = a if stage is None else {k: stage[k] + a[k] for k in stage}
+        reg.setProfiling(1)
+        barrier()
+
     # single-stream latency of one registration (no concurrency), for the roofline of the dominant kernel in isolation
     lat = dict(ms=0.0, match=0.0, iters=0, n=0)
     for k in range(0 if args.profile_run else len(pairs)):
@@ -265,7 +275,7 @@ def run_b200(args, rank, world, local_rank):
         n_launch_match = iters_total                                   # k_match launches that did work
         match_ms = agg["match"] / max(1, n_launch_match)
         alg_match = 24.0 * N_POINTS                                    # read point 16 + write pos 4 + d2 4
-        achieved = alg_match / (match_ms * 1e-3) / 1e9
+        achieved = alg_match / (match_ms * 1e-3) / 1e9 if match_ms > 0 else 0.0
         I = iters_total / (P * args.steps)
         b_reg = 72.0 * N_POINTS + I * 84.0 * N_POINTS + 32.0 * N_POINTS
         reg_ms = dev_ms / (P * args.steps)          # amortised device time per registration with S streams busy
@@ -284,8 +294,10 @@ def run_b200(args, rank, world, local_rank):
                 "roofline_registration": {"algorithmic_bytes": b_reg, "iterations_mean": I, "ms": reg_ms,
                                           "achieved": b_reg / (reg_ms * 1e-3) / 1e9, "frac": b_reg / (reg_ms * 1e-3) / 1e9 / peak,
                                           "unit": "GB/s"},
-                "stage_ms_per_registration": {k: agg[k] / (P * args.steps) for k in ("index", "normals", "match", "select", "accumulate", "tail_pick", "tail_select",
-                                                                                       "tail_solve", "setup", "loop", "reg_ms")},
+                "stage_ms_per_registration": None if stage is None else dict(
+                    {k: stage[k] / (P * 2) for k in ("index", "normals", "match", "select", "accumulate", "tail_pick", "tail_select",
+                                                     "tail_solve", "setup", "loop", "reg_ms")},
+                    note="separate untimed pass with CUDA events around every stage; per-stream times while %d registrations share the GPU" % S),
                 "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(P * 2 * N_POINTS * 16),
                         "d2h_bytes_per_step": int(P * 64)},
                 "gpu_launches": int(agg["launches"]), "clocks": clocks, "wall_s": wall_s, "ratios": ratios}
@@ -308,12 +320,13 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=16, help="cloud pairs registered per GPU per step")
-    ap.add_argument("--streams", type=int, default=4, help="concurrent registrations per GPU (CUDA streams)")
+    ap.add_argument("--pairs", type=int, default=64, help="cloud pairs registered per GPU per step")
+    ap.add_argument("--streams", type=int, default=8, help="concurrent registrations per GPU (CUDA streams)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-profile", action="store_true", help="no per-stage CUDA events inside the registrations")
     ap.add_argument("--profile-run", action="store_true", help="device-resident leg only (the command profiled under ncu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -75,8 +75,8 @@ typedef struct {
   float   ms_setup;                   /* index + normals + centring */
   float   ms_iterations;              /* ICP loop */
   int32_t gpu_launches;               /* kernels launched by this call */
-  /* filled only when aicp_b200_set_profiling(h, 1): CUDA-event time of each stage on the handle's stream, summed over
-   * the iterations that actually ran */
+  /* filled only when aicp_b200_set_profiling(h, level > 0): CUDA-event time of each stage on the handle's stream, summed
+   * over the iterations that actually ran (level 1: ms_match only) */
   int32_t profiled;
   float   ms_index, ms_normals;       /* setup: Morton index build, SurfaceNormal filter */
   float   ms_match, ms_select, ms_accumulate;   /* loop: k_match, k_select23, k_accumulate(+solve) */
@@ -134,8 +134,9 @@ int aicp_b200_get_reference_normals(aicp_b200_handle* h, float* normals_xyzd, in
 /* parity instrumentation: when enabled the next registrations record the correspondence (original reference index)
  * of every reading point at every iteration; fetch with get_trace_matches (iters x n_read int32, row per iteration) */
 int aicp_b200_enable_match_trace(aicp_b200_handle* h, int enable);
-/* measurement instrumentation: record CUDA events around every stage of the next registrations (see aicp_b200_stats) */
-int aicp_b200_set_profiling(aicp_b200_handle* h, int enable);
+/* measurement instrumentation for the next registrations (see aicp_b200_stats): level 0 none, 1 CUDA events around the
+ * dominant kernel (k_match) only, 2 around every stage (costs ~5 % throughput) */
+int aicp_b200_set_profiling(aicp_b200_handle* h, int level);
 int aicp_b200_get_trace_matches(aicp_b200_handle* h, int32_t* idx, int64_t iters, int64_t n_read);
 
 /* ---- stage entry points (same kernels as aicp_b200_register; exposed for the parity tests) -----------------------

@@ -1,0 +1,106 @@
+"""GPU tests for the BASELINE.json configurations beyond the headline pair: C4 (localisation against a fixed map) and C5
+(batched validation sweep).  Reduced sizes are compared bit for bit with the oracle; BASELINE's full sizes are checked
+through size-independent properties (exact NN against a brute-force sample, decrease of the trimmed objective, determinism,
+idempotence of the output cloud, batch == sequential)."""
+import numpy as np
+import pytest
+
+import aicp_mapping_b200 as ab
+from aicp_mapping_b200 import capi, synth
+from conftest import rot_angle
+
+pytestmark = pytest.mark.gpu
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def reg():
+    r = ab.B200Registration()
+    yield r
+    r.close()
+
+
+def test_c4_reduced_map_parity_with_oracle(reg, orc):
+    """Fixed map (400k points) + two readings (30k): set_reference once, register twice; every reading's trajectory is
+    bit-identical to the oracle's full ICP on (map, reading)."""
+    case = synth.make_map_case(n_map=400_000, n_read=30_000, trial=1, n_poses=2)
+    reg.setConfig(ratio=0.5, max_iterations=20)          # app.cpp:123-127: overlap forced to 50 % against a prior map
+    reg.setReference(case["map"])
+    reg.enableMatchTrace(True)
+    for rd in case["readings"]:
+        T = reg.registerToReference(rd["read"])
+        o = orc.icp(case["map"], rd["read"], orc.default_config(ratio=0.5, threads=8), want_trace_idx=True)
+        assert o.rc == 0 and reg.stats.iterations == o.iterations
+        assert np.array_equal(reg.getTraceMatches(), o.trace_idx)
+        assert np.array_equal(u32(T), u32(o.T))
+        # and the registration undoes the injected prior error (the map is noisy: centimetres, not micrometres)
+        d = T.astype(np.float64) @ np.linalg.inv(rd["T_true"])
+        assert np.linalg.norm(d[:3, 3]) < 0.05 and rot_angle(d[:3, :3]) < 0.01
+    reg.enableMatchTrace(False)
+
+
+def test_c4_full_size_map_properties(reg):
+    """BASELINE config 4 at full size: 122 880-point reading against a 10 485 760-point map."""
+    case = synth.make_map_case(n_map=10_485_760, n_read=122_880, trial=0, n_poses=1)
+    mp, rd = case["map"], case["readings"][0]
+    # (1) exact NN on the full map: a sample of queries against a float32 brute force with the oracle's operation order
+    rng = np.random.default_rng(7)
+    sample = rd["read"][rng.choice(len(rd["read"]), 96, replace=False)]
+    idx, d2 = reg.match(mp, sample)
+    for q, i, d in zip(sample, idx, d2):
+        df = mp - q[None, :]
+        dd = (df[:, 0] * df[:, 0] + df[:, 1] * df[:, 1]) + df[:, 2] * df[:, 2]
+        j = int(np.argmin(dd))                       # first minimum == lowest index on ties
+        assert i == j and np.float32(d) == dd[j]
+    # (2) localisation lowers the trimmed point-to-map objective (the campus map is sampled on every face, visible or
+    #     not, and is weakly constrained along the boulevard, so the pose error itself is only bounded loosely)
+    reg.setConfig(ratio=0.5, max_iterations=20)
+    reg.setReference(mp)
+    T = reg.registerToReference(rd["read"])
+    it = reg.stats.iterations
+    aligned = reg.getOutputReading()[:, :3]
+    probe = rng.choice(len(aligned), 4096, replace=False)
+
+    def trimmed(cloud):
+        _, dd = reg.match(mp, cloud[probe])
+        return float(np.sort(dd)[:len(dd) // 2].mean())
+    before, after = trimmed(rd["read"]), trimmed(aligned)
+    assert after < 0.5 * before, (before, after)
+    d = T.astype(np.float64) @ np.linalg.inv(rd["T_true"])
+    assert np.linalg.norm(d[:3, 3]) < 1.0 and rot_angle(d[:3, :3]) < 0.05
+    reg.setReference(mp)                                   # reg.match used the scratch index; the map index is kept
+    T = reg.registerToReference(rd["read"])
+    # (3) deterministic and reference reuse is stateless: the same call again gives the same bits
+    T2 = reg.registerToReference(rd["read"])
+    assert np.array_equal(u32(T), u32(T2)) and reg.stats.iterations == it
+    # (4) idempotence: registering the aligned output is (nearly) a no-op
+    out = reg.getOutputReading()[:, :3]
+    T3 = reg.registerToReference(out)
+    assert np.linalg.norm(T3[:3, 3]) < 0.02 and rot_angle(T3[:3, :3]) < 0.005
+
+
+def test_c5_batch_of_perturbed_pairs(reg, orc):
+    """BASELINE config 5 (scaled to 48 pairs of 38 400 points): the concurrent batch equals one-by-one calls bit for bit,
+    three of the pairs are checked against the oracle, and every pair recovers its perturbation."""
+    ov = ab.B200Overlap()
+    pairs = [synth.make_pair(5, t) for t in range(48)]
+    ratios = []
+    for p in pairs:
+        ov.computeOverlap(p["ref"], p["read"], p["ref_origin"], p["read_origin"])
+        ratios.append(ab.autotune_ratio(float(ov.getOverlap())))
+    ov.close()
+    reg.setConfig(max_iterations=20)
+    T, stats, status, ms = reg.registerBatch([(p["ref"], p["read"]) for p in pairs], ratios=ratios, streams=8)
+    assert all(s == 0 for s in status) and ms > 0
+    for t in (0, 17, 47):
+        reg.setConfig(ratio=ratios[t], max_iterations=20)
+        Ts = reg.registerClouds(pairs[t]["ref"], pairs[t]["read"])
+        assert np.array_equal(u32(Ts), u32(T[t]))
+        o = orc.icp(pairs[t]["ref"], pairs[t]["read"], orc.default_config(ratio=ratios[t], threads=8))
+        assert o.rc == 0 and np.array_equal(u32(o.T), u32(T[t])) and o.iterations == stats[t].iterations
+    for p, Tp in zip(pairs, T):
+        d = Tp.astype(np.float64) @ np.linalg.inv(p["T_true"])
+        assert np.linalg.norm(d[:3, 3]) < 0.02 and rot_angle(d[:3, :3]) < 0.01

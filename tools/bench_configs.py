@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE.json configurations that are not the bench.py headline (C3): one JSON line each.
+
+    python tools/bench_configs.py [--configs 2,4,5,overlap] [--streams 8]
+
+  C2  VLP-16 ANYmal-shaped 32 768 x 32 768 pairs, batched (registrations/s)
+  C4  122 880-point readings against a fixed 10 485 760-point map on ONE GPU: map index + normals built once
+      (reported), then registrations/s and ms per registration with the map resident
+  C5  validation sweep: 4096 registrations of 38 400-point cube pairs (16 distinct perturbations cycled), batched
+  overlap  the octree-overlap parameter of the C3 pair (ms per call, voxel counts)
+All inputs are device-resident when timing starts unless the line says e2e.  Single GPU; see bench.py for multi-GPU.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="2,4,5,overlap")
+    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--map-points", type=int, default=10485760)
+    args = ap.parse_args()
+    import torch
+    import aicp_mapping_b200 as ab
+    from aicp_mapping_b200 import capi, synth
+    want = args.configs.split(",")
+    reg = ab.B200Registration(device=0)
+    ovl = ab.B200Overlap(device=0)
+
+    def dev(a):
+        return torch.from_numpy(capi.to_xyzw(a)).cuda()
+
+    def batch_line(name, pairs, n_total, streams):
+        ratios = []
+        for p in pairs:
+            ovl.computeOverlap(p["ref"], p["read"], p["ref_origin"], p["read_origin"])
+            ratios.append(ab.autotune_ratio(float(ovl.getOverlap())))
+        dpairs = [(dev(p["ref"]), dev(p["read"])) for p in pairs]
+        order = [i % len(pairs) for i in range(n_total)]
+        batch = [dpairs[i] for i in order]
+        rat = [ratios[i] for i in order]
+        reg.setConfig(max_iterations=20)
+        reg.setProfiling(0)
+        reg.registerBatch(batch[:4 * streams], ratios=rat[:4 * streams], streams=streams)       # warm-up (allocations)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        T, stats, status, ms = reg.registerBatch(batch, ratios=rat, streams=streams)
+        wall = time.perf_counter() - t0
+        iters = float(np.mean([s.iterations for s in stats]))
+        err_t = max(float(np.linalg.norm((T[i].astype(np.float64) @ np.linalg.inv(pairs[order[i]]["T_true"]))[:3, 3])) for i in range(min(n_total, 64)))
+        print(json.dumps({"config": name, "metric": "ICP registrations/sec", "value": n_total / (ms * 1e-3), "unit": "registrations/s",
+                          "registrations": n_total, "distinct_pairs": len(pairs), "points_per_cloud": int(pairs[0]["ref"].shape[0]),
+                          "streams": streams, "device_ms": ms, "wall_s": wall, "iterations_mean": iters,
+                          "failed": int(np.count_nonzero(status)), "max_translation_error_m_first64": err_t,
+                          "inputs": "device-resident"}), flush=True)
+
+    if "2" in want:
+        batch_line("C2 VLP-16 32768x32768", [synth.make_pair(2, t) for t in range(4)], 256, args.streams)
+    if "5" in want:
+        batch_line("C5 validation sweep, cube pairs 38400 pts", [synth.make_pair(5, t) for t in range(16)], 4096, args.streams)
+    if "overlap" in want:
+        p = synth.make_pair(3, 0)
+        r, q = dev(p["ref"]), dev(p["read"])
+        counts = ovl.computeOverlap(r, q, p["ref_origin"], p["read_origin"])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ovl.computeOverlap(r, q, p["ref_origin"], p["read_origin"])
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / 20 * 1e3
+        print(json.dumps({"config": "overlap of the C3 pair (131072 + 131072 rays, 0.2 m voxels)", "metric": "ms per computeOverlap",
+                          "value": ms, "unit": "ms", "overlap_pct": float(ovl.getOverlap()), "voxel_counts_AandB_A_B": [int(c) for c in counts],
+                          "inputs": "device-resident, host synchronised per call"}), flush=True)
+    if "4" in want:
+        t0 = time.perf_counter()
+        case = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=8)
+        gen_s = time.perf_counter() - t0
+        mp = dev(case["map"])
+        reads = [dev(r["read"]) for r in case["readings"]]
+        reg.setConfig(ratio=0.5, max_iterations=20)       # app.cpp:123-127
+        reg.setProfiling(2)
+        reg.setReference(mp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reg.registerToReference(reads[0])                 # builds the map index + normals
+        first_ms = (time.perf_counter() - t0) * 1e3
+        build = dict(index_ms=reg.stats.ms_index, normals_ms=reg.stats.ms_normals)
+        reg.setProfiling(0)
+        for r in reads[:2]:
+            reg.registerToReference(r)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n, iters, dev_ms, errs = 0, 0, 0.0, []
+        for rep in range(4):
+            for i, r in enumerate(reads):
+                T = reg.registerToReference(r)
+                n += 1; iters += reg.stats.iterations; dev_ms += reg.stats.ms_total
+                d = T.astype(np.float64) @ np.linalg.inv(case["readings"][i]["T_true"])
+                errs.append(float(np.linalg.norm(d[:3, 3])))
+        wall = time.perf_counter() - t0
+        print(json.dumps({"config": "C4 localisation: 122880-pt readings vs %d-pt fixed map, one GPU" % args.map_points,
+                          "metric": "ICP registrations/sec", "value": n / wall, "unit": "registrations/s", "registrations": n,
+                          "ms_per_registration_device": dev_ms / n, "ms_per_registration_wall": wall / n * 1e3,
+                          "iterations_mean": iters / n, "map_build_once": build, "first_call_ms": first_ms,
+                          "max_translation_error_m": max(errs), "synthetic_generation_s": gen_s,
+                          "inputs": "device-resident, one registration at a time (latency mode)"}), flush=True)
+    reg.close(); ovl.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,7 @@ import json
 try:
     d = json.loads(open("$OUT/${TAG}_bench_s$S.log").read().strip().splitlines()[-1])
     print("S=$S value %.1f e2e %.1f lat %.3f ms" % (d["value"], d["e2e"]["value"], d["latency_single_stream"]["ms_per_registration"]))
-    print("   ", {k: round(v, 4) for k, v in d["stage_ms_per_registration"].items()}, "launches", d["gpu_launches"])
+    print("   ", {k: (round(v, 4) if isinstance(v, float) else v) for k, v in d["stage_ms_per_registration"].items() if k != "note"}, "launches", d["gpu_launches"], "k_match ms", round(d["roofline"]["avg_launch_ms"], 4))
 except Exception as e:
     print("failed", e); print(open("$OUT/${TAG}_bench_s$S.log").read()[-2000:])
 PY
