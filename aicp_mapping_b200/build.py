@@ -34,7 +34,16 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: build an experiment copy (lib/libaicp_b200_<variant>.so with -D<define>...) next to the product
+    library; used by tools/ab_bench.py only."""
+    global LIB
+    lib_path = LIB if not variant else os.path.join(LIB_DIR, "libaicp_b200_%s.so" % variant)
+    obj_dir = OBJ_DIR if not variant else os.path.join(OBJ_DIR, variant)
+    return _build(force or bool(variant), verbose, lib_path, obj_dir, ["-D" + d for d in defines])
+
+
+def _build(force, verbose, LIB, OBJ_DIR, extra):
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdrs = _deps()
@@ -45,7 +54,7 @@ def build(force=False, verbose=False):
         op = os.path.join(OBJ_DIR, src.rsplit(".", 1)[0] + ".o")
         objs.append(op)
         if force or _stale(op, [sp] + hdrs + [os.path.abspath(__file__)]):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", sp, "-o", op]
+            cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", sp, "-o", op]
             jobs.append(cmd)
 
     def run(cmd):

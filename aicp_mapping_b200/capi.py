@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libaicp_b200.so")
+# AICP_B200_LIB selects an experiment build of the same library (tools/ab_bench.py); there is still no fallback
+LIB_PATH = os.environ.get("AICP_B200_LIB") or os.path.join(HERE, "lib", "libaicp_b200.so")
 MAX_ITERS = 256
 
 OK = 0
