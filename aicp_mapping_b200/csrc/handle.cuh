@@ -90,6 +90,8 @@ struct Handle {
   int* progress_dev = nullptr;             // the same two words, device address
   DevBuf<int> trace_idx;
   bool trace_matches = false;
+  int knn_schedule = 0;          // SurfaceNormal k-NN kernel: 0 auto, 1 warp per query (latency), 2 tile per warp (throughput)
+  bool batch_worker = false;     // this handle is one of the concurrent workers of aicp_b200_register_batch
   int profiling = 0;             // 0 off, 1 CUDA events around k_match only, 2 around every stage
   std::vector<cudaEvent_t> prof_ev;   // 3 setup + 4 per iteration
   int64_t trace_iters = 0, trace_n = 0;

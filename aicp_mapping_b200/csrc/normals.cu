@@ -215,6 +215,181 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k_knn_tile: one WARP per tile of 32 consecutive Morton-ordered points, one QUERY PER LANE.
+// The 32 queries of a tile are spatial neighbours, so they need almost the same candidates.  Instead of 32 tree walks
+// the warp does ONE: after scanning the tile itself (every lane then holds an upper bound rho_i on its k-th distance) it
+// climbs from the tile's leaf to the first ancestor whose Morton cell contains all 32 balls (q_i, rho_i) -- nothing
+// outside that ancestor can be a neighbour of any lane -- and walks that subtree once, nearest child first, pruning a
+// child when no lane's ball reaches its box.  A surviving chunk (<= 32 points) is staged in shared memory with one
+// coalesced load and every lane measures every point of it against its own query: ~12 instructions per candidate for 32
+// queries.  Each lane keeps its k best in a private max-heap in shared memory (column layout, conflict free), keyed by
+// the 64-bit (d2 bits, original index) so the order is the oracle's; a heap sort at the end lists them ascending.
+// Exactness: a candidate can enter lane i's heap only if (d2, id) < current worst; a subtree is pruned only when its box
+// distance exceeds every lane's current worst distance; bounds only shrink.  Result = the k smallest (d2, id) per query.
+#define TILE_WARPS 4
+#define KNN_INF_KEY 0x7F8000007FFFFFFFull
+
+__device__ __forceinline__ unsigned long long knn_key(float d, int id) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)id;
+}
+
+// per-lane max-heap of size k in shared memory; K / P already point at this lane's column (stride 32)
+__device__ __forceinline__ void heap_replace_top(unsigned long long* K, int* P, int k, unsigned long long key, int pos) {
+  int i = 0;
+  while (true) {
+    int c = 2 * i + 1;
+    if (c >= k) break;
+    unsigned long long kc = K[c * 32];
+    if (c + 1 < k) {
+      unsigned long long kr = K[(c + 1) * 32];
+      if (kr > kc) { kc = kr; ++c; }
+    }
+    if (kc <= key) break;
+    K[i * 32] = kc; P[i * 32] = P[c * 32];
+    i = c;
+  }
+  K[i * 32] = key; P[i * 32] = pos;
+}
+
+// every lane measures the points [first, first + cnt) (cnt <= 32) against its own query; positions in [skip_lo, skip_hi)
+// were scanned before.  Two steps, so that the expensive heap updates of the 32 lanes run side by side: (1) a
+// divergence-free pass marks, per lane, the candidates within the lane's current bound (a 32-bit mask); (2) rounds in
+// which every lane with a marked candidate left inserts its next one -- max_i popcount(mask_i) rounds instead of one
+// round per candidate that ANY lane accepts.
+__device__ __forceinline__ void tile_scan(const IndexView& ix, float4* s_pts, int first, int cnt, int skip_lo, int skip_hi,
+                                          float qx, float qy, float qz, bool active, unsigned long long* K, int* P, int k,
+                                          unsigned long long& top, int lane) {
+  if (lane < cnt) s_pts[lane] = __ldg(&ix.pts[first + lane]);
+  __syncwarp();
+  const float bound = __uint_as_float((unsigned int)(top >> 32));
+  unsigned int mask = 0;
+  for (int j = 0; j < cnt; ++j) {
+    const float4 p = s_pts[j];                                          // broadcast read
+    const float d = d2_f(qx, qy, qz, p.x, p.y, p.z);
+    if (d <= bound) mask |= 1u << j;
+  }
+  // drop the positions scanned before (warp-uniform range) and the padding lanes
+  const int lo = skip_lo - first, hi = skip_hi - first;
+  if (hi > 0 && lo < 32) {
+    const unsigned int upto_hi = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+    const unsigned int upto_lo = lo <= 0 ? 0u : ((1u << lo) - 1u);
+    mask &= ~(upto_hi & ~upto_lo);
+  }
+  if (!active) mask = 0;
+  while (__any_sync(0xFFFFFFFFu, mask != 0)) {
+    if (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float4 p = s_pts[j];
+      const float d = d2_f(qx, qy, qz, p.x, p.y, p.z);
+      const unsigned long long key = knn_key(d, __float_as_int(p.w));
+      if (key < top) { heap_replace_top(K, P, k, key, first + j); top = K[0]; }
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * TILE_WARPS) k_knn_tile(IndexView ix, int k, int* __restrict__ knn_pos,
+                                                              int* __restrict__ knn_out_orig) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tile = blockIdx.x * TILE_WARPS + wid;
+  const int i0 = tile * 32;
+  if (i0 >= ix.n) return;                                               // whole warp; no block-level barrier below
+  const size_t per_warp = (size_t)k * 32 * 12 + 512 + AICP_STACK * 4;
+  unsigned char* base = smem + per_warp * wid;
+  unsigned long long* K = reinterpret_cast<unsigned long long*>(base) + lane;
+  int* P = reinterpret_cast<int*>(base + (size_t)k * 32 * 8) + lane;
+  float4* s_pts = reinterpret_cast<float4*>(base + (size_t)k * 32 * 12);
+  int* stack = reinterpret_cast<int*>(base + (size_t)k * 32 * 12 + 512);
+  const int cnt0 = ix.n - i0 < 32 ? ix.n - i0 : 32;
+  const bool active = lane < cnt0;
+  const float4 q = __ldg(&ix.pts[i0 + (active ? lane : 0)]);
+  for (int s = 0; s < k; ++s) { K[s * 32] = KNN_INF_KEY; P[s * 32] = -1; }
+  unsigned long long top = KNN_INF_KEY;
+  tile_scan(ix, s_pts, i0, cnt0, 0, 0, q.x, q.y, q.z, active, K, P, k, top, lane);
+  // the two Morton-adjacent tiles as well: a tile that straddles a jump of the Morton curve holds too few points near
+  // each of its queries, and its bounds would otherwise cover the gap
+  int s_lo = i0, s_hi = i0 + cnt0;                                     // positions scanned so far
+  if (i0 >= 32) { tile_scan(ix, s_pts, i0 - 32, 32, 0, 0, q.x, q.y, q.z, active, K, P, k, top, lane); s_lo = i0 - 32; }
+  if (i0 + 32 < ix.n) {
+    const int c1 = ix.n - (i0 + 32) < 32 ? ix.n - (i0 + 32) : 32;
+    tile_scan(ix, s_pts, i0 + 32, c1, 0, 0, q.x, q.y, q.z, active, K, P, k, top, lane);
+    s_hi = i0 + 32 + c1;
+  }
+  if (ix.n > s_hi - s_lo) {
+    // box around the 32 balls (q_i, rho_i): radii rounded up, ends rounded outward
+    float blx = INFINITY, bly = INFINITY, blz = INFINITY, bhx = -INFINITY, bhy = -INFINITY, bhz = -INFINITY;
+    if (active) {
+      const float r = __fsqrt_ru(__uint_as_float((unsigned int)(top >> 32)));
+      blx = __fsub_rd(q.x, r); bly = __fsub_rd(q.y, r); blz = __fsub_rd(q.z, r);
+      bhx = __fadd_ru(q.x, r); bhy = __fadd_ru(q.y, r); bhz = __fadd_ru(q.z, r);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      blx = fminf(blx, __shfl_xor_sync(0xFFFFFFFFu, blx, off)); bhx = fmaxf(bhx, __shfl_xor_sync(0xFFFFFFFFu, bhx, off));
+      bly = fminf(bly, __shfl_xor_sync(0xFFFFFFFFu, bly, off)); bhy = fmaxf(bhy, __shfl_xor_sync(0xFFFFFFFFu, bhy, off));
+      blz = fminf(blz, __shfl_xor_sync(0xFFFFFFFFu, blz, off)); bhz = fmaxf(bhz, __shfl_xor_sync(0xFFFFFFFFu, bhz, off));
+    }
+    // climb to the first ancestor whose (shrunk) Morton cell holds the whole box: no point outside it is in any ball
+    int node = __ldg(&ix.owner32[i0]) >> 1;
+    while (true) {
+      const int up = __float_as_int(__ldg(&ix.rec[4 * (size_t)node + 3]).w);
+      if (up < 0) break;
+      const float4 clo = __ldg(&ix.cellbox[2 * (size_t)node]), chi = __ldg(&ix.cellbox[2 * (size_t)node + 1]);
+      if (blx >= clo.x && bly >= clo.y && blz >= clo.z && bhx <= chi.x && bhy <= chi.y && bhz <= chi.z) break;
+      node = up >> 2;
+    }
+    // one walk of that subtree for the whole tile
+    int sp = 0, code = node;
+    while (true) {
+      const float4* r = ix.rec + 4 * (size_t)code;                      // same address in every lane: broadcast
+      const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
+      const int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w);
+      const float dl = box_d2_f(make_float3(r0.x, r0.y, r0.z), make_float3(r1.x, r1.y, r1.z), q.x, q.y, q.z);
+      const float dr = box_d2_f(make_float3(r2.x, r2.y, r2.z), make_float3(r3.x, r3.y, r3.z), q.x, q.y, q.z);
+      // nearest child first (by the closest lane); children inside the already scanned positions are skipped
+      const unsigned int ml = __reduce_min_sync(0xFFFFFFFFu, active ? __float_as_uint(dl) : 0xFFFFFFFFu);
+      const unsigned int mr = __reduce_min_sync(0xFFFFFFFFu, active ? __float_as_uint(dr) : 0xFFFFFFFFu);
+      const bool lfirst = ml <= mr;
+      const bool own_l = first >= s_lo && split <= s_hi, own_r = split >= s_lo && end <= s_hi;
+      int next = -1;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool left = (pass == 0) == lfirst;
+        if (left ? own_l : own_r) continue;
+        const float dc = left ? dl : dr;
+        if (__ballot_sync(0xFFFFFFFFu, active && dc <= __uint_as_float((unsigned int)(top >> 32))) == 0u) continue;
+        const int cf = left ? first : split, cc = left ? split - first : end - split;
+        if (cc <= 32) tile_scan(ix, s_pts, cf, cc, s_lo, s_hi, q.x, q.y, q.z, active, K, P, k, top, lane);
+        else {
+          const int child = left ? split - 1 : split;
+          if (next < 0) next = child; else stack[sp++] = child;        // the nearer internal child goes first
+        }
+      }
+      if (next >= 0) code = next;
+      else if (sp > 0) code = stack[--sp];
+      else break;
+    }
+  }
+  // heap sort: ascending (d2, id) in slots 0..k-1
+  for (int m = k - 1; m > 0; --m) {
+    const unsigned long long km = K[m * 32];
+    const int pm = P[m * 32];
+    K[m * 32] = K[0]; P[m * 32] = P[0];
+    heap_replace_top(K, P, m, km, pm);
+  }
+  if (active) {
+    int* out = knn_pos + (size_t)(i0 + lane) * k;
+    for (int s = 0; s < k; ++s) out[s] = P[s * 32];
+    if (knn_out_orig) {
+      int* oo = knn_out_orig + (size_t)__float_as_int(q.w) * k;
+      for (int s = 0; s < k; ++s) oo[s] = (int)(unsigned int)K[s * 32];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) k_normals_from_knn(IndexView ix, int k, const int* __restrict__ knn_pos,
                                                           float4* __restrict__ normals_morton) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,7 +450,18 @@ int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* norm
   if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "SurfaceNormalDataPointsFilter: knn %d outside [1,32]", knn);
   if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "SurfaceNormalDataPointsFilter: knn %d >= %d points", knn, ix.n);
   CUDA_TRY(h->knn_pos.reserve((size_t)ix.n * knn));
-  k_knn_warp<<<(unsigned)((ix.n + KNN_WARPS * KNN_RUN - 1) / (KNN_WARPS * KNN_RUN)), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
+  // Two schedules of the same exact search (identical output): the tile kernel executes ~45 % fewer instructions and wins
+  // whenever the GPU is full (batched registrations, large clouds); the warp-per-query kernel has twice as many, shorter
+  // warps and wins the latency of ONE lidar-sized cloud on an otherwise idle GPU.
+  const bool tile = h->knn_schedule == 2 || (h->knn_schedule == 0 && (h->batch_worker || ix.n >= (1 << 20)));
+  if (!tile) {
+    k_knn_warp<<<(unsigned)((ix.n + KNN_WARPS * KNN_RUN - 1) / (KNN_WARPS * KNN_RUN)), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
+  } else {
+    const size_t smem = ((size_t)knn * 32 * 12 + 512 + AICP_STACK * 4) * TILE_WARPS;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (ix.n + 31) / 32;
+    k_knn_tile<<<(unsigned)((tiles + TILE_WARPS - 1) / TILE_WARPS), 32 * TILE_WARPS, smem, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
+  }
   k_normals_from_knn<<<(ix.n + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton);
   CUDA_TRY(cudaGetLastError());
   h->launches += 2;

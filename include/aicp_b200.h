@@ -138,6 +138,10 @@ int aicp_b200_enable_match_trace(aicp_b200_handle* h, int enable);
  * dominant kernel (k_match) only, 2 around every stage (costs ~5 % throughput) */
 int aicp_b200_set_profiling(aicp_b200_handle* h, int level);
 int aicp_b200_get_trace_matches(aicp_b200_handle* h, int32_t* idx, int64_t iters, int64_t n_read);
+/* kernel schedule of the SurfaceNormal k-NN search (identical results): 0 automatic (tile kernel for batched
+ * registrations and clouds >= 2^20 points, warp-per-query kernel otherwise), 1 warp per query, 2 one tile of 32 queries
+ * per warp.  Exposed for the parity tests and benchmarks. */
+int aicp_b200_set_knn_schedule(aicp_b200_handle* h, int schedule);
 
 /* ---- stage entry points (same kernels as aicp_b200_register; exposed for the parity tests) -----------------------
  * SurfaceNormalDataPointsFilter alone: out_normals n x 4, out_knn nullable n x knn (ids sorted by (d2, id)) */

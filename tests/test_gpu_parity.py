@@ -73,7 +73,10 @@ def test_match_bit_exact_full_size_lidar(reg, orc, pair_cache):
 
 
 # ---- normals ---------------------------------------------------------------------------------------------------------
-def test_surface_normals_parity_small_and_degenerate(reg, orc):
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_surface_normals_parity_small_and_degenerate(reg, orc, schedule):
+    """Both k-NN kernel schedules (1 warp per query, 2 tile per warp) against the oracle."""
+    reg.setKnnSchedule(schedule)
     rng = np.random.default_rng(12)
     pts = rng.uniform(-2, 2, (3000, 3)).astype(np.float32)
     pts[:, 2] = (0.3 * pts[:, 0] - 0.2 * pts[:, 1] + 0.01 * rng.normal(size=3000)).astype(np.float32)
@@ -89,14 +92,32 @@ def test_surface_normals_parity_small_and_degenerate(reg, orc):
     assert np.array_equal(u32(gn), u32(on)) and np.array_equal(gn[:, :3], np.tile(np.float32([0, 1, 0]), (200, 1)))
     with pytest.raises(capi.AicpError, match="KNN_TOO_LARGE"):
         reg.surfaceNormals(pts[:20], 20)
+    reg.setKnnSchedule(0)
 
 
-def test_surface_normals_parity_full_size(reg, orc, pair_cache):
+@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("n,knn", [(21, 20), (33, 20), (64, 10), (65, 32), (97, 5), (1000, 1), (4099, 30)])
+def test_surface_normals_ragged_sizes_and_knn(reg, orc, schedule, n, knn):
+    """Cloud sizes around the 32-point tile / chunk boundaries, knn from 1 to 32, lattice points (many exact ties)."""
+    reg.setKnnSchedule(schedule)
+    rng = np.random.default_rng(100 + n)
+    pts = (np.round(rng.uniform(-3, 3, (n, 3)) * 4) / 4).astype(np.float32)
+    gn, gk = reg.surfaceNormals(pts, knn)
+    on, ok = orc.surface_normals(pts, knn, use_kdtree=False)
+    assert np.array_equal(gk, ok)
+    assert np.array_equal(u32(gn), u32(on))
+    reg.setKnnSchedule(0)
+
+
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_surface_normals_parity_full_size(reg, orc, pair_cache, schedule):
+    reg.setKnnSchedule(schedule)
     pair = pair_cache(3, 0)
     gn, gk = reg.surfaceNormals(pair["ref"], 20)
     on, ok = orc.surface_normals(pair["ref"], 20, use_kdtree=True, threads=NCPU)
     assert np.array_equal(gk, ok)
     assert np.array_equal(u32(gn), u32(on))
+    reg.setKnnSchedule(0)
 
 
 # ---- trimmed quantile --------------------------------------------------------------------------------------------------
