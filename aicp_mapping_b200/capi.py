@@ -20,7 +20,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aic
            "aicp_b200_set_config_struct", "aicp_b200_get_config", "aicp_b200_parse_icp_yaml", "aicp_b200_register",
            "aicp_b200_set_reference", "aicp_b200_register_to_reference", "aicp_b200_get_output_reading",
            "aicp_b200_get_initialized_reading", "aicp_b200_get_reference_normals", "aicp_b200_enable_match_trace",
-           "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
+           "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
            "aicp_b200_overlap", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_comm_unique_id",
            "aicp_b200_comm_init", "aicp_b200_comm_destroy"]
 
@@ -85,6 +85,7 @@ def lib():
         L.aicp_b200_enable_match_trace.argtypes = [C.c_void_p, C.c_int]
         L.aicp_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.aicp_b200_set_knn_schedule.argtypes = [C.c_void_p, C.c_int]
+        L.aicp_b200_set_match_schedule.argtypes = [C.c_void_p, C.c_int]
         L.aicp_b200_get_trace_matches.argtypes = [C.c_void_p, C.c_void_p, i64, i64]
         L.aicp_b200_surface_normals.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_int32, C.c_void_p, C.c_void_p]
         L.aicp_b200_match.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p]

@@ -275,6 +275,13 @@ int aicp_b200_set_knn_schedule(aicp_b200_handle* hh, int schedule) {
   return AICP_B200_OK;
 }
 
+int aicp_b200_set_match_schedule(aicp_b200_handle* hh, int schedule) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || schedule < 0 || schedule > 2) return AICP_B200_ERR_BAD_ARG;
+  h->match_schedule = schedule;
+  return AICP_B200_OK;
+}
+
 int aicp_b200_get_trace_matches(aicp_b200_handle* hh, int32_t* idx, int64_t iters, int64_t n_read) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   H_CHECK(h);
@@ -391,7 +398,7 @@ int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float*
     Handle* wh = h->workers[w];
     wh->cfg = h->cfg; wh->cfg_from_file = false;
     wh->profiling = h->profiling; wh->trace_matches = false;
-    wh->batch_worker = streams > 1; wh->knn_schedule = h->knn_schedule;
+    wh->batch_worker = streams > 1; wh->knn_schedule = h->knn_schedule; wh->match_schedule = h->match_schedule;
     CUDA_TRY(cudaStreamWaitEvent(wh->stream, h->batch_ev[0], 0));
   }
   std::atomic<int64_t> next(0);

@@ -91,6 +91,7 @@ struct Handle {
   DevBuf<int> trace_idx;
   bool trace_matches = false;
   int knn_schedule = 0;          // SurfaceNormal k-NN kernel: 0 auto, 1 warp per query (latency), 2 tile per warp (throughput)
+  int match_schedule = 0;        // correspondence search kernel: 0 auto, 1 one query per thread (k_match), 2 one tile per warp (k_match_tile)
   bool batch_worker = false;     // this handle is one of the concurrent workers of aicp_b200_register_batch
   int profiling = 0;             // 0 off, 1 CUDA events around k_match only, 2 around every stage
   std::vector<cudaEvent_t> prof_ev;   // 3 setup + 4 per iteration

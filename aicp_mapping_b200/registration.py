@@ -248,6 +248,10 @@ class B200Registration:
         """0 automatic, 1 warp-per-query k-NN kernel, 2 tile kernel (identical results)."""
         self._check(self._lib.aicp_b200_set_knn_schedule(self._h, int(schedule)))
 
+    def setMatchSchedule(self, schedule=0):
+        """0 automatic, 1 per-thread correspondence search, 2 tile search (identical results)."""
+        self._check(self._lib.aicp_b200_set_match_schedule(self._h, int(schedule)))
+
     def getTraceMatches(self):
         it, n = int(self.stats.iterations), int(self.stats.n_read)
         out = np.zeros((it, n), dtype=np.int32)

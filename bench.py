@@ -173,6 +173,7 @@ def run_b200(args, rank, world, local_rank):
     pairs = [load_pair(t) for t in trials]
     reg = ab.B200Registration(device=local_rank)
     ovl = ab.B200Overlap(device=local_rank)
+    reg.setMatchSchedule(args.match_schedule)
     reg.setProfiling(0 if args.no_profile else 1)     # CUDA events around k_match only inside the timed region
     dev, host, ratios = [], [], []
     for p in pairs:
@@ -326,6 +327,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=64, help="cloud pairs registered per GPU per step")
     ap.add_argument("--streams", type=int, default=8, help="concurrent registrations per GPU (CUDA streams)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--match-schedule", type=int, default=0, help="0 auto, 1 per-thread search, 2 tile search (experiments)")
     ap.add_argument("--no-profile", action="store_true", help="no per-stage CUDA events inside the registrations")
     ap.add_argument("--profile-run", action="store_true", help="device-resident leg only (the command profiled under ncu)")
     args = ap.parse_args()

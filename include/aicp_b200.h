@@ -142,6 +142,9 @@ int aicp_b200_get_trace_matches(aicp_b200_handle* h, int32_t* idx, int64_t iters
  * registrations and clouds >= 2^20 points, warp-per-query kernel otherwise), 1 warp per query, 2 one tile of 32 queries
  * per warp.  Exposed for the parity tests and benchmarks. */
 int aicp_b200_set_knn_schedule(aicp_b200_handle* h, int schedule);
+/* kernel schedule of the ICP correspondence search (identical results): 0 automatic (tile kernel inside batched registrations), 1 one query per thread (k_match),
+ * 2 one tile of 32 queries per warp with a shared tree walk (k_match_tile) */
+int aicp_b200_set_match_schedule(aicp_b200_handle* h, int schedule);
 
 /* ---- stage entry points (same kernels as aicp_b200_register; exposed for the parity tests) -----------------------
  * SurfaceNormalDataPointsFilter alone: out_normals n x 4, out_knn nullable n x knn (ids sorted by (d2, id)) */

@@ -187,16 +187,40 @@ def test_icp_parity_c1_sample_scans(reg, orc):
         assert_full_parity(reg, T, o)
 
 
-def test_icp_parity_c2_vlp16(reg, orc, pair_cache):
+@pytest.mark.parametrize("match_schedule,knn_schedule", [(1, 1), (2, 2)])
+def test_icp_parity_c2_vlp16(reg, orc, pair_cache, match_schedule, knn_schedule):
+    """Whole trajectory against the oracle with the per-thread kernels (1, 1) and with the tile kernels (2, 2)."""
+    reg.setMatchSchedule(match_schedule); reg.setKnnSchedule(knn_schedule)
     pair = pair_cache(2, 0)
     T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.7)
     assert_full_parity(reg, T, o)
+    reg.setMatchSchedule(0); reg.setKnnSchedule(0)
+
+
+@pytest.mark.parametrize("n_ref,n_qry", [(20, 7), (33, 40), (100, 31), (5000, 1000)])
+def test_icp_tile_kernels_ragged_sizes(reg, orc, n_ref, n_qry):
+    """Tile kernels on cloud sizes around the 32-point tile boundary (partial warps, single-chunk references)."""
+    rng = np.random.default_rng(n_ref * 7 + n_qry)
+    ref = rng.uniform(-1, 1, (n_ref, 3)).astype(np.float32)
+    ref[:, 2] = (0.2 * ref[:, 0] + 0.02 * rng.normal(size=n_ref)).astype(np.float32)
+    read = (ref[rng.integers(0, n_ref, n_qry)] + np.float32([0.03, -0.02, 0.01]) +
+            0.002 * rng.normal(size=(n_qry, 3))).astype(np.float32)
+    for sched in (1, 2):
+        reg.setMatchSchedule(sched); reg.setKnnSchedule(sched)
+        T, o = run_both(reg, orc, ref, read, 0.8, knn_normals=10, max_iterations=6)
+        assert_full_parity(reg, T, o)
+    reg.setMatchSchedule(0); reg.setKnnSchedule(0)
+    reg.setConfig(knn_normals=20, max_iterations=20)          # the handle is shared by the module: back to the defaults
 
 
 def test_icp_parity_c3_hdl64_full_size(reg, orc, pair_cache):
     pair = pair_cache(3, 0)
     T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.7)
     assert_full_parity(reg, T, o)
+    reg.setMatchSchedule(2); reg.setKnnSchedule(2)           # the schedules the batched path picks
+    T, o2 = run_both(reg, orc, pair["ref"], pair["read"], 0.7)
+    assert_full_parity(reg, T, o2)
+    reg.setMatchSchedule(0); reg.setKnnSchedule(0)
     # second trial, auto-tuned ratio from the GPU overlap
     pair = pair_cache(3, 1, 65536)
     ov = ab.B200Overlap()

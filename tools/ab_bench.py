@@ -15,14 +15,15 @@ from aicp_mapping_b200 import capi
 v = sys.argv[1]
 if v != "base":
     capi.LIB_PATH = capi.LIB_PATH.replace("libaicp_b200.so", "libaicp_b200_%%s.so" %% v)
-sys.argv = ["bench.py", "--steps", "5", "--warmup", "3", "--streams", sys.argv[2], "--no-cpu", "--pairs", "32"]
+sys.argv = ["bench.py", "--steps", "5", "--warmup", "3", "--streams", sys.argv[2], "--no-cpu", "--pairs", "32"] + sys.argv[3:]
 import runpy
 runpy.run_path(%r, run_name="__main__")
 ''' % (ROOT, os.path.join(ROOT, "bench.py"))
 
-for v in sys.argv[1:]:
+extra = [a for a in sys.argv[1:] if a.startswith("--")]
+for v in [a for a in sys.argv[1:] if not a.startswith("--")]:
     for S in ("1", "8"):
-        r = subprocess.run([sys.executable, "-c", CHILD, v, S], capture_output=True, text=True)
+        r = subprocess.run([sys.executable, "-c", CHILD, v, S] + extra, capture_output=True, text=True)
         try:
             d = json.loads(r.stdout.strip().splitlines()[-1])
             st = d["stage_ms_per_registration"]
