@@ -37,4 +37,7 @@ def orc():
 
 
 def rot_angle(R):
-    return float(np.arccos(np.clip((np.trace(np.asarray(R, dtype=np.float64)) - 1.0) / 2.0, -1.0, 1.0)))
+    """Rotation angle of a (nearly) orthonormal 3x3, well conditioned near zero: atan2(|skew part|, (trace - 1) / 2)."""
+    R = np.asarray(R, dtype=np.float64)
+    v = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.arctan2(np.linalg.norm(v), (np.trace(R) - 1.0) / 2.0))
