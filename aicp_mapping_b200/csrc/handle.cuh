@@ -33,7 +33,8 @@ struct SpatialIndex {
   DevBuf<float4> rec;            // 4 float4 per internal node of the radix tree (see search.cuh)
   DevBuf<int4> node_meta;        // (first, split, end, -) per internal node, build-time scratch
   DevBuf<unsigned int> keys, keys_alt, vals, vals_alt;
-  DevBuf<int> flags;             // bottom-up refit arrival counters, parent links
+  DevBuf<int> flags;             // parent links (internal nodes | points)
+  DevBuf<float4> chunkbox;       // boxes of every 32 / 1024 / 32768 consecutive sorted points (lo, hi pairs)
   DevBuf<int> owner;             // per point: lowest node with > 8 (first n) resp. > 32 (next n) points above it
   DevBuf<float4> cellbox;        // per internal node: shrunk float box of the node's Morton cell (lo, hi), see search.cuh
   DevBuf<unsigned char> sort_tmp;
@@ -42,7 +43,7 @@ struct SpatialIndex {
   IndexView view() const { return IndexView{pts.p, rec.p, owner.p, owner.p + n, cellbox.p, n}; }
   void release() {
     pts.release(); rec.release(); node_meta.release(); keys.release(); keys_alt.release(); vals.release(); vals_alt.release();
-    flags.release(); owner.release(); cellbox.release(); sort_tmp.release();
+    flags.release(); chunkbox.release(); owner.release(); cellbox.release(); sort_tmp.release();
     if (meta) cudaFree(meta);
     meta = nullptr;
   }
