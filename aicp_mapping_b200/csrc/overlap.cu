@@ -17,6 +17,7 @@
 namespace aicp {
 
 #define OCT_MAX_VAL 32768
+#define RAY_BATCH 4
 
 struct KeyBounds { int lo[3]; int hi[3]; };
 
@@ -110,20 +111,41 @@ __global__ void __launch_bounds__(128) k_ray_mark(const float4* __restrict__ pts
       tDelta[a] = res / fabs((double)dir[a]);
     } else { tMax[a] = DBL_MAX; tDelta[a] = DBL_MAX; }
   }
-  for (int guard = 0; guard < 400000; ++guard) {
-    int dim;
-    if (tMax[0] < tMax[1]) dim = (tMax[0] < tMax[2]) ? 0 : 2;
-    else dim = (tMax[1] < tMax[2]) ? 1 : 2;
-    // static indexing keeps tMax / cur in registers
-    if (dim == 0) { cur[0] += step[0]; tMax[0] += tDelta[0]; }
-    else if (dim == 1) { cur[1] += step[1]; tMax[1] += tDelta[1]; }
-    else { cur[2] += step[2]; tMax[2] += tDelta[2]; }
-    if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
-    double dmin = tMax[0] < tMax[1] ? tMax[0] : tMax[1];
-    if (tMax[2] < dmin) dmin = tMax[2];
-    if (dmin > (double)length) break;
-    if ((unsigned)cur[0] >= 65536u || (unsigned)cur[1] >= 65536u || (unsigned)cur[2] >= 65536u) break;
-    mark(bits, g, cur[0], cur[1], cur[2], oob);
+  // The DDA itself is a short dependent chain of register arithmetic, but every visited voxel costs an L2 round trip for
+  // the test-before-atomicOr.  Steps are therefore taken in batches of RAY_BATCH: advance (sequentially, exactly as
+  // octomap does), issue all the bitmap loads of the batch, then test them -- RAY_BATCH loads in flight per thread
+  // instead of one.
+  bool done = false;
+  for (int guard = 0; guard < 400000 && !done; guard += RAY_BATCH) {
+    unsigned int* wp[RAY_BATCH];
+    unsigned int wm[RAY_BATCH], wv[RAY_BATCH];
+#pragma unroll
+    for (int b = 0; b < RAY_BATCH; ++b) {
+      wp[b] = nullptr;
+      if (done) continue;
+      int dim;
+      if (tMax[0] < tMax[1]) dim = (tMax[0] < tMax[2]) ? 0 : 2;
+      else dim = (tMax[1] < tMax[2]) ? 1 : 2;
+      // static indexing keeps tMax / cur in registers
+      if (dim == 0) { cur[0] += step[0]; tMax[0] += tDelta[0]; }
+      else if (dim == 1) { cur[1] += step[1]; tMax[1] += tDelta[1]; }
+      else { cur[2] += step[2]; tMax[2] += tDelta[2]; }
+      if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) { done = true; continue; }
+      double dmin = tMax[0] < tMax[1] ? tMax[0] : tMax[1];
+      if (tMax[2] < dmin) dmin = tMax[2];
+      if (dmin > (double)length) { done = true; continue; }
+      if ((unsigned)cur[0] >= 65536u || (unsigned)cur[1] >= 65536u || (unsigned)cur[2] >= 65536u) { done = true; continue; }
+      if ((unsigned)(cur[0] - g.lo[0]) >= (unsigned)g.dim[0] || (unsigned)(cur[1] - g.lo[1]) >= (unsigned)g.dim[1] ||
+          (unsigned)(cur[2] - g.lo[2]) >= (unsigned)g.dim[2]) { atomicAdd(oob, 1ull); continue; }
+      unsigned long long idx = ((unsigned long long)(cur[0] - g.lo[0]) * (unsigned)g.dim[1] + (unsigned)(cur[1] - g.lo[1])) * (unsigned)g.dim[2] +
+                               (unsigned)(cur[2] - g.lo[2]);
+      wp[b] = bits + (idx >> 5);
+      wm[b] = 1u << (idx & 31);
+    }
+#pragma unroll
+    for (int b = 0; b < RAY_BATCH; ++b) wv[b] = wp[b] ? __ldcg(wp[b]) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = 0; b < RAY_BATCH; ++b) if (wp[b] && !(wv[b] & wm[b])) atomicOr(wp[b], wm[b]);
   }
 }
 

@@ -52,6 +52,16 @@ def load_pair(trial, n_points=N_POINTS):
     return p
 
 
+def profiled_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            d = json.load(f)["k_match_tile"]
+            return float(d["dram_bytes_per_launch"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -81,9 +91,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (perf_counter times; the sampler is started well before the timed
+        region because nvidia-smi needs a few hundred ms to deliver its first line)."""
         if not self.proc:
             return None
         self.proc.terminate()
@@ -92,7 +104,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smmax, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -174,6 +188,7 @@ def run_b200(args, rank, world, local_rank):
     reg = ab.B200Registration(device=local_rank)
     ovl = ab.B200Overlap(device=local_rank)
     reg.setMatchSchedule(args.match_schedule)
+    reg.setKnnSchedule(args.knn_schedule)
     reg.setProfiling(0 if args.no_profile else 1)     # CUDA events around k_match only inside the timed region
     dev, host, ratios = [], [], []
     for p in pairs:
@@ -211,20 +226,25 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         one_step(False)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     t_wall0 = time.perf_counter()
     dev_ms, agg = 0.0, None
+    if args.profile_run:
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: capture the timed step only
     for _ in range(args.steps):
         ms, a = one_step(False)
         dev_ms += ms
         agg = a if agg is None else {k: agg[k] + a[k] for k in agg}
     barrier()
-    wall_s = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    if args.profile_run:
+        torch.cuda.profiler.stop()
+    t_wall1 = time.perf_counter()
+    wall_s = t_wall1 - t_wall0
+    clocks = sampler.stop(t_wall0, t_wall1)
 
     # e2e: pinned host buffers through the same plugin call, wall clock around the synchronous call (copies inside)
     for _ in range(0 if args.profile_run else min(args.warmup, 2)):
@@ -284,8 +304,10 @@ def run_b200(args, rank, world, local_rank):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(P, "flushed before every step (256 MiB write)"), streams_per_gpu=S),
-                "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "roofline": {"bound": "hbm", "kernel": "k_match_tile (k_match for the cold first iteration)" if S > 1 else "k_match",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": profiled_traffic()[0], "traffic_source": profiled_traffic()[1],
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_match, "avg_launch_ms": match_ms,
                              "launches_timed": n_launch_match,
                              "note": "timed live in the step with %d registrations in flight per GPU; k_match alone "
@@ -328,6 +350,7 @@ def main():
     ap.add_argument("--streams", type=int, default=8, help="concurrent registrations per GPU (CUDA streams)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--match-schedule", type=int, default=0, help="0 auto, 1 per-thread search, 2 tile search (experiments)")
+    ap.add_argument("--knn-schedule", type=int, default=0, help="0 auto, 1 warp-per-query k-NN, 2 tile k-NN (experiments)")
     ap.add_argument("--no-profile", action="store_true", help="no per-stage CUDA events inside the registrations")
     ap.add_argument("--profile-run", action="store_true", help="device-resident leg only (the command profiled under ncu)")
     args = ap.parse_args()
