@@ -182,8 +182,9 @@ def run_b200(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     P = args.pairs
-    # distinct pairs per rank (weak scaling: every rank registers P pairs per step)
-    trials = [(rank * 2 + i) % 16 for i in range(min(P, 2))]
+    # weak scaling: every rank registers the SAME P pairs per step (the two seeded C3 pairs, 9 and 6 ICP iterations), so
+    # that per-GPU work is identical for every N; different pairs per rank would make the slowest pair set the job time
+    trials = [i % 16 for i in range(min(P, 2))]
     pairs = [load_pair(t) for t in trials]
     reg = ab.B200Registration(device=local_rank)
     ovl = ab.B200Overlap(device=local_rank)
