@@ -362,3 +362,53 @@ def test_overlap_parity(orc, pair_cache):
     ov.computeOverlap(a, a + np.float32(500.0), [0, 0, 0.6], [500, 500, 500.6])
     assert ov.getOverlap() == 0.0 and ov.counts[0] == 0
     ov.close()
+
+
+# ---- randomised sweep -------------------------------------------------------------------------------------------------
+def _random_scene(rng, n, kind):
+    if kind == "plane":          # noisy tilted plane: well-conditioned normals
+        p = rng.uniform(-2, 2, (n, 3)); p[:, 2] = 0.3 * p[:, 0] - 0.1 * p[:, 1] + 0.01 * rng.normal(size=n)
+    elif kind == "corner":       # three orthogonal faces: constrains all six degrees of freedom
+        f = rng.integers(0, 3, n); p = rng.uniform(0, 2, (n, 3)); p[np.arange(n), f] = 0.005 * rng.normal(size=n)
+    elif kind == "lattice":      # quantised coordinates: many exactly equal distances (tie rule)
+        f = rng.integers(0, 3, n); p = np.round(rng.uniform(0, 2, (n, 3)) * 16) / 16; p[np.arange(n), f] = 0.0
+    elif kind == "clusters":     # dense blobs far apart: deep, unbalanced radix tree and large empty cells
+        c = rng.uniform(-20, 20, (8, 3)); p = c[rng.integers(0, 8, n)] + 0.05 * rng.normal(size=(n, 3))
+        p[:, 2] *= 0.05
+    else:                        # duplicates: identical points inside every neighbourhood
+        f = rng.integers(0, 3, n); p = rng.uniform(0, 2, (n, 3)); p[np.arange(n), f] = 0.004 * rng.normal(size=n)
+        p[n // 2:] = p[:n - n // 2]
+    return p.astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_icp_randomised_parity_sweep(reg, orc, seed):
+    """Random scene type, sizes, knn, ratio, perturbation and kernel schedule; the whole trajectory must equal the oracle's.
+    Error outcomes (ConvergenceError-type statuses) must match too."""
+    rng = np.random.default_rng(9000 + seed)
+    kind = ["plane", "corner", "lattice", "clusters", "duplicates"][seed % 5]
+    n_ref, n_read = int(rng.integers(40, 6000)), int(rng.integers(1, 4000))
+    knn = int(rng.integers(3, 33))
+    if knn >= n_ref:
+        knn = n_ref - 1
+    ratio = float(np.float32(rng.choice([0.25, 0.4, 0.55, 0.7, 0.9, 1.0])))
+    ref = _random_scene(rng, n_ref, kind)
+    P = synth.rigid(*rng.uniform(-0.05, 0.05, 3), *np.deg2rad(rng.uniform(-1.5, 1.5, 3)))
+    read = synth.apply_T(P, ref[rng.integers(0, n_ref, n_read)].astype(np.float64) + 0.003 * rng.normal(size=(n_read, 3)))
+    sched = 1 + seed % 2
+    reg.setMatchSchedule(sched); reg.setKnnSchedule(sched)
+    reg.setConfig(ratio=ratio, knn_normals=knn, max_iterations=12)
+    reg.enableMatchTrace(True)
+    cfg = orc.default_config(ratio=ratio, threads=NCPU, knn_normals=knn, max_iterations=12)
+    o = orc.icp(ref, read, cfg, want_trace_idx=True, want_normals=True)
+    try:
+        T = reg.registerClouds(ref, read)
+        code = "OK"
+    except capi.AicpError as e:
+        T, code = None, e.code_name
+    finally:
+        reg.setMatchSchedule(0); reg.setKnnSchedule(0)
+        reg.setConfig(knn_normals=20, max_iterations=20)
+    assert code == o.error, (kind, n_ref, n_read, knn, ratio)
+    if T is not None:
+        assert_full_parity(reg, T, o)
