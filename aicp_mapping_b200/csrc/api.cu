@@ -132,7 +132,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->match_pos.release(); h->d2.release(); h->hist.release(); h->cand.release(); h->acc_slots.release(); h->trace_idx.release();
   if (h->progress_host) cudaFreeHost((void*)h->progress_host);
   h->tmp_ix.release(); h->tmp_a.release(); h->tmp_b.release(); h->tmp_i.release(); h->tmp_f.release();
-  h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release();
+  h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release(); h->crop_status.release(); h->crop_out.release();
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -356,6 +356,34 @@ int aicp_b200_overlap(aicp_b200_handle* hh, const float* ref_xyzw, int64_t n_ref
   if (rc) return rc;
   if ((rc = upload_points(h, h->tmp_b, read_xyzw, n_read > 0 ? n_read : 1, &read))) return rc;
   return run_overlap(h, ref, n_ref, ref_origin, read, n_read, read_origin, resolution, overlap_pct, counts);
+}
+
+int aicp_b200_crop_box(aicp_b200_handle* hh, const float* xyzw, int64_t n, float box_min, float box_max, const float rotation_rpy[3],
+                       const float translation[3], float* out_xyzw, int64_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!xyzw || !rotation_rpy || !translation || !n_out || n < 0 || n > (1ll << 31))
+    return fail(h, AICP_B200_ERR_BAD_ARG, "crop_box: bad arguments");
+  *n_out = 0;
+  if (n == 0) return AICP_B200_OK;
+  const float4* pts;
+  int rc = upload_points(h, h->tmp_a, xyzw, n, &pts);
+  if (rc) return rc;
+  // the result stays on the device (h->crop_out) when out_xyzw is NULL: aicp_b200_get_cropped() returns its address
+  const bool out_is_dev = out_xyzw && is_device_ptr(out_xyzw);
+  float4* dst = out_is_dev ? reinterpret_cast<float4*>(out_xyzw) : nullptr;
+  if (!dst) { CUDA_TRY(h->crop_out.reserve((size_t)n)); dst = h->crop_out.p; }
+  if ((rc = run_crop_box(h, pts, n, box_min, box_max, rotation_rpy, translation, dst, n_out))) return rc;
+  h->crop_n = *n_out;
+  if (out_xyzw && !out_is_dev && *n_out > 0) return download(h, out_xyzw, dst, sizeof(float4) * (size_t)*n_out);
+  return AICP_B200_OK;
+}
+
+const float* aicp_b200_get_cropped(aicp_b200_handle* hh, int64_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return nullptr;
+  if (n_out) *n_out = h->crop_n;
+  return reinterpret_cast<const float*>(h->crop_out.p);
 }
 
 float aicp_b200_autotune_ratio(float overlap_pct) {

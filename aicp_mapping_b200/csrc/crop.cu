@@ -1,0 +1,144 @@
+// crop.cu -- getPointsInOrientedBox on the GPU: the oriented crop of the (prior or built) map around the robot.
+//
+// replaces getPointsInOrientedBox (aicp_core/src/utils/filteringUtils.cpp:621-637), i.e. pcl::CropBox with
+// min = (m,m,m), max = (M,M,M), rotation = origin.block<3,3>(0,0).eulerAngles(0,1,2), translation = origin.col(3), which
+// App runs on the whole map before every registration against it (app.cpp:41-69; +-15 m, aicp.launch:56).
+// [UPSTREAM, recalled] CropBox keeps a point when  min <= R^-1 (p - t) <= max  with R = pcl::getTransformation(rpy).
+//
+// One pass over the map, HBM-bound: a 10 485 760-point map is 168 MB read + 16 B per kept point written.
+//   k_crop_box  tiles of 2048 points (256 threads x 8 rows, coalesced float4 loads kept in registers); per-row warp
+//               ballots rank the kept points, a 64-entry shared scan orders (row, warp) pairs so that the output keeps the
+//               INPUT ORDER (CropBox semantics); the tile's base offset comes from a single-pass chained scan with
+//               decoupled look-back (tiles take their number from an atomic ticket, so a tile only ever waits for tiles
+//               that are already running).
+// Arithmetic: local_k = (m_k0*dx + m_k1*dy) + m_k2*dz in float32 without FMA, inverse rotation = transpose; identical to
+// oracle/aicp_oracle_filters.c, so the kept set is bit-for-bit the oracle's.
+#include <math.h>
+
+#include "handle.cuh"
+
+namespace aicp {
+
+#define CROP_ROWS 8
+#define CROP_TILE (256 * CROP_ROWS)
+// tile status word: bits 63..62 = 0 not ready, 1 aggregate of this tile only, 2 inclusive prefix; bits 61..0 = count
+#define CROP_AGG (1ull << 62)
+#define CROP_PREFIX (2ull << 62)
+#define CROP_MASK ((1ull << 62) - 1ull)
+
+struct CropBox9 {
+  float m[9];        // inverse rotation (row-major): local = m * (p - t)
+  float t[3];
+  float bmin, bmax;
+};
+
+__global__ void k_crop_reset(unsigned long long* status, int n_tiles, unsigned int* ticket, unsigned long long* total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tiles) status[i] = 0ull;
+  if (i == 0) { *ticket = 0u; *total = 0ull; }
+}
+
+__global__ void __launch_bounds__(256) k_crop_box(const float4* __restrict__ pts, long long n, CropBox9 box, float4* __restrict__ out,
+                                                  unsigned long long* status, unsigned int* ticket, unsigned long long* total) {
+  __shared__ unsigned int s_tile;
+  __shared__ int s_cnt[CROP_ROWS * 8 + 1];
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const long long base = (long long)tile * CROP_TILE;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float4 p[CROP_ROWS];
+  unsigned int keep = 0;              // bit r: row r of this thread is inside the box
+  int rank[CROP_ROWS];
+#pragma unroll
+  for (int r = 0; r < CROP_ROWS; ++r) {
+    const long long i = base + r * 256 + threadIdx.x;
+    bool in = false;
+    if (i < n) {
+      p[r] = __ldg(&pts[i]);
+      if (isfinite(p[r].x) && isfinite(p[r].y) && isfinite(p[r].z)) {
+        const float dx = __fsub_rn(p[r].x, box.t[0]), dy = __fsub_rn(p[r].y, box.t[1]), dz = __fsub_rn(p[r].z, box.t[2]);
+        const float lx = __fadd_rn(__fadd_rn(__fmul_rn(box.m[0], dx), __fmul_rn(box.m[1], dy)), __fmul_rn(box.m[2], dz));
+        const float ly = __fadd_rn(__fadd_rn(__fmul_rn(box.m[3], dx), __fmul_rn(box.m[4], dy)), __fmul_rn(box.m[5], dz));
+        const float lz = __fadd_rn(__fadd_rn(__fmul_rn(box.m[6], dx), __fmul_rn(box.m[7], dy)), __fmul_rn(box.m[8], dz));
+        in = !(lx < box.bmin || ly < box.bmin || lz < box.bmin || lx > box.bmax || ly > box.bmax || lz > box.bmax);
+      }
+    }
+    const unsigned int bal = __ballot_sync(0xFFFFFFFFu, in);
+    rank[r] = __popc(bal & ((1u << lane) - 1u));
+    if (in) keep |= 1u << r;
+    if (lane == 0) s_cnt[r * 8 + w] = __popc(bal);
+  }
+  __syncthreads();
+  // exclusive scan of the 64 (row, warp) counts, row-major = input order; warp 0, two entries per lane
+  if (w == 0) {
+    const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+    int incl = a + b;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    const int excl = incl - (a + b);
+    s_cnt[2 * lane] = excl; s_cnt[2 * lane + 1] = excl + a;
+    const int tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (lane == 0) {
+      s_cnt[CROP_ROWS * 8] = tile_total;
+      // chained scan with decoupled look-back: publish this tile's aggregate, then walk back over the predecessors
+      unsigned long long prefix = 0;
+      if (tile == 0) {
+        atomicExch(&status[0], CROP_PREFIX | (unsigned long long)tile_total);
+      } else {
+        atomicExch(&status[tile], CROP_AGG | (unsigned long long)tile_total);
+        long long j = (long long)tile - 1;
+        while (true) {
+          unsigned long long s = *(volatile unsigned long long*)&status[j];
+          if ((s >> 62) == 0ull) continue;                  // predecessor not published yet (it is running: ticket order)
+          prefix += s & CROP_MASK;
+          if ((s >> 62) == 2ull) break;
+          --j;
+        }
+        atomicExch(&status[tile], CROP_PREFIX | (prefix + (unsigned long long)tile_total));
+      }
+      s_base = prefix;
+      if (base + CROP_TILE >= n) *total = prefix + (unsigned long long)tile_total;     // the last tile knows the answer
+    }
+  }
+  __syncthreads();
+  const unsigned long long obase = s_base;
+#pragma unroll
+  for (int r = 0; r < CROP_ROWS; ++r)
+    if (keep & (1u << r)) out[obase + (unsigned long long)(s_cnt[r * 8 + w] + rank[r])] = p[r];
+}
+
+int run_crop_box(Handle* h, const float4* pts, int64_t n, float bmin, float bmax, const float* rpy, const float* translation,
+                 float4* out_dev, int64_t* n_out) {
+  cudaStream_t s = h->stream;
+  *n_out = 0;
+  if (n == 0) return AICP_B200_OK;
+  // pcl::getTransformation(0,0,0,roll,pitch,yaw) in float (host libm, the same calls as the oracle), then the transpose
+  const float A = cosf(rpy[2]), B = sinf(rpy[2]), C = cosf(rpy[1]), D = sinf(rpy[1]), E = cosf(rpy[0]), F = sinf(rpy[0]);
+  const float DE = D * E, DF = D * F;
+  const float R[9] = {A * C, A * DF - B * E, B * F + A * DE, B * C, A * E + B * DF, B * DE - A * F, -D, C * F, C * E};
+  CropBox9 box;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) box.m[3 * r + c] = R[3 * c + r];
+  for (int d = 0; d < 3; ++d) box.t[d] = translation[d];
+  box.bmin = bmin; box.bmax = bmax;
+  const long long n_tiles = (n + CROP_TILE - 1) / CROP_TILE;
+  CUDA_TRY(h->crop_status.reserve((size_t)n_tiles + 2));
+  unsigned long long* status = h->crop_status.p;
+  unsigned long long* total = status + n_tiles;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(status + n_tiles + 1);
+  k_crop_reset<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(status, (int)n_tiles, ticket, total);
+  k_crop_box<<<(unsigned)n_tiles, 256, 0, s>>>(pts, (long long)n, box, out_dev, status, ticket, total);
+  CUDA_TRY(cudaGetLastError());
+  unsigned long long host_total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&host_total, total, sizeof(host_total), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  h->launches += 2;
+  *n_out = (int64_t)host_total;
+  return AICP_B200_OK;
+}
+
+}  // namespace aicp

@@ -105,6 +105,9 @@ struct Handle {
   DevBuf<float> tmp_f;
   DevBuf<unsigned int> ovl_bits_a, ovl_bits_b;
   DevBuf<unsigned long long> ovl_counts;
+  DevBuf<unsigned long long> crop_status;   // chained-scan tile status of the crop box + total + ticket
+  int64_t crop_n = 0;
+  DevBuf<float4> crop_out;                  // cropped cloud when the caller asks for a device-resident result
 
   Comm* comm = nullptr;
 
@@ -128,6 +131,9 @@ int run_trim_stage(Handle* h, const float* d2_dev, int64_t n, float ratio, float
 // ---- overlap.cu
 int run_overlap(Handle* h, const float4* ref, int64_t n_ref, const double* ref_origin, const float4* read, int64_t n_read,
                 const double* read_origin, double resolution, float* overlap_pct, int64_t* counts);
+// ---- crop.cu
+int run_crop_box(Handle* h, const float4* pts, int64_t n, float bmin, float bmax, const float* rpy, const float* translation,
+                 float4* out_dev, int64_t* n_out);
 // ---- comm.cu (sharded registration; NCCL is loaded at run time, the library has no link-time dependency on it)
 int comm_allreduce_u32(Handle* h, unsigned int* buf, size_t count);
 int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count);

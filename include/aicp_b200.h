@@ -167,6 +167,20 @@ int aicp_b200_overlap(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref,
                       const float* read_xyzw, int64_t n_read, const double read_origin[3], double resolution,
                       float* overlap_pct, int64_t counts[3]);
 
+/* ---- map handling ---------------------------------------------------------------------------
+ * replaces: getPointsInOrientedBox(cloud, min, max, origin)   aicp_core/src/utils/filteringUtils.cpp:621-637
+ *           = pcl::CropBox{min (m,m,m), max (M,M,M), rotation origin.block<3,3>(0,0).eulerAngles(0,1,2), translation origin.col(3)},
+ *           which App runs on the whole prior / built map before every registration against it (app.cpp:41-69).
+ * rotation_rpy: the three Euler angles exactly as the reference passes them to CropBox::setRotation (the adapter computes them
+ * with Eigen like the reference does); translation: origin.col(3).  A point is kept when min <= R(rpy)^-1 (p - t) <= max on
+ * every axis; the output keeps the input order; non-finite points are dropped.
+ * out_xyzw: host or device buffer of capacity n records, or NULL to keep the result on the device only -- then
+ * aicp_b200_get_cropped() returns its device address, valid until the next crop on this handle, which can be passed straight
+ * to aicp_b200_register / aicp_b200_set_reference as the reference cloud. */
+int aicp_b200_crop_box(aicp_b200_handle* h, const float* xyzw, int64_t n, float box_min, float box_max,
+                       const float rotation_rpy[3], const float translation[3], float* out_xyzw, int64_t* n_out);
+const float* aicp_b200_get_cropped(aicp_b200_handle* h, int64_t* n_out);
+
 /* ---- auto-tune glue --------------------------------------------------------------------------------------------
  * replaces (for callers that do not go through a file): App::computeRegistration's clamp, app.cpp:198-202, followed by
  * the 6-significant-digit text round trip of replaceRatioConfigFile, fileIO.cpp:194-198.  Pure host code. */

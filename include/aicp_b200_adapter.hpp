@@ -213,6 +213,38 @@ class B200Overlap : public AbstractOverlapper {
   int64_t counts_[3];
 };
 
+// ---- map handling: stands where getPointsInOrientedBox stands (aicp_core/src/utils/filteringUtils.cpp:621-637) -----------
+// App crops the prior / built map around the prior pose before every registration against it (app.cpp:41-69).  Same
+// signature as the reference's free function plus the handle; `cloud` is replaced by the points inside the box, in input
+// order.  The Euler angles are taken with Eigen exactly as the reference does, so this overload needs the real
+// Eigen/Geometry (it is compiled only when that header has been included); rpy-taking overload below has no such need.
+inline bool getPointsInOrientedBoxB200(aicp_b200_handle* h, pcl::PointCloud<pcl::PointXYZ>& cloud, float min, float max,
+                                       const float rpy[3], const float position[3]) {
+  const int64_t n = (int64_t)cloud.points.size();
+  std::vector<float> out(4 * (size_t)(n > 0 ? n : 1));
+  int64_t kept = 0;
+  const int rc = aicp_b200_crop_box(h, reinterpret_cast<const float*>(cloud.points.data()), n, min, max, rpy, position, out.data(), &kept);
+  if (rc != AICP_B200_OK) {
+    std::cerr << "[B200] getPointsInOrientedBox failed (" << rc << "): " << aicp_b200_last_error(h) << std::endl;
+    return false;
+  }
+  cloud.points.resize((size_t)kept);
+  if (kept > 0) std::memcpy(cloud.points.data(), out.data(), sizeof(float) * 4 * (size_t)kept);
+  cloud.width = (uint32_t)kept;
+  cloud.height = 1;
+  return true;
+}
+
+#ifdef EIGEN_GEOMETRY_MODULE_H
+inline bool getPointsInOrientedBoxB200(aicp_b200_handle* h, pcl::PointCloud<pcl::PointXYZ>::Ptr& cloud, float min, float max,
+                                       Eigen::Matrix4f& origin) {
+  Eigen::Vector3f orientation = origin.block<3, 3>(0, 0).eulerAngles(0, 1, 2);      // (rx,ry,rz), filteringUtils.cpp:629
+  const float rpy[3] = {orientation(0), orientation(1), orientation(2)};
+  const float position[3] = {origin(0, 3), origin(1, 3), origin(2, 3)};
+  return getPointsInOrientedBoxB200(h, *cloud, min, max, rpy, position);
+}
+#endif
+
 }  // namespace aicp
 
 #endif

@@ -125,6 +125,11 @@ int orc_overlap(const float* ref, int64_t n_ref, const double* ref_origin, const
 /* sorted unique 48-bit keys of one cloud (x<<32|y<<16|z); returns count; keys may be NULL to only count */
 int64_t orc_ray_keys(const float* pts, int64_t n, const double* origin, double resolution, uint64_t* keys, int64_t cap);
 
+/* ---- map handling: getPointsInOrientedBox = pcl::CropBox (filteringUtils.cpp:621-637), see aicp_oracle_filters.c ---- */
+void orc_rpy_to_matrix(const float* rpy, float* R_rowmajor9);
+/* returns the number of points kept; out (nullable) receives them in input order, capacity n x 4 floats */
+int64_t orc_crop_box(const float* xyzw, int64_t n, float bmin, float bmax, const float* rpy, const float* translation, float* out);
+
 /* ---- text glue KATs ---- */
 /* app.cpp:198-202 clamp + fileIO.cpp:194-198 "%g"-style 6-digit print + float re-parse */
 float orc_autotune_ratio(float overlap_pct, char* text_out /* >=32 bytes, nullable */);

@@ -36,7 +36,7 @@ class IcpResult(C.Structure):
 
 def build(force=False):
     """Compile the oracle with oracle/Makefile (gcc)."""
-    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle_filters.c", "aicp_oracle.h", "Makefile")]
     if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return _LIB_PATH
     subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
@@ -54,6 +54,7 @@ def lib():
         _lib.orc_autotune_ratio.restype = C.c_float
         _lib.orc_autotune_ratio.argtypes = [C.c_float, C.c_char_p]
         _lib.orc_ray_keys.restype = C.c_int64
+        _lib.orc_crop_box.restype = C.c_int64
     return _lib
 
 
@@ -236,3 +237,13 @@ def autotune_ratio(overlap_pct):
     buf = C.create_string_buffer(32)
     r = lib().orc_autotune_ratio(C.c_float(overlap_pct), buf)
     return np.float32(r), buf.value.decode()
+
+
+def crop_box(cloud, bmin, bmax, rpy, translation):
+    """getPointsInOrientedBox / pcl::CropBox (filteringUtils.cpp:621-637): points inside the oriented box, input order."""
+    pts = to_xyzw(cloud)
+    out = np.zeros_like(pts)
+    r = np.ascontiguousarray(rpy, dtype=np.float32)
+    t = np.ascontiguousarray(translation, dtype=np.float32)
+    m = lib().orc_crop_box(_ptr(pts), C.c_int64(pts.shape[0]), C.c_float(bmin), C.c_float(bmax), _ptr(r), _ptr(t), _ptr(out))
+    return out[:m].copy()
