@@ -132,7 +132,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->match_pos.release(); h->d2.release(); h->hist.release(); h->cand.release(); h->acc_slots.release(); h->trace_idx.release();
   if (h->progress_host) cudaFreeHost((void*)h->progress_host);
   h->tmp_ix.release(); h->tmp_a.release(); h->tmp_b.release(); h->tmp_i.release(); h->tmp_f.release();
-  h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release(); h->crop_status.release(); h->crop_out.release();
+  h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release(); h->crop_status.release(); h->crop_out.release(); h->map.release();
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -377,6 +377,57 @@ int aicp_b200_crop_box(aicp_b200_handle* hh, const float* xyzw, int64_t n, float
   h->crop_n = *n_out;
   if (out_xyzw && !out_is_dev && *n_out > 0) return download(h, out_xyzw, dst, sizeof(float4) * (size_t)*n_out);
   return AICP_B200_OK;
+}
+
+int aicp_b200_map_append(aicp_b200_handle* hh, const float* xyzw, int64_t n, int replace) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n < 0 || (n > 0 && !xyzw) || n > (1ll << 31)) return fail(h, AICP_B200_ERR_BAD_ARG, "map_append: bad arguments");
+  if (replace) h->map_n = 0;
+  if (n == 0) return AICP_B200_OK;
+  const int64_t total = h->map_n + n;
+  if (total > (1ll << 31)) return fail(h, AICP_B200_ERR_BAD_ARG, "map_append: map would exceed 2^31 points");
+  if ((size_t)total > h->map.cap) {
+    // grow geometrically and carry the existing points over (DevBuf::reserve alone would drop them)
+    DevBuf<float4> bigger;
+    CUDA_TRY(bigger.reserve((size_t)total + (size_t)total / 2));
+    if (h->map_n > 0) CUDA_TRY(cudaMemcpyAsync(bigger.p, h->map.p, sizeof(float4) * (size_t)h->map_n, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->map.release();
+    h->map = bigger;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->map.p + h->map_n, xyzw, sizeof(float4) * (size_t)n,
+                           is_device_ptr(xyzw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->map_n = total;
+  return AICP_B200_OK;
+}
+
+int64_t aicp_b200_map_size(const aicp_b200_handle* hh) {
+  const Handle* h = reinterpret_cast<const Handle*>(hh);
+  return h ? h->map_n : 0;
+}
+
+int aicp_b200_map_crop(aicp_b200_handle* hh, float box_min, float box_max, const float rotation_rpy[3], const float translation[3],
+                       int64_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!rotation_rpy || !translation || !n_out) return fail(h, AICP_B200_ERR_BAD_ARG, "map_crop: bad arguments");
+  *n_out = 0; h->crop_n = 0;
+  if (h->map_n == 0) return AICP_B200_OK;
+  CUDA_TRY(h->crop_out.reserve((size_t)h->map_n));
+  int rc = run_crop_box(h, h->map.p, h->map_n, box_min, box_max, rotation_rpy, translation, h->crop_out.p, n_out);
+  if (rc) return rc;
+  h->crop_n = *n_out;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_download_cropped(aicp_b200_handle* hh, float* xyzw, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n != h->crop_n || (n > 0 && !xyzw)) return fail(h, AICP_B200_ERR_BAD_ARG, "download_cropped: the last crop holds %lld points", (long long)h->crop_n);
+  if (n == 0) return AICP_B200_OK;
+  return download(h, xyzw, h->crop_out.p, sizeof(float4) * (size_t)n);
 }
 
 const float* aicp_b200_get_cropped(aicp_b200_handle* hh, int64_t* n_out) {

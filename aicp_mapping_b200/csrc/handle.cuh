@@ -107,6 +107,8 @@ struct Handle {
   DevBuf<unsigned long long> ovl_counts;
   DevBuf<unsigned long long> crop_status;   // chained-scan tile status of the crop box + total + ticket
   int64_t crop_n = 0;
+  DevBuf<float4> map;                       // persistent device-resident map (aicp_b200_map_*), original point order
+  int64_t map_n = 0;
   DevBuf<float4> crop_out;                  // cropped cloud when the caller asks for a device-resident result
 
   Comm* comm = nullptr;

@@ -68,6 +68,62 @@ class B200CropBox:
         return out[:n_out.value].copy()
 
 
+class B200Map(B200CropBox):
+    """The prior / built map of App (aligned_map_, prior_map_) kept on the GPU: upload once, append aligned clouds, crop
+    around the prior pose before every registration (app.cpp:41-69,469-493)."""
+
+    def _check(self, rc):
+        if rc:
+            raise capi.AicpError(rc, self._lib.aicp_b200_last_error(self._h).decode())
+
+    def updateCloud(self, cloud):
+        p, n, keep = capi.ptr_and_count(cloud)
+        self._check(self._lib.aicp_b200_map_append(self._h, p, n, 1))
+
+    def append(self, cloud):
+        p, n, keep = capi.ptr_and_count(cloud)
+        self._check(self._lib.aicp_b200_map_append(self._h, p, n, 0))
+
+    def size(self):
+        return int(self._lib.aicp_b200_map_size(self._h))
+
+    def cropAround(self, half_extent, origin):
+        """getPointsInOrientedBox(map copy, -half_extent, +half_extent, origin): returns a device cloud view of the crop
+        (valid until the next crop), to be passed to registerClouds / setReference."""
+        origin = np.asarray(origin, dtype=np.float32)
+        rpy = euler_angles_xyz(origin[:3, :3])
+        t = np.ascontiguousarray(origin[:3, 3], dtype=np.float32)
+        n_out = C.c_int64()
+        self._check(self._lib.aicp_b200_map_crop(self._h, C.c_float(-half_extent), C.c_float(half_extent),
+                                                 rpy.ctypes.data_as(C.POINTER(C.c_float)), t.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 C.byref(n_out)))
+        return DeviceCloudView(self._lib.aicp_b200_get_cropped(self._h, None), int(n_out.value))
+
+    def cropToHost(self):
+        """The last crop as an n x 4 float32 array."""
+        n = C.c_int64()
+        self._lib.aicp_b200_get_cropped(self._h, C.byref(n))
+        out = np.zeros((n.value, 4), dtype=np.float32)
+        self._check(self._lib.aicp_b200_download_cropped(self._h, C.c_void_p(out.ctypes.data), n.value))
+        return out
+
+
+class DeviceCloudView:
+    """A library-owned device buffer of n (x, y, z, pad) records, accepted wherever a device cloud is (capi.ptr_and_count)."""
+
+    def __init__(self, address, n):
+        self._a, self.shape, self.dtype = address, (n, 4), "torch.float32"
+
+    def data_ptr(self):
+        return self._a
+
+    def dim(self):
+        return 2
+
+    def is_contiguous(self):
+        return True
+
+
 def getPointsInOrientedBox(cloud, box_min, box_max, origin, cropper=None):
     """filteringUtils.cpp:621-637: crop `cloud` with the box [min, max]^3 placed at the 4x4 pose `origin`."""
     origin = np.asarray(origin, dtype=np.float32)

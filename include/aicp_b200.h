@@ -180,6 +180,17 @@ int aicp_b200_overlap(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref,
 int aicp_b200_crop_box(aicp_b200_handle* h, const float* xyzw, int64_t n, float box_min, float box_max,
                        const float rotation_rpy[3], const float translation[3], float* out_xyzw, int64_t* n_out);
 const float* aicp_b200_get_cropped(aicp_b200_handle* h, int64_t* n_out);
+int aicp_b200_download_cropped(aicp_b200_handle* h, float* xyzw, int64_t n);   /* copy of the last device-resident crop */
+
+/* A device-resident map, so that the (10 M-point, 168 MB) prior map is uploaded once instead of once per registration:
+ * replaces the host-side aligned_map_ / prior_map_ clouds of App (app.hpp:140-160).
+ *   map_append(replace = 1)  prior_map_->updateCloud(cloud)                              app.cpp:478-493
+ *   map_append(replace = 0)  *merged_map = *(prior_map_->getCloud()) + *output           app.cpp:476-480 (concatenation)
+ *   map_crop                 getPointsInOrientedBox(copy of the map, -c, +c, prior pose) app.cpp:41-69; result: get_cropped */
+int aicp_b200_map_append(aicp_b200_handle* h, const float* xyzw, int64_t n, int replace);
+int64_t aicp_b200_map_size(const aicp_b200_handle* h);
+int aicp_b200_map_crop(aicp_b200_handle* h, float box_min, float box_max, const float rotation_rpy[3], const float translation[3],
+                       int64_t* n_out);
 
 /* ---- auto-tune glue --------------------------------------------------------------------------------------------
  * replaces (for callers that do not go through a file): App::computeRegistration's clamp, app.cpp:198-202, followed by

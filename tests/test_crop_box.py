@@ -97,3 +97,25 @@ def test_crop_box_full_map_and_registration_against_the_crop(orc):
     T_host = reg.registerClouds(g, rd["read"])
     assert np.array_equal(T_dev.view(np.uint32), T_host.view(np.uint32))
     reg.close(); crop.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_map_append_and_crop(orc):
+    """App's map handling on the GPU: updateCloud, merge of aligned clouds (concatenation, app.cpp:476-480), crop around a
+    pose; equal to the oracle's crop of the concatenated host map, and growth keeps the points already stored."""
+    rng = np.random.default_rng(11)
+    parts = [rng.uniform(-30, 30, (n, 3)).astype(np.float32) for n in (50000, 1, 70001, 300000)]
+    m = ab.B200Map()
+    m.updateCloud(parts[0])
+    for p in parts[1:]:
+        m.append(p)
+    full = np.concatenate(parts, 0)
+    assert m.size() == len(full)
+    origin = synth.rigid(3.0, -4.0, 0.5, 0.01, 0.02, -1.1).astype(np.float32)
+    view = m.cropAround(15.0, origin)
+    got = m.cropToHost()
+    want = orc.crop_box(full, -15.0, 15.0, filtering.euler_angles_xyz(origin[:3, :3]), origin[:3, 3])
+    assert view.shape[0] == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    m.updateCloud(parts[1])                       # replace: a one-point map
+    assert m.size() == 1 and m.cropAround(1000.0, np.eye(4)).shape[0] == 1
+    m.close()
