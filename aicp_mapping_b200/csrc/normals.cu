@@ -234,9 +234,10 @@ __device__ __forceinline__ unsigned long long knn_key(float d, int id) {
   return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)id;
 }
 
-// per-lane max-heap of size k in shared memory; K / P already point at this lane's column (stride 32)
-__device__ __forceinline__ void heap_replace_top(unsigned long long* K, int* P, int k, unsigned long long key, int pos) {
-  int i = 0;
+// per-lane max-heap of size k in shared memory; K / P already point at this lane's column (stride 32).
+// Places (key, pos) at index i0 and sifts it down.
+__device__ __forceinline__ void heap_sift_down(unsigned long long* K, int* P, int k, int i0, unsigned long long key, int pos) {
+  int i = i0;
   while (true) {
     int c = 2 * i + 1;
     if (c >= k) break;
@@ -251,6 +252,25 @@ __device__ __forceinline__ void heap_replace_top(unsigned long long* K, int* P, 
   }
   K[i * 32] = key; P[i * 32] = pos;
 }
+__device__ __forceinline__ void heap_replace_top(unsigned long long* K, int* P, int k, unsigned long long key, int pos) {
+  heap_sift_down(K, P, k, 0, key, pos);
+}
+
+// One accepted candidate.  The first k of a lane are stored as they come and turned into a heap once (Floyd, k/2 short
+// sift-downs) instead of k full-depth replacements of infinite sentinels; `fill` counts them (== k afterwards).
+__device__ __forceinline__ void heap_accept(unsigned long long* K, int* P, int k, int& fill, unsigned long long& top,
+                                            unsigned long long key, int pos) {
+  if (fill < k) {
+    K[fill * 32] = key; P[fill * 32] = pos;
+    if (++fill == k) {
+      for (int i = k / 2 - 1; i >= 0; --i) heap_sift_down(K, P, k, i, K[i * 32], P[i * 32]);
+      top = K[0];
+    }
+  } else if (key < top) {
+    heap_replace_top(K, P, k, key, pos);
+    top = K[0];
+  }
+}
 
 // every lane measures the points [first, first + cnt) (cnt <= 32) against its own query; positions in [skip_lo, skip_hi)
 // were scanned before.  Two steps, so that the expensive heap updates of the 32 lanes run side by side: (1) a
@@ -259,7 +279,7 @@ __device__ __forceinline__ void heap_replace_top(unsigned long long* K, int* P, 
 // round per candidate that ANY lane accepts.
 __device__ __forceinline__ void tile_scan(const IndexView& ix, float4* s_pts, int first, int cnt, int skip_lo, int skip_hi,
                                           float qx, float qy, float qz, bool active, unsigned long long* K, int* P, int k,
-                                          unsigned long long& top, int lane) {
+                                          int& fill, unsigned long long& top, int lane) {
   if (lane < cnt) s_pts[lane] = __ldg(&ix.pts[first + lane]);
   __syncwarp();
   const float bound = __uint_as_float((unsigned int)(top >> 32));
@@ -283,8 +303,7 @@ __device__ __forceinline__ void tile_scan(const IndexView& ix, float4* s_pts, in
       mask &= mask - 1;
       const float4 p = s_pts[j];
       const float d = d2_f(qx, qy, qz, p.x, p.y, p.z);
-      const unsigned long long key = knn_key(d, __float_as_int(p.w));
-      if (key < top) { heap_replace_top(K, P, k, key, first + j); top = K[0]; }
+      heap_accept(K, P, k, fill, top, knn_key(d, __float_as_int(p.w)), first + j);
     }
   }
   __syncwarp();
@@ -306,16 +325,16 @@ __global__ void __launch_bounds__(32 * TILE_WARPS) k_knn_tile(IndexView ix, int 
   const int cnt0 = ix.n - i0 < 32 ? ix.n - i0 : 32;
   const bool active = lane < cnt0;
   const float4 q = __ldg(&ix.pts[i0 + (active ? lane : 0)]);
-  for (int s = 0; s < k; ++s) { K[s * 32] = KNN_INF_KEY; P[s * 32] = -1; }
-  unsigned long long top = KNN_INF_KEY;
-  tile_scan(ix, s_pts, i0, cnt0, 0, 0, q.x, q.y, q.z, active, K, P, k, top, lane);
+  unsigned long long top = KNN_INF_KEY;      // worst kept key; infinite until the lane holds k candidates
+  int fill = 0;
+  tile_scan(ix, s_pts, i0, cnt0, 0, 0, q.x, q.y, q.z, active, K, P, k, fill, top, lane);
   // the two Morton-adjacent tiles as well: a tile that straddles a jump of the Morton curve holds too few points near
   // each of its queries, and its bounds would otherwise cover the gap
   int s_lo = i0, s_hi = i0 + cnt0;                                     // positions scanned so far
-  if (i0 >= 32) { tile_scan(ix, s_pts, i0 - 32, 32, 0, 0, q.x, q.y, q.z, active, K, P, k, top, lane); s_lo = i0 - 32; }
+  if (i0 >= 32) { tile_scan(ix, s_pts, i0 - 32, 32, 0, 0, q.x, q.y, q.z, active, K, P, k, fill, top, lane); s_lo = i0 - 32; }
   if (i0 + 32 < ix.n) {
     const int c1 = ix.n - (i0 + 32) < 32 ? ix.n - (i0 + 32) : 32;
-    tile_scan(ix, s_pts, i0 + 32, c1, 0, 0, q.x, q.y, q.z, active, K, P, k, top, lane);
+    tile_scan(ix, s_pts, i0 + 32, c1, 0, 0, q.x, q.y, q.z, active, K, P, k, fill, top, lane);
     s_hi = i0 + 32 + c1;
   }
   if (ix.n > s_hi - s_lo) {
@@ -362,7 +381,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS) k_knn_tile(IndexView ix, int 
         const float dc = left ? dl : dr;
         if (__ballot_sync(0xFFFFFFFFu, active && dc <= __uint_as_float((unsigned int)(top >> 32))) == 0u) continue;
         const int cf = left ? first : split, cc = left ? split - first : end - split;
-        if (cc <= 32) tile_scan(ix, s_pts, cf, cc, s_lo, s_hi, q.x, q.y, q.z, active, K, P, k, top, lane);
+        if (cc <= 32) tile_scan(ix, s_pts, cf, cc, s_lo, s_hi, q.x, q.y, q.z, active, K, P, k, fill, top, lane);
         else {
           const int child = left ? split - 1 : split;
           if (next < 0) next = child; else stack[sp++] = child;        // the nearer internal child goes first
