@@ -30,6 +30,7 @@ struct CropBox9 {
   float m[9];        // inverse rotation (row-major): local = m * (p - t)
   float t[3];
   float bmin, bmax;
+  float reach;       // sqrt(3) * max(|bmin|, |bmax|) * (1 + 1e-4): no point with a larger |p_k - t_k| can be inside
 };
 
 __global__ void k_crop_reset(unsigned long long* status, int n_tiles, unsigned int* ticket, unsigned long long* total) {
@@ -48,22 +49,27 @@ __global__ void __launch_bounds__(256) k_crop_box(const float4* __restrict__ pts
   const unsigned int tile = s_tile;
   const long long base = (long long)tile * CROP_TILE;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // all loads of the tile first (8 independent 16-byte loads in flight per thread), then the tests
   float4 p[CROP_ROWS];
+#pragma unroll
+  for (int r = 0; r < CROP_ROWS; ++r) {
+    const long long i = base + r * 256 + threadIdx.x;
+    p[r] = i < n ? __ldg(&pts[i]) : make_float4(NAN, NAN, NAN, 0.f);          // padding behaves like a non-finite point
+  }
   unsigned int keep = 0;              // bit r: row r of this thread is inside the box
   int rank[CROP_ROWS];
 #pragma unroll
   for (int r = 0; r < CROP_ROWS; ++r) {
-    const long long i = base + r * 256 + threadIdx.x;
     bool in = false;
-    if (i < n) {
-      p[r] = __ldg(&pts[i]);
-      if (isfinite(p[r].x) && isfinite(p[r].y) && isfinite(p[r].z)) {
-        const float dx = __fsub_rn(p[r].x, box.t[0]), dy = __fsub_rn(p[r].y, box.t[1]), dz = __fsub_rn(p[r].z, box.t[2]);
-        const float lx = __fadd_rn(__fadd_rn(__fmul_rn(box.m[0], dx), __fmul_rn(box.m[1], dy)), __fmul_rn(box.m[2], dz));
-        const float ly = __fadd_rn(__fadd_rn(__fmul_rn(box.m[3], dx), __fmul_rn(box.m[4], dy)), __fmul_rn(box.m[5], dz));
-        const float lz = __fadd_rn(__fadd_rn(__fmul_rn(box.m[6], dx), __fmul_rn(box.m[7], dy)), __fmul_rn(box.m[8], dz));
-        in = !(lx < box.bmin || ly < box.bmin || lz < box.bmin || lx > box.bmax || ly > box.bmax || lz > box.bmax);
-      }
+    const float dx = __fsub_rn(p[r].x, box.t[0]), dy = __fsub_rn(p[r].y, box.t[1]), dz = __fsub_rn(p[r].z, box.t[2]);
+    // cheap conservative reject before the rotation: inside needs |local_k| <= B on every axis, hence |d|_2 <= sqrt(3) B;
+    // a single |d_k| beyond that bound (with 1e-4 of slack, 100x the float error of the rotated values) decides "outside".
+    // NaN and infinite coordinates fail this test too (the comparison is false for NaN), so no separate isfinite pass.
+    if (fabsf(dx) <= box.reach && fabsf(dy) <= box.reach && fabsf(dz) <= box.reach) {
+      const float lx = __fadd_rn(__fadd_rn(__fmul_rn(box.m[0], dx), __fmul_rn(box.m[1], dy)), __fmul_rn(box.m[2], dz));
+      const float ly = __fadd_rn(__fadd_rn(__fmul_rn(box.m[3], dx), __fmul_rn(box.m[4], dy)), __fmul_rn(box.m[5], dz));
+      const float lz = __fadd_rn(__fadd_rn(__fmul_rn(box.m[6], dx), __fmul_rn(box.m[7], dy)), __fmul_rn(box.m[8], dz));
+      in = !(lx < box.bmin || ly < box.bmin || lz < box.bmin || lx > box.bmax || ly > box.bmax || lz > box.bmax);
     }
     const unsigned int bal = __ballot_sync(0xFFFFFFFFu, in);
     rank[r] = __popc(bal & ((1u << lane) - 1u));
@@ -82,25 +88,31 @@ __global__ void __launch_bounds__(256) k_crop_box(const float4* __restrict__ pts
     }
     const int excl = incl - (a + b);
     s_cnt[2 * lane] = excl; s_cnt[2 * lane + 1] = excl + a;
-    const int tile_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (lane == 0) {
-      s_cnt[CROP_ROWS * 8] = tile_total;
-      // chained scan with decoupled look-back: publish this tile's aggregate, then walk back over the predecessors
-      unsigned long long prefix = 0;
-      if (tile == 0) {
-        atomicExch(&status[0], CROP_PREFIX | (unsigned long long)tile_total);
-      } else {
-        atomicExch(&status[tile], CROP_AGG | (unsigned long long)tile_total);
-        long long j = (long long)tile - 1;
-        while (true) {
-          unsigned long long s = *(volatile unsigned long long*)&status[j];
-          if ((s >> 62) == 0ull) continue;                  // predecessor not published yet (it is running: ticket order)
-          prefix += s & CROP_MASK;
-          if ((s >> 62) == 2ull) break;
-          --j;
-        }
-        atomicExch(&status[tile], CROP_PREFIX | (prefix + (unsigned long long)tile_total));
+    const unsigned int tile_total = (unsigned int)__shfl_sync(0xFFFFFFFFu, incl, 31);
+    // chained scan with decoupled look-back, one warp wide: publish this tile's aggregate, then read the status words of
+    // the 32 preceding tiles at once, add the aggregates down to the nearest tile that already knows its inclusive prefix
+    unsigned long long prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&status[0], CROP_PREFIX | (unsigned long long)tile_total);
+    } else {
+      if (lane == 0) atomicExch(&status[tile], CROP_AGG | (unsigned long long)tile_total);
+      long long j0 = (long long)tile - 1;
+      while (true) {
+        const long long j = j0 - lane;
+        unsigned long long st = j >= 0 ? *(volatile unsigned long long*)&status[j] : CROP_PREFIX;   // nothing before tile 0
+        while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0ull))                  // predecessors are running (ticket order)
+          if ((st >> 62) == 0ull) st = *(volatile unsigned long long*)&status[j];
+        const unsigned int has_prefix = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2ull);
+        const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;
+        const unsigned int part = __reduce_add_sync(0xFFFFFFFFu, lane <= stop ? (unsigned int)(st & CROP_MASK) : 0u);
+        prefix += part;
+        if (has_prefix) break;
+        j0 -= 32;
       }
+      if (lane == 0) atomicExch(&status[tile], CROP_PREFIX | (prefix + (unsigned long long)tile_total));
+    }
+    if (lane == 0) {
+      s_cnt[CROP_ROWS * 8] = (int)tile_total;
       s_base = prefix;
       if (base + CROP_TILE >= n) *total = prefix + (unsigned long long)tile_total;     // the last tile knows the answer
     }
@@ -125,6 +137,8 @@ int run_crop_box(Handle* h, const float4* pts, int64_t n, float bmin, float bmax
   for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) box.m[3 * r + c] = R[3 * c + r];
   for (int d = 0; d < 3; ++d) box.t[d] = translation[d];
   box.bmin = bmin; box.bmax = bmax;
+  box.reach = 1.7320508f * fmaxf(fabsf(bmin), fabsf(bmax)) * 1.0001f;
+  if (!(box.reach < INFINITY)) box.reach = 3.0e38f;      // finite, so that non-finite coordinates are still rejected
   const long long n_tiles = (n + CROP_TILE - 1) / CROP_TILE;
   CUDA_TRY(h->crop_status.reserve((size_t)n_tiles + 2));
   unsigned long long* status = h->crop_status.p;
