@@ -37,7 +37,7 @@ struct SpatialIndex {
   DevBuf<float4> chunkbox;       // boxes of every 32 / 1024 / 32768 consecutive sorted points (lo, hi pairs)
   DevBuf<int> owner;             // per point: lowest node with > 8 (first n) resp. > 32 (next n) points above it
   DevBuf<float4> cellbox;        // per internal node: shrunk float box of the node's Morton cell (lo, hi), see search.cuh
-  DevBuf<unsigned char> sort_tmp;
+  DevBuf<unsigned int> sort_tmp;  // radix sort scratch: digit histograms, tickets, per-tile status words
   IndexMeta* meta = nullptr;     // device
   int n = 0;
   IndexView view() const { return IndexView{pts.p, rec.p, owner.p, owner.p + n, cellbox.p, n}; }
@@ -123,6 +123,9 @@ struct Handle {
 // ---- index.cu
 // with_tree = false: Morton order only (pts), no radix tree -- enough to make the queries of a warp spatially coherent
 int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n, bool with_tree = true);
+// ---- sort.cu
+int radix_sort_pairs(Handle* h, unsigned int* keys, unsigned int* vals, unsigned int* keys_alt, unsigned int* vals_alt, int n,
+                     DevBuf<unsigned int>& scratch);
 // ---- normals.cu
 int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig);
 // ---- icp.cu

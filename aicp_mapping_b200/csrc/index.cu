@@ -3,7 +3,7 @@
 //   k_index_stats   one pass over the cloud: bounding box (ordered-int atomics), exact fixed-point centroid sums
 //                   (order independent, so the mean is identical on every GPU count), non-finite flag
 //   k_morton_keys   30-bit Morton key of the isotropically quantised position + identity permutation
-//   radix sort      (key, original index) pairs, 30 significant bits
+//   radix sort      (key, original index) pairs, 30 significant bits (sort.cu)
 //   k_gather        Morton-ordered float4 copy with the original index in .w
 //   k_radix_tree    Karras binary radix tree over the sorted keys: one thread per internal node
 //   k_chunk_boxes   boxes of every 32 / 1024 / 32768 consecutive sorted points
@@ -12,8 +12,6 @@
 //
 // Algorithmic HBM bytes per point: read 16 + key/perm 8 written + 8 read by the gather + 16 written = 48,
 // plus 64 B of tree record and 16 B of node range per point.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "handle.cuh"
 
 namespace aicp {
@@ -314,10 +312,6 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
   }
   CUDA_TRY(ix.keys.reserve((size_t)n)); CUDA_TRY(ix.keys_alt.reserve((size_t)n));
   CUDA_TRY(ix.vals.reserve((size_t)n)); CUDA_TRY(ix.vals_alt.reserve((size_t)n));
-  size_t tmp_bytes = 0;
-  cub::DoubleBuffer<unsigned int> dk(ix.keys.p, ix.keys_alt.p), dv(ix.vals.p, ix.vals_alt.p);
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, 30, s));
-  CUDA_TRY(ix.sort_tmp.reserve(tmp_bytes));
 
   k_meta_init<<<1, 32, 0, s>>>(ix.meta);
   int blocks = (n + 255) / 256;
@@ -325,9 +319,10 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
   k_index_stats<<<stat_blocks, 256, 0, s>>>(pts_dev, n, ix.meta);
   k_quant_params<<<1, 32, 0, s>>>(ix.meta);
   k_morton_keys<<<blocks, 256, 0, s>>>(pts_dev, n, ix.meta, ix.keys.p, ix.vals.p);
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(ix.sort_tmp.p, tmp_bytes, dk, dv, n, 0, 30, s));
-  k_gather<<<blocks, 256, 0, s>>>(pts_dev, dv.Current(), n, ix.pts.p);
-  h->launches += 5 + 4;    // own kernels + the radix sort's passes
+  int rc = radix_sort_pairs(h, ix.keys.p, ix.vals.p, ix.keys_alt.p, ix.vals_alt.p, n, ix.sort_tmp);    // result in keys / vals
+  if (rc) return rc;
+  k_gather<<<blocks, 256, 0, s>>>(pts_dev, ix.vals.p, n, ix.pts.p);
+  h->launches += 5;
   if (n > 1 && with_tree) {
     int* parent_int = ix.flags.p;
     int* parent_leaf = ix.flags.p + n;
@@ -337,7 +332,7 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
     float4* l3 = l2 + 2 * (size_t)n_l2;
     k_chunk_boxes<<<n_l2, 1024, 0, s>>>(ix.pts.p, n, l1, l2);
     k_chunk_boxes_top<<<(n_l3 * 32 + 255) / 256, 256, 0, s>>>(l2, n_l2, l3, n_l3);
-    k_radix_tree<<<blocks, 256, 0, s>>>(dk.Current(), n, ix.node_meta.p, parent_int, parent_leaf, ix.owner.p, ix.owner.p + n, ix.meta, ix.cellbox.p);
+    k_radix_tree<<<blocks, 256, 0, s>>>(ix.keys.p, n, ix.node_meta.p, parent_int, parent_leaf, ix.owner.p, ix.owner.p + n, ix.meta, ix.cellbox.p);
     k_refit<<<(2 * (n - 1) + 255) / 256, 256, 0, s>>>(ix.pts.p, n, ix.node_meta.p, parent_int, l1, l2, l3, ix.rec.p);
     h->launches += 4;
   }
