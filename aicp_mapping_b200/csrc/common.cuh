@@ -41,6 +41,7 @@ struct DeviceState {
   // loop control
   int   iter;
   int   done;
+  int   done_at;                    // sharded loop: index of the iteration whose solve (or status exchange) ended the loop, -1 before
   int   stop_reason;
   int   status;                     // AICP_B200_* error raised on device
   int   hist_n;

@@ -17,6 +17,7 @@
 // differential checker cannot stop earlier) and then stays at most two iterations ahead of the device, reading the
 // iteration counter the solve publishes in mapped pinned memory -- a registration that converges after 8 of 20
 // iterations does not pay for 36 empty launches.
+#include <atomic>
 #include <thread>
 
 #include "detmath.cuh"
@@ -53,7 +54,7 @@ __device__ __forceinline__ void raise_status(DeviceState* st, int code) {
 // ---- setup --------------------------------------------------------------------------------------------------------
 __global__ void k_loop_init(DeviceState* st, const IndexMeta* __restrict__ meta, long long n_ref, int have_init) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  st->status = 0; st->done = 0; st->stop_reason = 0; st->iter = 0; st->hist_n = 1;
+  st->status = 0; st->done = 0; st->done_at = -1; st->stop_reason = 0; st->iter = 0; st->hist_n = 1;
   st->prefix = 0; st->k_rem = 0; st->n_valid = 0; st->limit = 0.f; st->n_used_last = 0;
   for (int i = 0; i < 4; ++i) st->ticket[i] = 0;
   st->cand_n = 0;
@@ -663,20 +664,31 @@ __global__ void k_sums_to_limbs(DeviceState* st, unsigned long long* limbs) {
   if (i == AICP_NSUM) limbs[4 * AICP_NSUM] = st->status != 0 ? 1ull : 0ull;
 }
 
-__global__ void k_limbs_solve(DeviceState* st, const unsigned long long* limbs, LoopParams lp, int n) {
+// Sharded loop control: every rank holds the same state after the exchange, so "the loop ended at iteration D" is the same
+// fact on every rank.  The kernel publishes, in this order, (D + 1) and then the number of iterations whose exchange has
+// completed; the hosts enqueue iteration `it` unless the loop had ended by iteration it - 2 -- a rule that depends only on
+// D, not on when a host happens to look, so all ranks issue the same number of NCCL calls.
+__global__ void k_limbs_solve(DeviceState* st, const unsigned long long* limbs, LoopParams lp, int n, int it, volatile int* progress) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (limbs[4 * AICP_NSUM] != 0 && st->status == 0) raise_status(st, AICP_B200_ERR_COMM);
-  if (ld_int(&st->done)) return;
-  for (int i = 0; i < AICP_NSUM; ++i) {
-    unsigned long long l0 = limbs[4 * i], l1 = limbs[4 * i + 1], l2 = limbs[4 * i + 2], l3 = limbs[4 * i + 3];
-    unsigned long long c = l0 >> 32;  unsigned long long w0 = l0 & 0xFFFFFFFFull;
-    l1 += c; c = l1 >> 32;            unsigned long long w1 = l1 & 0xFFFFFFFFull;
-    l2 += c; c = l2 >> 32;            unsigned long long w2 = l2 & 0xFFFFFFFFull;
-    l3 += c;                          unsigned long long w3 = l3 & 0xFFFFFFFFull;      // modulo 2^128
-    st->sum_lo[i] = w0 | (w1 << 32);
-    st->sum_hi[i] = (long long)(w2 | (w3 << 32));
+  if (!ld_int(&st->done)) {
+    for (int i = 0; i < AICP_NSUM; ++i) {
+      unsigned long long l0 = limbs[4 * i], l1 = limbs[4 * i + 1], l2 = limbs[4 * i + 2], l3 = limbs[4 * i + 3];
+      unsigned long long c = l0 >> 32;  unsigned long long w0 = l0 & 0xFFFFFFFFull;
+      l1 += c; c = l1 >> 32;            unsigned long long w1 = l1 & 0xFFFFFFFFull;
+      l2 += c; c = l2 >> 32;            unsigned long long w2 = l2 & 0xFFFFFFFFull;
+      l3 += c;                          unsigned long long w3 = l3 & 0xFFFFFFFFull;      // modulo 2^128
+      st->sum_lo[i] = w0 | (w1 << 32);
+      st->sum_hi[i] = (long long)(w2 | (w3 << 32));
+    }
+    solve_and_check(st, lp, n);
   }
-  solve_and_check(st, lp, n);
+  if (ld_int(&st->done) && st->done_at < 0) st->done_at = it;
+  if (progress) {
+    if (st->done_at >= 0) { progress[1] = st->done_at + 1; __threadfence_system(); }
+    progress[0] = it + 1;
+    __threadfence_system();
+  }
 }
 
 // ---- epilogue ----------------------------------------------------------------------------------------------------
@@ -861,18 +873,21 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   prog[0] = 0; prog[1] = 0;           // the stream is idle here: every earlier call ended with a synchronisation
   int enqueued = 0;
   for (int it = 0; it < cfg.max_iterations; ++it) {
-    if (!h->comm && it >= cfg.smooth_length && it >= LOOKAHEAD) {
+    if (it >= cfg.smooth_length && it >= LOOKAHEAD) {
       unsigned spins = 0;
       // busy-wait on purpose: sleeping on a blocking-sync event instead was measured 6 % slower (wake-up latency), also with
       // four ranks on one host; after a short spin the thread yields so that oversubscribed hosts degrade gracefully
-      while (prog[1] == 0 && prog[0] < it - LOOKAHEAD + 1) {
+      while ((h->comm || prog[1] == 0) && prog[0] < it - LOOKAHEAD + 1) {
         if ((++spins & 0x3FFu) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;   // stream drained or failed: stop waiting
         if (spins > 256) std::this_thread::yield();
 #if defined(__x86_64__)
         else __builtin_ia32_pause();
 #endif
       }
-      if (prog[1] != 0) break;
+      std::atomic_thread_fence(std::memory_order_acquire);
+      const int ended = prog[1];
+      if (!h->comm) { if (ended != 0) break; }
+      else if (ended != 0 && ended - 1 <= it - LOOKAHEAD) break;       // same decision on every rank (see k_limbs_solve)
     }
     mark_match(3 + 4 * (size_t)it);
     if (!h->comm) {
@@ -906,7 +921,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
       unsigned long long* limbs = comm_limbs(h);
       k_sums_to_limbs<<<1, 32, 0, s>>>(h->st, limbs);
       if ((rc = comm_allreduce_u64(h, limbs, 4 * AICP_NSUM + 1))) return rc;
-      k_limbs_solve<<<1, 32, 0, s>>>(h->st, limbs, lp, n_read);
+      k_limbs_solve<<<1, 32, 0, s>>>(h->st, limbs, lp, n_read, it, h->progress_dev);
       mark(6 + 4 * (size_t)it);
       h->launches += 9;
     }
