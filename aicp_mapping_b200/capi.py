@@ -21,7 +21,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aic
            "aicp_b200_set_reference", "aicp_b200_register_to_reference", "aicp_b200_get_output_reading",
            "aicp_b200_get_initialized_reading", "aicp_b200_get_reference_normals", "aicp_b200_enable_match_trace",
            "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
-           "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_comm_unique_id",
+           "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_comm_unique_id",
            "aicp_b200_comm_init", "aicp_b200_comm_destroy"]
 
 
@@ -104,6 +104,9 @@ def lib():
         L.aicp_b200_autotune_ratio.restype = C.c_float
         L.aicp_b200_register_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_void_p),
                                                C.POINTER(i64), fp, C.c_int, fp, C.POINTER(Stats), C.POINTER(C.c_int32), fp]
+        L.aicp_b200_aicp_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double), C.c_double, C.c_int, fp, fp,
+                                           C.POINTER(Stats), C.POINTER(C.c_int32), fp]
         L.aicp_b200_comm_unique_id.argtypes = [C.c_void_p]
         L.aicp_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.aicp_b200_comm_destroy.argtypes = [C.c_void_p]

@@ -448,9 +448,12 @@ float aicp_b200_autotune_ratio(float overlap_pct) {
   return strtof(buf, nullptr);
 }
 
-int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
-                             const float* const* read_xyzw, const int64_t* n_read, const float* ratios, int streams,
-                             float* out_T, aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
+// common implementation of the two batch entry points; origins != nullptr: one AICP step per pair (overlap -> clamp and
+// 6-digit round trip -> registration with that ratio), else registration only with the given / configured ratios
+static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                      const float* const* read_xyzw, const int64_t* n_read, const float* ratios, const double* ref_origins,
+                      const double* read_origins, double resolution, int streams, float* out_T, float* out_overlap,
+                      aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   H_CHECK(h);
   if (n_pairs < 0 || (n_pairs > 0 && (!ref_xyzw || !n_ref || !read_xyzw || !n_read || !out_T)))
@@ -490,8 +493,27 @@ int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float*
       int64_t i = next.fetch_add(1);
       if (i >= n_pairs) break;
       if (ratios) wh->cfg.ratio = ratios[i];
-      int r = aicp_b200_register(reinterpret_cast<aicp_b200_handle*>(wh), ref_xyzw[i], n_ref[i], read_xyzw[i], n_read[i], nullptr,
-                                 out_T + 16 * i, stats ? stats + i : nullptr);
+      int r = AICP_B200_OK;
+      if (ref_origins) {
+        // App::runAicpPipeline (app.cpp:218-247): computeOverlap, then computeRegistration with the auto-tuned ratio
+        // both clouds are staged once into the worker's own buffers and used by the overlap and by the registration
+        float ov = 0.f;
+        if (!ref_xyzw[i] || !read_xyzw[i] || n_ref[i] < 1 || n_read[i] < 1 || n_ref[i] > (1ll << 30) || n_read[i] > (1ll << 30))
+          r = fail(wh, AICP_B200_ERR_BAD_ARG, "aicp_batch: null or empty cloud in pair %lld", (long long)i);
+        if (!r) r = stage_owned(wh, wh->ref_in, ref_xyzw[i], n_ref[i]);
+        if (!r) r = stage_owned(wh, wh->read_in, read_xyzw[i], n_read[i]);
+        if (!r) r = run_overlap(wh, wh->ref_in.p, n_ref[i], ref_origins + 3 * i, wh->read_in.p, n_read[i], read_origins + 3 * i,
+                                resolution, &ov, nullptr);
+        if (out_overlap) out_overlap[i] = ov;
+        if (!r) {
+          wh->cfg.ratio = aicp_b200_autotune_ratio(ov);
+          wh->n_ref = n_ref[i]; wh->n_read = n_read[i];
+          r = run_registration(wh, nullptr, true, stats ? stats + i : nullptr, out_T + 16 * i);
+        }
+      } else {
+        r = aicp_b200_register(reinterpret_cast<aicp_b200_handle*>(wh), ref_xyzw[i], n_ref[i], read_xyzw[i], n_read[i], nullptr,
+                               out_T + 16 * i, stats ? stats + i : nullptr);
+      }
       if (status) status[i] = r;
       if (r) {
         int expected = 0;
@@ -513,6 +535,22 @@ int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float*
     return first_err.load();
   }
   return AICP_B200_OK;
+}
+
+int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                             const float* const* read_xyzw, const int64_t* n_read, const float* ratios, int streams,
+                             float* out_T, aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
+  return batch_impl(hh, n_pairs, ref_xyzw, n_ref, read_xyzw, n_read, ratios, nullptr, nullptr, 0.0, streams, out_T, nullptr, stats,
+                    status, batch_ms);
+}
+
+int aicp_b200_aicp_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                         const double* ref_origins, const float* const* read_xyzw, const int64_t* n_read,
+                         const double* read_origins, double resolution, int streams, float* out_T, float* out_overlap,
+                         aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
+  if (!ref_origins || !read_origins) return AICP_B200_ERR_BAD_ARG;
+  return batch_impl(hh, n_pairs, ref_xyzw, n_ref, read_xyzw, n_read, nullptr, ref_origins, read_origins, resolution, streams, out_T,
+                    out_overlap, stats, status, batch_ms);
 }
 
 }  // extern "C"

@@ -222,6 +222,33 @@ class B200Registration:
         self._check(rc)
         return np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4), stats, status, float(ms.value)
 
+    def aicpBatch(self, pairs, origins, resolution=float(np.float32(0.2)), streams=0):
+        """aicp_b200_aicp_batch: one AICP step (overlap -> auto-tuned ratio -> registration, app.cpp:218-247) per pair.
+        `pairs`: list of (cloud_ref, cloud_read); `origins`: list of (ref_origin[3], read_origin[3]).
+        Returns (T [n,4,4], overlap [n] percent, stats list, status array, batch_ms)."""
+        n = len(pairs)
+        keep, refs, reads = [], (C.c_void_p * n)(), (C.c_void_p * n)()
+        n_ref, n_read = (C.c_int64 * n)(), (C.c_int64 * n)()
+        for i, (r, q) in enumerate(pairs):
+            pr, nr, kr = capi.ptr_and_count(r)
+            pq, nq, kq = capi.ptr_and_count(q)
+            refs[i], reads[i], n_ref[i], n_read[i] = pr, pq, nr, nq
+            keep.append((kr, kq))
+        ro = np.ascontiguousarray([o[0] for o in origins], dtype=np.float64).reshape(n, 3)
+        so = np.ascontiguousarray([o[1] for o in origins], dtype=np.float64).reshape(n, 3)
+        T = np.zeros((n, 16), dtype=np.float32)
+        ov = np.zeros(n, dtype=np.float32)
+        stats = (capi.Stats * n)()
+        status = np.zeros(n, dtype=np.int32)
+        ms = C.c_float()
+        fp = C.POINTER(C.c_float)
+        rc = self._lib.aicp_b200_aicp_batch(self._h, n, refs, n_ref, ro.ctypes.data_as(C.POINTER(C.c_double)), reads, n_read,
+                                            so.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(resolution), int(streams),
+                                            T.ctypes.data_as(fp), ov.ctypes.data_as(fp), stats,
+                                            status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
+        self._check(rc)
+        return (np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4)), ov, stats, status, float(ms.value)
+
     # ---- multi-GPU single registration (reading sharded over ranks) --------------------------------------------------
     def commInit(self, unique_id, rank, n_ranks):
         """aicp_b200_comm_init.  unique_id: the 128 bytes from comm_unique_id() on rank 0, broadcast by the caller."""

@@ -211,6 +211,16 @@ int aicp_b200_register_batch(aicp_b200_handle* h, int64_t n_pairs, const float* 
                              const float* const* read_xyzw, const int64_t* n_read, const float* ratios /*nullable*/,
                              int streams, float* out_T, aicp_b200_stats* stats, int32_t* status, float* batch_ms);
 
+/* One whole AICP step per pair, batched: replaces App::runAicpPipeline's computeOverlap + computeRegistration
+ * (aicp_core/src/registration/app.cpp:218-247, 112-141, 187-216) for many independent pairs -- the registration-validation
+ * sweep of BASELINE.json config 5 ("overlap + ..."): per pair the octree overlap, the clamp to [0.25, 0.70] with the 6-digit
+ * text round trip, and the registration with that trimmed ratio, all inside the pair's worker stream.
+ * ref_origins / read_origins: n_pairs x 3 doubles (sensor pose translations); out_overlap: nullable, n_pairs percentages. */
+int aicp_b200_aicp_batch(aicp_b200_handle* h, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                         const double* ref_origins, const float* const* read_xyzw, const int64_t* n_read,
+                         const double* read_origins, double resolution, int streams, float* out_T, float* out_overlap,
+                         aicp_b200_stats* stats, int32_t* status, float* batch_ms);
+
 /* ---- multi-GPU single registration (BASELINE.json config 4: reading sharded, reference replicated) ---------------
  * nccl_unique_id: the 128-byte ncclUniqueId obtained on rank 0 with aicp_b200_comm_unique_id and broadcast by the
  * caller (e.g. torch.distributed).  After comm_init, aicp_b200_register* calls on every rank take that rank's SHARD of

@@ -104,3 +104,25 @@ def test_c5_batch_of_perturbed_pairs(reg, orc):
     for p, Tp in zip(pairs, T):
         d = Tp.astype(np.float64) @ np.linalg.inv(p["T_true"])
         assert np.linalg.norm(d[:3, 3]) < 0.02 and rot_angle(d[:3, :3]) < 0.01
+
+
+def test_aicp_batch_whole_step_equals_separate_calls(reg, orc):
+    """aicp_b200_aicp_batch (overlap -> auto-tuned ratio -> registration per pair, concurrently) against the same steps made
+    one by one, and one pair against the oracle's overlap + registration."""
+    ov = ab.B200Overlap()
+    pairs = [synth.make_pair(5, t, 6000 + 700 * t) for t in range(6)] + [synth.make_pair(2, 0, 8192)]
+    reg.setConfig(max_iterations=20)
+    T, overlap, stats, status, ms = reg.aicpBatch([(p["ref"], p["read"]) for p in pairs],
+                                                 [(p["ref_origin"], p["read_origin"]) for p in pairs], streams=4)
+    assert all(s == 0 for s in status) and ms > 0
+    for i, p in enumerate(pairs):
+        ov.computeOverlap(p["ref"], p["read"], p["ref_origin"], p["read_origin"])
+        assert np.float32(ov.getOverlap()) == overlap[i]
+        reg.setConfig(ratio=ab.autotune_ratio(float(ov.getOverlap())), max_iterations=20)
+        Ts = reg.registerClouds(p["ref"], p["read"])
+        assert np.array_equal(u32(Ts), u32(T[i])) and reg.stats.iterations == stats[i].iterations
+    p = pairs[-1]
+    o_ov, _ = orc.overlap(p["ref"], p["ref_origin"], p["read"], p["read_origin"])
+    o = orc.icp(p["ref"], p["read"], orc.default_config(ratio=float(orc.autotune_ratio(float(o_ov))[0]), threads=8))
+    assert np.float32(o_ov) == overlap[-1] and np.array_equal(u32(o.T), u32(T[-1]))
+    ov.close()
