@@ -21,7 +21,9 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aic
            "aicp_b200_set_reference", "aicp_b200_register_to_reference", "aicp_b200_get_output_reading",
            "aicp_b200_get_initialized_reading", "aicp_b200_get_reference_normals", "aicp_b200_enable_match_trace",
            "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
-           "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_comm_unique_id",
+           "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_prefilter_default_config", "aicp_b200_prefilter", "aicp_b200_get_prefiltered",
+           "aicp_b200_prefilter_get_sampled", "aicp_b200_prefilter_get_normals", "aicp_b200_prefilter_get_labels", "aicp_b200_voxel_grid",
+           "aicp_b200_map_prefilter", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_comm_unique_id",
            "aicp_b200_comm_init", "aicp_b200_comm_destroy"]
 
 
@@ -46,6 +48,18 @@ class Stats(C.Structure):
                 ("profiled", C.c_int32), ("ms_index", C.c_float), ("ms_normals", C.c_float), ("ms_match", C.c_float),
                 ("ms_select", C.c_float), ("ms_accumulate", C.c_float), ("ms_tail_pick", C.c_float), ("ms_tail_select", C.c_float),
                 ("ms_tail_solve", C.c_float), ("trace", IterTrace * MAX_ITERS)]
+
+
+class PrefilterConfig(C.Structure):
+    """aicp_b200_prefilter_config: the PCL parameters hard-coded in filteringUtils.cpp:10-34."""
+    _fields_ = [("leaf_size", C.c_float), ("knn_normals", C.c_int32), ("n_neighbours", C.c_int32),
+                ("min_cluster_size", C.c_int32), ("max_cluster_size", C.c_int32), ("smoothness_threshold", C.c_float),
+                ("curvature_threshold", C.c_float)]
+
+
+class PrefilterInfo(C.Structure):
+    _fields_ = [("n_sampled", C.c_int64), ("n_clusters", C.c_int64), ("n_out", C.c_int64), ("passes", C.c_int32),
+                ("gpu_launches", C.c_int32), ("ms_total", C.c_float)]
 
 
 class AicpError(RuntimeError):
@@ -100,6 +114,16 @@ def lib():
         L.aicp_b200_map_size.argtypes = [C.c_void_p]
         L.aicp_b200_map_size.restype = i64
         L.aicp_b200_map_crop.argtypes = [C.c_void_p, C.c_float, C.c_float, fp, fp, C.POINTER(i64)]
+        L.aicp_b200_prefilter_default_config.argtypes = [C.POINTER(PrefilterConfig)]
+        L.aicp_b200_prefilter.argtypes = [C.c_void_p, C.c_void_p, i64, C.POINTER(PrefilterConfig), fp, C.c_void_p, C.POINTER(i64),
+                                          C.POINTER(PrefilterInfo)]
+        L.aicp_b200_get_prefiltered.argtypes = [C.c_void_p, C.POINTER(i64)]
+        L.aicp_b200_get_prefiltered.restype = C.c_void_p
+        L.aicp_b200_prefilter_get_sampled.argtypes = [C.c_void_p, C.c_void_p, i64]
+        L.aicp_b200_prefilter_get_normals.argtypes = [C.c_void_p, C.c_void_p, i64]
+        L.aicp_b200_prefilter_get_labels.argtypes = [C.c_void_p, C.c_void_p, i64]
+        L.aicp_b200_voxel_grid.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_float, C.c_void_p, C.POINTER(i64)]
+        L.aicp_b200_map_prefilter.argtypes = [C.c_void_p, C.POINTER(PrefilterConfig), C.POINTER(i64), C.POINTER(PrefilterInfo)]
         L.aicp_b200_autotune_ratio.argtypes = [C.c_float]
         L.aicp_b200_autotune_ratio.restype = C.c_float
         L.aicp_b200_register_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_void_p),

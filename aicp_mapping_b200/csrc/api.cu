@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of libaicp_b200.so (include/aicp_b200.h).  Thin: argument checks, host<->device staging on the
 // handle's stream, and calls into index.cu / normals.cu / icp.cu / overlap.cu.  No compute happens on the host.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -133,6 +134,13 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   if (h->progress_host) cudaFreeHost((void*)h->progress_host);
   h->tmp_ix.release(); h->tmp_a.release(); h->tmp_b.release(); h->tmp_i.release(); h->tmp_f.release();
   h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release(); h->crop_status.release(); h->crop_out.release(); h->map.release();
+  h->pf_ix.release(); h->pf_sampled.release(); h->pf_normals.release(); h->pf_normals_orig.release(); h->pf_out.release();
+  h->pf_keys.release(); h->pf_keys_alt.release(); h->pf_vals.release(); h->pf_vals_alt.release(); h->pf_sort_tmp.release();
+  h->pf_flag.release(); h->pf_slot.release(); h->pf_tiles.release(); h->pf_mask.release(); h->pf_count.release();
+  h->pf_label.release(); h->pf_seed_pos.release(); h->pf_labels_out.release();
+  if (h->pf_meta) cudaFree(h->pf_meta);
+  if (h->pf_meta_host) cudaFreeHost(h->pf_meta_host);
+  for (int i = 0; i < 2; ++i) if (h->pf_ev[i]) cudaEventDestroy(h->pf_ev[i]);
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -435,6 +443,107 @@ const float* aicp_b200_get_cropped(aicp_b200_handle* hh, int64_t* n_out) {
   if (!h) return nullptr;
   if (n_out) *n_out = h->crop_n;
   return reinterpret_cast<const float*>(h->crop_out.p);
+}
+
+int aicp_b200_prefilter_default_config(aicp_b200_prefilter_config* cfg) {
+  if (!cfg) return AICP_B200_ERR_BAD_ARG;
+  cfg->leaf_size = 0.08f;
+  cfg->knn_normals = 30;
+  cfg->n_neighbours = 15;
+  cfg->min_cluster_size = 50;
+  cfg->max_cluster_size = 1000000;
+  cfg->smoothness_threshold = (float)(3.0 / 180.0 * M_PI);
+  cfg->curvature_threshold = 1.0f;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_prefilter(aicp_b200_handle* hh, const float* xyzw, int64_t n, const aicp_b200_prefilter_config* cfg,
+                        const float viewpoint[3], float* out_xyzw, int64_t* n_out, aicp_b200_prefilter_info* info) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!n_out || n < 0 || (n > 0 && !xyzw)) return fail(h, AICP_B200_ERR_BAD_ARG, "prefilter: bad arguments");
+  *n_out = 0;
+  if (info) memset(info, 0, sizeof(*info));
+  h->pf_n_out = 0; h->pf_n_sampled = 0; h->pf_n_clusters = 0; h->pf_has_segments = false;
+  if (n == 0) return AICP_B200_OK;
+  aicp_b200_prefilter_config def;
+  if (!cfg) { aicp_b200_prefilter_default_config(&def); cfg = &def; }
+  const float4* pts;
+  int rc = upload_points(h, h->tmp_a, xyzw, n, &pts);
+  if (rc) return rc;
+  if ((rc = run_prefilter(h, pts, n, cfg, viewpoint, info))) return rc;
+  *n_out = h->pf_n_out;
+  if (out_xyzw && h->pf_n_out > 0) return download(h, out_xyzw, h->pf_out.p, sizeof(float4) * (size_t)h->pf_n_out);
+  return AICP_B200_OK;
+}
+
+const float* aicp_b200_get_prefiltered(aicp_b200_handle* hh, int64_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return nullptr;
+  if (n_out) *n_out = h->pf_n_out;
+  return reinterpret_cast<const float*>(h->pf_out.p);
+}
+
+int aicp_b200_prefilter_get_sampled(aicp_b200_handle* hh, float* xyzw, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n != h->pf_n_sampled || (n > 0 && !xyzw)) return fail(h, AICP_B200_ERR_BAD_ARG, "prefilter_get_sampled: the last call sampled %lld points", (long long)h->pf_n_sampled);
+  if (n == 0) return AICP_B200_OK;
+  return download(h, xyzw, h->pf_sampled.p, sizeof(float4) * (size_t)n);
+}
+
+int aicp_b200_prefilter_get_normals(aicp_b200_handle* hh, float* normals_xyzc, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n != h->pf_n_sampled || (n > 0 && !normals_xyzc)) return fail(h, AICP_B200_ERR_BAD_ARG, "prefilter_get_normals: the last call sampled %lld points", (long long)h->pf_n_sampled);
+  if (n == 0) return AICP_B200_OK;
+  if (!h->pf_has_segments) return fail(h, AICP_B200_ERR_BAD_ARG, "prefilter_get_normals: the last call did not reach the normals stage");
+  return download(h, normals_xyzc, h->pf_normals_orig.p, sizeof(float4) * (size_t)n);
+}
+
+int aicp_b200_prefilter_get_labels(aicp_b200_handle* hh, int32_t* labels, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n != h->pf_n_sampled || (n > 0 && !labels)) return fail(h, AICP_B200_ERR_BAD_ARG, "prefilter_get_labels: the last call sampled %lld points", (long long)h->pf_n_sampled);
+  if (n == 0) return AICP_B200_OK;
+  if (!h->pf_has_segments) {          // fewer sampled points than neighbours: no region can be kept
+    if (is_device_ptr(labels)) { CUDA_TRY(cudaMemsetAsync(labels, 0xFF, sizeof(int32_t) * (size_t)n, h->stream)); CUDA_TRY(cudaStreamSynchronize(h->stream)); }
+    else for (int64_t i = 0; i < n; ++i) labels[i] = -1;
+    return AICP_B200_OK;
+  }
+  return download(h, labels, h->pf_labels_out.p, sizeof(int32_t) * (size_t)n);
+}
+
+int aicp_b200_voxel_grid(aicp_b200_handle* hh, const float* xyzw, int64_t n, float leaf_size, float* out_xyzw, int64_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!n_out || n < 0 || (n > 0 && (!xyzw || !out_xyzw))) return fail(h, AICP_B200_ERR_BAD_ARG, "voxel_grid: bad arguments");
+  *n_out = 0;
+  if (n == 0) return AICP_B200_OK;
+  const float4* pts;
+  int rc = upload_points(h, h->tmp_a, xyzw, n, &pts);
+  if (rc) return rc;
+  if ((rc = run_voxel_grid(h, pts, n, leaf_size, n_out))) return rc;
+  if (*n_out > 0) return download(h, out_xyzw, h->pf_sampled.p, sizeof(float4) * (size_t)*n_out);
+  return AICP_B200_OK;
+}
+
+int aicp_b200_map_prefilter(aicp_b200_handle* hh, const aicp_b200_prefilter_config* cfg, int64_t* n_out, aicp_b200_prefilter_info* info) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n_out) *n_out = 0;
+  if (info) memset(info, 0, sizeof(*info));
+  if (h->map_n == 0) return AICP_B200_OK;
+  aicp_b200_prefilter_config def;
+  if (!cfg) { aicp_b200_prefilter_default_config(&def); cfg = &def; }
+  int rc = run_prefilter(h, h->map.p, h->map_n, cfg, nullptr, info);
+  if (rc) return rc;
+  // prior_map_->updateCloud(map_prefiltered) (app.cpp:491-492): the output never exceeds the input, so it fits in place
+  if (h->pf_n_out > 0) CUDA_TRY(cudaMemcpyAsync(h->map.p, h->pf_out.p, sizeof(float4) * (size_t)h->pf_n_out, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->map_n = h->pf_n_out;
+  if (n_out) *n_out = h->pf_n_out;
+  return AICP_B200_OK;
 }
 
 float aicp_b200_autotune_ratio(float overlap_pct) {

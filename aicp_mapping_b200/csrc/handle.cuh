@@ -111,6 +111,19 @@ struct Handle {
   int64_t map_n = 0;
   DevBuf<float4> crop_out;                  // cropped cloud when the caller asks for a device-resident result
 
+  // pre-filter (prefilter.cu): VoxelGrid -> normals -> region growing
+  SpatialIndex pf_ix;                       // Morton index over the voxel-grid output
+  DevBuf<float4> pf_sampled;                // voxel centroids, ascending voxel index ("sampled order")
+  DevBuf<float4> pf_normals, pf_normals_orig;   // (nx, ny, nz, curvature): Morton order / sampled order
+  DevBuf<float4> pf_out;                    // kept clusters, concatenated
+  DevBuf<unsigned int> pf_keys, pf_keys_alt, pf_vals, pf_vals_alt, pf_sort_tmp, pf_flag, pf_slot, pf_tiles, pf_mask, pf_count;
+  DevBuf<int> pf_label, pf_seed_pos, pf_labels_out;
+  void* pf_meta = nullptr;                  // PfMeta, device
+  void* pf_meta_host = nullptr;             // pinned
+  int64_t pf_n_sampled = 0, pf_n_out = 0, pf_n_clusters = 0;
+  bool pf_has_segments = false;
+  cudaEvent_t pf_ev[2] = {nullptr, nullptr};
+
   Comm* comm = nullptr;
 
   // batch workers: one child handle (own stream + buffers) per concurrent registration
@@ -128,6 +141,7 @@ int radix_sort_pairs(Handle* h, unsigned int* keys, unsigned int* vals, unsigned
                      DevBuf<unsigned int>& scratch);
 // ---- normals.cu
 int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig);
+int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig);   // lists -> h->knn_pos (Morton positions)
 // ---- icp.cu
 int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference, aicp_b200_stats* stats, float* out_T);
 int run_match_stage(Handle* h, const SpatialIndex& ix, const float4* qry, int64_t n_qry, int* out_idx, float* out_d2);
@@ -139,6 +153,10 @@ int run_overlap(Handle* h, const float4* ref, int64_t n_ref, const double* ref_o
 // ---- crop.cu
 int run_crop_box(Handle* h, const float4* pts, int64_t n, float bmin, float bmax, const float* rpy, const float* translation,
                  float4* out_dev, int64_t* n_out);
+// ---- prefilter.cu
+int run_voxel_grid(Handle* h, const float4* pts, int64_t n, float leaf, int64_t* n_out);
+int run_prefilter(Handle* h, const float4* pts, int64_t n, const aicp_b200_prefilter_config* cfg, const float* viewpoint,
+                  aicp_b200_prefilter_info* info);
 // ---- comm.cu (sharded registration; NCCL is loaded at run time, the library has no link-time dependency on it)
 int comm_allreduce_u32(Handle* h, unsigned int* buf, size_t count);
 int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count);

@@ -465,9 +465,11 @@ __global__ void __launch_bounds__(128) k_normals_from_knn(IndexView ix, int k, c
   normals_morton[i] = make_float4((float)nx, (float)ny, (float)nz, (float)(kd / vol));
 }
 
-int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig) {
-  if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "SurfaceNormalDataPointsFilter: knn %d outside [1,32]", knn);
-  if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "SurfaceNormalDataPointsFilter: knn %d >= %d points", knn, ix.n);
+// exact k-NN lists (positions in Morton order, ascending (d2, original index)) into h->knn_pos; shared by the SurfaceNormal
+// filter of the ICP chain and by the pre-filter (prefilter.cu: pcl::NormalEstimation + pcl::RegionGrowing neighbourhoods)
+int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig) {
+  if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "k-NN search: knn %d outside [1,32]", knn);
+  if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "k-NN search: knn %d >= %d points", knn, ix.n);
   CUDA_TRY(h->knn_pos.reserve((size_t)ix.n * knn));
   // Two schedules of the same exact search (identical output): the tile kernel executes ~45 % fewer instructions and wins
   // whenever the GPU is full (batched registrations, large clouds); the warp-per-query kernel has twice as many, shorter
@@ -481,9 +483,17 @@ int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* norm
     const int tiles = (ix.n + 31) / 32;
     k_knn_tile<<<(unsigned)((tiles + TILE_WARPS - 1) / TILE_WARPS), 32 * TILE_WARPS, smem, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
   }
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return AICP_B200_OK;
+}
+
+int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig) {
+  int rc = run_knn(h, ix, knn, knn_out_orig);
+  if (rc) return rc;
   k_normals_from_knn<<<(ix.n + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton);
   CUDA_TRY(cudaGetLastError());
-  h->launches += 2;
+  h->launches += 1;
   return AICP_B200_OK;
 }
 

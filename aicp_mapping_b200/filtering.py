@@ -1,7 +1,10 @@
-"""Host-side mirror of the reference's map-handling filter that sits next to the registration path
-(aicp_core/src/utils/filteringUtils.cpp:621-637, called from App on the prior / built map before every registration,
-app.cpp:41-69): getPointsInOrientedBox = pcl::CropBox.  The crop itself runs on the GPU (csrc/crop.cu) through the C ABI;
-this module only prepares the arguments the way the reference does."""
+"""Host-side mirror of the reference's cloud filters that sit next to the registration path (aicp_utils/filteringUtils.hpp):
+  getPointsInOrientedBox = pcl::CropBox (filteringUtils.cpp:621-637; App crops the prior / built map with it before every
+    registration, app.cpp:41-69)                                                           -> csrc/crop.cu
+  regionGrowingUniformPlaneSegmentationFilter = VoxelGrid + NormalEstimation + RegionGrowing (filteringUtils.cpp:5-104;
+    App pre-filters every reading, the first cloud and periodically the map with it, app.cpp:102-110,295,486-493)
+                                                                                           -> csrc/prefilter.cu
+Everything runs on the GPU through the C ABI; this module only prepares the arguments the way the reference does."""
 import ctypes as C
 import math
 
@@ -106,6 +109,121 @@ class B200Map(B200CropBox):
         out = np.zeros((n.value, 4), dtype=np.float32)
         self._check(self._lib.aicp_b200_download_cropped(self._h, C.c_void_p(out.ctypes.data), n.value))
         return out
+
+
+    def prefilter(self, cfg=None):
+        """app.cpp:486-493: prior_map_ <- regionGrowingUniformPlaneSegmentationFilter(prior_map_), on the device.  Returns
+        the capi.PrefilterInfo of the run."""
+        info = capi.PrefilterInfo()
+        n_out = C.c_int64()
+        self._check(self._lib.aicp_b200_map_prefilter(self._h, C.byref(cfg) if cfg is not None else None, C.byref(n_out), C.byref(info)))
+        return info
+
+    def download(self):
+        """The whole map as an n x 4 float32 array (a crop with an all-enclosing box; non-finite points do not survive it)."""
+        if self.size() == 0:
+            return np.zeros((0, 4), np.float32)
+        z = np.zeros(3, dtype=np.float32)
+        n_out = C.c_int64()
+        self._check(self._lib.aicp_b200_map_crop(self._h, C.c_float(-1.0e30), C.c_float(1.0e30), z.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 z.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n_out)))
+        return self.cropToHost()
+
+
+class B200Prefilter:
+    """regionGrowingUniformPlaneSegmentationFilter on the GPU.  One instance owns one library handle (device buffers are
+    reused across calls, as App reuses its filter for every cloud)."""
+
+    def __init__(self, device=-1, cfg=None):
+        self._lib = capi.lib()
+        h = C.c_void_p()
+        rc = self._lib.aicp_b200_create(None, int(device), C.byref(h))
+        if rc:
+            raise capi.AicpError(rc, self._lib.aicp_b200_last_error(None).decode())
+        self._h = h
+        self.cfg = cfg or default_prefilter_config()
+        self.info = capi.PrefilterInfo()
+
+    def close(self):
+        if self._h:
+            self._lib.aicp_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise capi.AicpError(rc, self._lib.aicp_b200_last_error(self._h).decode())
+
+    def voxelGrid(self, cloud, leaf=None):
+        """pcl::VoxelGrid::filter (filteringUtils.cpp:10-13): n_voxels x 4 float32, ascending voxel index."""
+        p, n, keep = capi.ptr_and_count(cloud)
+        out = np.zeros((max(n, 1), 4), dtype=np.float32)
+        n_out = C.c_int64()
+        self._check(self._lib.aicp_b200_voxel_grid(self._h, p, n, C.c_float(self.cfg.leaf_size if leaf is None else leaf),
+                                                   C.c_void_p(out.ctypes.data), C.byref(n_out)))
+        return out[:n_out.value].copy()
+
+    def filter(self, cloud_in, view_point=None, keep_on_device=False):
+        """First overload (filteringUtils.cpp:5-45): returns cloud_out, the kept clusters concatenated (n_out x 4).
+        keep_on_device: returns a DeviceCloudView of the library-owned result instead (valid until the next call)."""
+        p, n, keep = capi.ptr_and_count(cloud_in)
+        vp = None
+        if view_point is not None:
+            vp = np.ascontiguousarray(view_point, dtype=np.float32)
+        out = None if keep_on_device else np.zeros((max(n, 1), 4), dtype=np.float32)
+        n_out = C.c_int64()
+        self._check(self._lib.aicp_b200_prefilter(self._h, p, n, C.byref(self.cfg), vp.ctypes.data_as(C.POINTER(C.c_float)) if vp is not None else None,
+                                                  C.c_void_p(out.ctypes.data) if out is not None else None, C.byref(n_out), C.byref(self.info)))
+        if keep_on_device:
+            return DeviceCloudView(self._lib.aicp_b200_get_prefiltered(self._h, None), int(n_out.value))
+        return out[:n_out.value].copy()
+
+    def segments(self):
+        """By-products of the last filter() call, as the second overload returns them (filteringUtils.cpp:51-104):
+        (cloud_sampled n x 4, normals n x 4 = (nx, ny, nz, curvature), labels n int32, clusters = list of index arrays)."""
+        n = int(self.info.n_sampled)
+        sampled = np.zeros((n, 4), dtype=np.float32)
+        normals = np.zeros((n, 4), dtype=np.float32)
+        labels = np.full(n, -1, dtype=np.int32)
+        if n:
+            self._check(self._lib.aicp_b200_prefilter_get_sampled(self._h, C.c_void_p(sampled.ctypes.data), n))
+            self._check(self._lib.aicp_b200_prefilter_get_labels(self._h, C.c_void_p(labels.ctypes.data), n))
+            if n > self.cfg.knn_normals:
+                self._check(self._lib.aicp_b200_prefilter_get_normals(self._h, C.c_void_p(normals.ctypes.data), n))
+        order = np.argsort(labels, kind="stable")
+        order = order[labels[order] >= 0]
+        bounds = np.flatnonzero(np.diff(labels[order])) + 1 if order.size else np.zeros(0, np.int64)
+        clusters = np.split(order, bounds) if order.size else []
+        return sampled, normals, labels, clusters
+
+
+def default_prefilter_config(**kw):
+    cfg = capi.PrefilterConfig()
+    capi.lib().aicp_b200_prefilter_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def regionGrowingUniformPlaneSegmentationFilter(cloud_in, view_point=None, prefilter=None):
+    """filteringUtils.cpp:5-45 (view_point None) / :51-104 (view_point given: returns (cloud_sampled_out with normals as an
+    n x 8 array (x, y, z, 1, nx, ny, nz, curvature), clusters))."""
+    own = prefilter is None
+    prefilter = prefilter or B200Prefilter()
+    try:
+        out = prefilter.filter(cloud_in, view_point)
+        if view_point is None:
+            return out
+        sampled, normals, labels, clusters = prefilter.segments()
+        return np.concatenate([sampled, normals], axis=1), clusters
+    finally:
+        if own:
+            prefilter.close()
 
 
 class DeviceCloudView:

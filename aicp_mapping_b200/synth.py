@@ -15,7 +15,7 @@ Configurations (BASELINE.json "configs"):
 import numpy as np
 
 __all__ = ["cube_cloud", "rigid", "apply_T", "lidar_scan", "street_scene", "room_scene", "make_pair",
-           "perturbation_T", "voxel_downsample", "campus_map"]
+           "perturbation_T", "voxel_downsample", "campus_map", "raw_sweep"]
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -267,6 +267,29 @@ def make_pair(config, trial=0, n_points=None):
     read = apply_T(E, read_true)
     return dict(ref=np.ascontiguousarray(ref, dtype=np.float32), read=read, ref_origin=np.asarray(ref_o, dtype=np.float64),
                 read_origin=(E[:3, :3] @ read_o + E[:3, 3]), T_true=np.linalg.inv(E), name=name)
+
+
+def raw_sweep(config, trial=0, n_sweeps=None):
+    """The UNFILTERED cloud that App hands to the pre-filter (regionGrowingUniformPlaneSegmentationFilter, app.cpp:102-110):
+    config 2 -- 7 accumulated VLP-16 sweeps in the room scene (aicp.launch:68), ~200 k points; config 3 -- one HDL-64 sweep
+    of the street scene with the ground, ~230 k points.  Returns dict(cloud n x 3 float32 world frame, origin float64[3])."""
+    rng = np.random.default_rng(1000 * config + trial + 500)
+    if config == 2:
+        boxes = room_scene(rng)
+        x0 = rng.uniform(-4.0, -2.0)
+        pts = []
+        ns = n_sweeps or 7
+        for s in range(ns):
+            pose = rigid(x0 + 0.35 * s, rng.uniform(-0.05, 0.05), 0.6, 0, 0, rng.uniform(-0.05, 0.05))
+            pts.append(lidar_scan(pose, boxes, VLP16_ELEV, 1800, rng, max_range=100.0, az_offset=rng.uniform(0, 0.01)))
+        return dict(cloud=np.concatenate(pts, 0).astype(np.float32), origin=np.array([x0 + 0.35 * (ns // 2), 0.0, 0.6]),
+                    name="raw VLP-16 accumulation, %d sweeps" % ns)
+    if config == 3:
+        boxes = street_scene(rng)
+        pose = rigid(rng.uniform(-10, -5), rng.uniform(-1, 1), 1.73, 0, 0, rng.uniform(-0.1, 0.1))
+        p = lidar_scan(pose, boxes, HDL64_ELEV, (n_sweeps or 1) * 4000, rng, max_range=120.0, az_offset=rng.uniform(0, 0.001))
+        return dict(cloud=p.astype(np.float32), origin=pose[:3, 3].copy(), name="raw HDL-64 sweep with ground")
+    raise ValueError("raw_sweep supports configs 2 and 3")
 
 
 def make_map_case(n_map=10485760, n_read=122880, trial=0, n_poses=1):

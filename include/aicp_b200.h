@@ -84,6 +84,27 @@ typedef struct {
   aicp_b200_iter_trace trace[AICP_B200_MAX_ITERS];
 } aicp_b200_stats;
 
+/* The pre-filter's PCL parameters as regionGrowingUniformPlaneSegmentationFilter hard-codes them
+ * (aicp_core/src/utils/filteringUtils.cpp:10-34). */
+typedef struct {
+  float   leaf_size;              /* pcl::VoxelGrid::setLeafSize                      (0.08f, :12) */
+  int32_t knn_normals;            /* pcl::NormalEstimation::setKSearch                (30, :22); 3..32 */
+  int32_t n_neighbours;           /* pcl::RegionGrowing::setNumberOfNeighbours        (15, :30); <= knn_normals */
+  int32_t min_cluster_size;       /* setMinClusterSize                                (50, :27) */
+  int32_t max_cluster_size;       /* setMaxClusterSize                                (1000000, :28) */
+  float   smoothness_threshold;   /* setSmoothnessThreshold, radians                  ((float)(3.0 / 180.0 * M_PI), :33) */
+  float   curvature_threshold;    /* setCurvatureThreshold                            (1.0, :34) */
+} aicp_b200_prefilter_config;
+
+typedef struct {
+  int64_t n_sampled;              /* points after the voxel grid */
+  int64_t n_clusters;             /* clusters kept (size within [min, max]) */
+  int64_t n_out;                  /* points in the output cloud */
+  int32_t passes;                 /* label-propagation passes enqueued by the region growing */
+  int32_t gpu_launches;
+  float   ms_total;               /* device time of the call (CUDA events) */
+} aicp_b200_prefilter_info;
+
 /* ---- lifetime --------------------------------------------------------------------------------------------------
  * replaces: aicp::create_registrator(params) / PointmatcherRegistration(params)
  *           aicp_core/include/aicp_registration/registration.hpp:9-19, pointmatcher_registration.cpp:7-9
@@ -191,6 +212,33 @@ int aicp_b200_map_append(aicp_b200_handle* h, const float* xyzw, int64_t n, int 
 int64_t aicp_b200_map_size(const aicp_b200_handle* h);
 int aicp_b200_map_crop(aicp_b200_handle* h, float box_min, float box_max, const float rotation_rpy[3], const float translation[3],
                        int64_t* n_out);
+
+/* ---- pre-filter ----------------------------------------------------------------------------
+ * replaces: regionGrowingUniformPlaneSegmentationFilter(cloud_in, cloud_out)   aicp_core/src/utils/filteringUtils.cpp:5-45
+ *           = pcl::VoxelGrid{0.08} -> pcl::NormalEstimation{k 30} -> pcl::RegionGrowing{50, 1e6, 15, 3 deg, 1.0} -> the kept
+ *           clusters concatenated in cluster order; App runs it on every reading (App::filterCloud, app.cpp:102-110), on the
+ *           first cloud (app.cpp:295) and on the merged map every 30 clouds (app.cpp:486-493);
+ *           and regionGrowingUniformPlaneSegmentationFilter(cloud_in, cloud_sampled_out, view_point, clusters)  :51-104,
+ *           the variant used by the alignability filter (normals flipped towards view_point, clusters returned).
+ * cfg: NULL for the reference's hard-coded parameters.  viewpoint: NULL for (0,0,0) (the first overload never sets one).
+ * out_xyzw: host or device buffer of capacity n records, or NULL to keep the result on the device only
+ * (aicp_b200_get_prefiltered returns its address, valid until the next pre-filter call on this handle, and can be passed
+ * to aicp_b200_register / aicp_b200_overlap as a device cloud).  After the call the by-products of the second overload can
+ * be fetched: the sampled cloud (voxel-grid output), its normals (nx, ny, nz, curvature) and the cluster ordinal of every
+ * sampled point (-1: not in a kept cluster; clusters[c].indices = ascending { i : label[i] == c }). */
+int aicp_b200_prefilter_default_config(aicp_b200_prefilter_config* cfg);
+int aicp_b200_prefilter(aicp_b200_handle* h, const float* xyzw, int64_t n, const aicp_b200_prefilter_config* cfg,
+                        const float viewpoint[3], float* out_xyzw, int64_t* n_out, aicp_b200_prefilter_info* info);
+const float* aicp_b200_get_prefiltered(aicp_b200_handle* h, int64_t* n_out);
+int aicp_b200_prefilter_get_sampled(aicp_b200_handle* h, float* xyzw, int64_t n_sampled);
+int aicp_b200_prefilter_get_normals(aicp_b200_handle* h, float* normals_xyzc, int64_t n_sampled);
+int aicp_b200_prefilter_get_labels(aicp_b200_handle* h, int32_t* labels, int64_t n_sampled);
+/* pcl::VoxelGrid alone (filteringUtils.cpp:10-13): one centroid per occupied voxel, ascending voxel index; non-finite points
+ * are skipped; when leaf is too small for the cloud's extent (more than INT32_MAX voxels) the input is returned unchanged,
+ * as PCL does.  out_xyzw: capacity n records, host or device. */
+int aicp_b200_voxel_grid(aicp_b200_handle* h, const float* xyzw, int64_t n, float leaf_size, float* out_xyzw, int64_t* n_out);
+/* the periodic re-filter of the merged map (app.cpp:486-493): map <- prefilter(map), all on the device */
+int aicp_b200_map_prefilter(aicp_b200_handle* h, const aicp_b200_prefilter_config* cfg, int64_t* n_out, aicp_b200_prefilter_info* info);
 
 /* ---- auto-tune glue --------------------------------------------------------------------------------------------
  * replaces (for callers that do not go through a file): App::computeRegistration's clamp, app.cpp:198-202, followed by

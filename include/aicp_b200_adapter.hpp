@@ -245,6 +245,55 @@ inline bool getPointsInOrientedBoxB200(aicp_b200_handle* h, pcl::PointCloud<pcl:
 }
 #endif
 
+// ---- pre-filter: stands where regionGrowingUniformPlaneSegmentationFilter stands (filteringUtils.cpp:5-45) -----------------
+// Same signature as the reference's free function plus the handle.  Like the reference, the kept clusters are APPENDED to
+// *cloud_out ("*cloud_out = *cloud_out + cloud_cluster", :43).  On failure cloud_out is left untouched and false is returned
+// (the reference has no failure path here).
+inline bool regionGrowingUniformPlaneSegmentationFilterB200(aicp_b200_handle* h, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in,
+                                                            pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_out) {
+  const int64_t n = (int64_t)cloud_in->points.size();
+  std::vector<float> out(4 * (size_t)(n > 0 ? n : 1));
+  int64_t kept = 0;
+  const int rc = aicp_b200_prefilter(h, reinterpret_cast<const float*>(cloud_in->points.data()), n, nullptr, nullptr, out.data(), &kept, nullptr);
+  if (rc != AICP_B200_OK) {
+    std::cerr << "[B200] regionGrowingUniformPlaneSegmentationFilter failed (" << rc << "): " << aicp_b200_last_error(h) << std::endl;
+    return false;
+  }
+  const size_t old = cloud_out->points.size();
+  cloud_out->points.resize(old + (size_t)kept);
+  if (kept > 0) std::memcpy(reinterpret_cast<float*>(cloud_out->points.data()) + 4 * old, out.data(), sizeof(float) * 4 * (size_t)kept);
+  cloud_out->width = (uint32_t)cloud_out->points.size();
+  cloud_out->height = 1;
+  return true;
+}
+
+// Second overload (filteringUtils.cpp:51-104) without the PCL point types it returns: the sampled cloud, its normals
+// (nx, ny, nz, curvature) flipped towards view_point, and the clusters as index lists into the sampled cloud.
+inline bool regionGrowingUniformPlaneSegmentationFilterB200(aicp_b200_handle* h, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_in,
+                                                            const float view_point[3], std::vector<float>& sampled_xyzw,
+                                                            std::vector<float>& normals_xyzc, std::vector<std::vector<int> >& clusters) {
+  const int64_t n = (int64_t)cloud_in->points.size();
+  int64_t kept = 0;
+  aicp_b200_prefilter_info info;
+  int rc = aicp_b200_prefilter(h, reinterpret_cast<const float*>(cloud_in->points.data()), n, nullptr, view_point, nullptr, &kept, &info);
+  std::vector<int32_t> labels((size_t)info.n_sampled);
+  sampled_xyzw.assign(4 * (size_t)info.n_sampled, 0.f);
+  normals_xyzc.assign(4 * (size_t)info.n_sampled, 0.f);
+  clusters.assign((size_t)info.n_clusters, std::vector<int>());
+  if (rc == AICP_B200_OK && info.n_sampled > 0) {
+    rc = aicp_b200_prefilter_get_sampled(h, sampled_xyzw.data(), info.n_sampled);
+    if (rc == AICP_B200_OK) rc = aicp_b200_prefilter_get_labels(h, labels.data(), info.n_sampled);
+    if (rc == AICP_B200_OK && info.n_clusters > 0) rc = aicp_b200_prefilter_get_normals(h, normals_xyzc.data(), info.n_sampled);
+  }
+  if (rc != AICP_B200_OK) {
+    std::cerr << "[B200] regionGrowingUniformPlaneSegmentationFilter failed (" << rc << "): " << aicp_b200_last_error(h) << std::endl;
+    return false;
+  }
+  for (int64_t i = 0; i < info.n_sampled; ++i)
+    if (labels[(size_t)i] >= 0) clusters[(size_t)labels[(size_t)i]].push_back((int)i);
+  return true;
+}
+
 }  // namespace aicp
 
 #endif

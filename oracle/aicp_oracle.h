@@ -130,6 +130,26 @@ void orc_rpy_to_matrix(const float* rpy, float* R_rowmajor9);
 /* returns the number of points kept; out (nullable) receives them in input order, capacity n x 4 floats */
 int64_t orc_crop_box(const float* xyzw, int64_t n, float bmin, float bmax, const float* rpy, const float* translation, float* out);
 
+/* ---- pre-filter: regionGrowingUniformPlaneSegmentationFilter (filteringUtils.cpp:5-104), see aicp_oracle_prefilter.c ---- */
+typedef struct {
+  float   leaf_size;              /* VoxelGrid leaf (0.08f) */
+  int32_t knn_normals;            /* NormalEstimation.setKSearch (30) */
+  int32_t n_neighbours;           /* RegionGrowing.setNumberOfNeighbours (15) */
+  int32_t min_cluster_size;       /* 50 */
+  int32_t max_cluster_size;       /* 1000000 */
+  float   smoothness_threshold;   /* radians, (float)(3/180*pi) */
+  float   curvature_threshold;    /* 1.0 */
+} orc_prefilter_config;
+void orc_prefilter_default_config(orc_prefilter_config* cfg);
+/* pcl::VoxelGrid: returns the number of voxels (or the input size in the "leaf too small" case), or -(error code) */
+int64_t orc_voxel_grid(const float* xyzw, int64_t n, float leaf, float* out);
+void orc_pcl_point_normal(const float* pts, const int32_t* nb, int32_t k, const float* query, const float* viewpoint, float* out4);
+int64_t orc_region_growing(const float* normals, const int32_t* knn, int64_t m, int32_t k_stride, int32_t n_nb,
+                           int32_t min_size, int32_t max_size, float cos_thr, float curv_thr, int32_t* labels);
+/* counts = {n_sampled, n_clusters, n_out}; viewpoint nullable (origin) */
+int orc_prefilter(const float* xyzw, int64_t n, const orc_prefilter_config* cfg, const float* viewpoint, int threads,
+                  float* sampled, float* normals, int32_t* labels, float* out, int64_t* counts);
+
 /* ---- text glue KATs ---- */
 /* app.cpp:198-202 clamp + fileIO.cpp:194-198 "%g"-style 6-digit print + float re-parse */
 float orc_autotune_ratio(float overlap_pct, char* text_out /* >=32 bytes, nullable */);

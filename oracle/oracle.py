@@ -36,7 +36,7 @@ class IcpResult(C.Structure):
 
 def build(force=False):
     """Compile the oracle with oracle/Makefile (gcc)."""
-    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle_filters.c", "aicp_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle_filters.c", "aicp_oracle_prefilter.c", "aicp_oracle.h", "Makefile")]
     if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return _LIB_PATH
     subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
@@ -247,3 +247,75 @@ def crop_box(cloud, bmin, bmax, rpy, translation):
     t = np.ascontiguousarray(translation, dtype=np.float32)
     m = lib().orc_crop_box(_ptr(pts), C.c_int64(pts.shape[0]), C.c_float(bmin), C.c_float(bmax), _ptr(r), _ptr(t), _ptr(out))
     return out[:m].copy()
+
+
+# ---- pre-filter (aicp_oracle_prefilter.c): regionGrowingUniformPlaneSegmentationFilter, filteringUtils.cpp:5-104 ----
+class PrefilterConfig(C.Structure):
+    _fields_ = [("leaf_size", C.c_float), ("knn_normals", C.c_int32), ("n_neighbours", C.c_int32),
+                ("min_cluster_size", C.c_int32), ("max_cluster_size", C.c_int32), ("smoothness_threshold", C.c_float),
+                ("curvature_threshold", C.c_float)]
+
+
+def prefilter_default_config(**kw):
+    cfg = PrefilterConfig()
+    lib().orc_prefilter_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def voxel_grid(cloud, leaf=np.float32(0.08)):
+    """pcl::VoxelGrid centroids in ascending voxel-index order (filteringUtils.cpp:10-13)."""
+    pts = to_xyzw(cloud)
+    out = np.zeros_like(pts)
+    L = lib()
+    L.orc_voxel_grid.restype = C.c_int64
+    m = L.orc_voxel_grid(_ptr(pts), C.c_int64(pts.shape[0]), C.c_float(leaf), _ptr(out))
+    if m < 0:
+        raise RuntimeError("oracle voxel_grid failed: %s" % ERR_NAMES.get(-m, -m))
+    return out[:m].copy()
+
+
+def region_growing(normals, knn, n_nb=15, min_size=50, max_size=1000000, cos_thr=None, curv_thr=1.0):
+    """Sequential pcl::RegionGrowing over given normals (m x 4: nx, ny, nz, curvature) and neighbour lists (m x k)."""
+    normals = _f32(normals)
+    knn = np.ascontiguousarray(knn, dtype=np.int32)
+    m, k = knn.shape
+    if cos_thr is None:
+        cos_thr = np.cos(np.float32(3.0 / 180.0 * np.pi), dtype=np.float32)
+    labels = np.zeros(m, dtype=np.int32)
+    L = lib()
+    L.orc_region_growing.restype = C.c_int64
+    nc = L.orc_region_growing(_ptr(normals), _ptr(knn, C.c_int32), C.c_int64(m), C.c_int32(k), C.c_int32(n_nb),
+                              C.c_int32(min_size), C.c_int32(max_size), C.c_float(cos_thr), C.c_float(curv_thr),
+                              _ptr(labels, C.c_int32))
+    return labels, int(nc)
+
+
+class PrefilterOutput:
+    pass
+
+
+def prefilter(cloud, cfg=None, viewpoint=None, threads=1):
+    """The whole pre-filter.  Returns PrefilterOutput: cloud (n_out x 4), sampled, normals (nx, ny, nz, curvature), labels,
+    n_clusters, rc."""
+    pts = to_xyzw(cloud)
+    n = pts.shape[0]
+    cfg = cfg or prefilter_default_config()
+    vp = np.ascontiguousarray(viewpoint, dtype=np.float32) if viewpoint is not None else None
+    sampled = np.zeros((max(n, 1), 4), dtype=np.float32)
+    normals = np.zeros((max(n, 1), 4), dtype=np.float32)
+    labels = np.zeros(max(n, 1), dtype=np.int32)
+    out = np.zeros((max(n, 1), 4), dtype=np.float32)
+    counts = np.zeros(3, dtype=np.int64)
+    rc = lib().orc_prefilter(_ptr(pts), C.c_int64(n), C.byref(cfg), _ptr(vp), int(threads), _ptr(sampled), _ptr(normals),
+                             _ptr(labels, C.c_int32), _ptr(out), _ptr(counts, C.c_int64))
+    o = PrefilterOutput()
+    o.rc = rc
+    o.error = ERR_NAMES.get(rc, str(rc))
+    o.sampled = sampled[:counts[0]].copy()
+    o.normals = normals[:counts[0]].copy()
+    o.labels = labels[:counts[0]].copy()
+    o.n_clusters = int(counts[1])
+    o.cloud = out[:counts[2]].copy()
+    return o

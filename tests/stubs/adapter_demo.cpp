@@ -65,6 +65,16 @@ int main(int argc, char** argv) {
   pcl::PointCloud<pcl::PointXYZ> out;
   registr->getOutputReading(out);
   if (out.points.size() != read.points.size()) return 4;
+  // the pre-filter as App::filterCloud calls it (app.cpp:102-110): free function + the library handle
+  {
+    aicp_b200_handle* fh = nullptr;
+    if (aicp_b200_create(nullptr, -1, &fh) != AICP_B200_OK) return 6;
+    pcl::PointCloud<pcl::PointXYZ>::Ptr in(new pcl::PointCloud<pcl::PointXYZ>(ref)), filtered(new pcl::PointCloud<pcl::PointXYZ>);
+    const bool ok = aicp::regionGrowingUniformPlaneSegmentationFilterB200(fh, in, filtered);
+    aicp_b200_destroy(fh);
+    if (!ok || filtered->points.empty() || filtered->points.size() > in->points.size()) return 7;
+    std::printf("prefilter %zu -> %zu points\n", in->points.size(), filtered->points.size());
+  }
   auto* b = static_cast<aicp::B200Registration*>(registr.get());
   std::printf("OK overlap=%.4f iterations=%d T=", overlap, b->getStats().iterations);
   for (int i = 0; i < 16; ++i) std::printf("%.9g ", T.data()[i]);

@@ -37,6 +37,7 @@ struct alignas(16) PointXYZRGB { float x, y, z, pad; float rgb; float pad2[3]; }
 struct alignas(16) PointXYZRGBNormal { float x, y, z, pad; float normal_x, normal_y, normal_z, pad1; float rgb, curvature, pad2[2]; };
 template <typename PointT>
 struct PointCloud {
+  typedef std::shared_ptr<PointCloud<PointT> > Ptr;      // boost::shared_ptr in PCL 1.8; only -> and * are used
   std::vector<PointT> points;
   uint32_t width = 0, height = 0;
   size_t size() const { return points.size(); }

@@ -8,6 +8,9 @@
       (reported), then registrations/s and ms per registration with the map resident
   C5  validation sweep: 4096 registrations of 38 400-point cube pairs (16 distinct perturbations cycled), batched
   overlap  the octree-overlap parameter of the C3 pair (ms per call, voxel counts)
+  prefilter  regionGrowingUniformPlaneSegmentationFilter (VoxelGrid 0.08 + k-30 normals + region growing) on the raw clouds
+      App feeds it: 7 accumulated VLP-16 sweeps (~200 k points) and one HDL-64 sweep (~250 k points); ms per call, the
+      voxel-grid stage alone against the HBM roofline, and the CPU oracle on the host cores beside it
 All inputs are device-resident when timing starts unless the line says e2e.  Single GPU; see bench.py for multi-GPU.
 """
 import argparse
@@ -24,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="2,4,4crop,5,5step,overlap")
+    ap.add_argument("--configs", default="2,4,4crop,5,5step,overlap,prefilter")
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--map-points", type=int, default=10485760)
     args = ap.parse_args()
@@ -93,6 +96,48 @@ def main():
         print(json.dumps({"config": "overlap of the C3 pair (131072 + 131072 rays, 0.2 m voxels)", "metric": "ms per computeOverlap",
                           "value": ms, "unit": "ms", "overlap_pct": float(ovl.getOverlap()), "voxel_counts_AandB_A_B": [int(c) for c in counts],
                           "inputs": "device-resident, host synchronised per call"}), flush=True)
+    if "prefilter" in want:
+        from oracle import oracle as orc          # CPU baseline leg only
+        ncpu = os.cpu_count() or 1
+        pf = ab.B200Prefilter(device=0)
+        for cfgid in (2, 3):
+            raw = synth.raw_sweep(cfgid, 0)
+            cloud = capi.to_xyzw(raw["cloud"])
+            d = torch.from_numpy(cloud).cuda()
+            for _ in range(3):
+                pf.filter(d, keep_on_device=True)
+            torch.cuda.synchronize()
+            reps = 20
+            dev_ms, t0 = 0.0, time.perf_counter()
+            for _ in range(reps):
+                pf.filter(d, keep_on_device=True)
+                dev_ms += pf.info.ms_total
+            wall_dev = (time.perf_counter() - t0) / reps * 1e3
+            info = pf.info
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = pf.filter(cloud)
+            wall_host = (time.perf_counter() - t0) / reps * 1e3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                vg = pf.voxelGrid(d)
+            vg_ms = (time.perf_counter() - t0) / reps * 1e3
+            t0 = time.perf_counter()
+            o = orc.prefilter(cloud, threads=ncpu)
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            same = bool(np.array_equal(out.view(np.uint32), o.cloud.view(np.uint32)))
+            n = cloud.shape[0]
+            vg_bytes = 16.0 * n + 8.0 * n + 16.0 * vg.shape[0]
+            print(json.dumps({"config": "pre-filter (VoxelGrid 0.08 + k-30 normals + region growing) of a %s, %d points" % (raw["name"], n),
+                              "metric": "ms per regionGrowingUniformPlaneSegmentationFilter", "value": dev_ms / reps, "unit": "ms",
+                              "wall_ms_device_input": wall_dev, "wall_ms_host_input_and_output": wall_host,
+                              "n_sampled": int(info.n_sampled), "n_clusters": int(info.n_clusters), "n_out": int(info.n_out),
+                              "region_growing_passes": int(info.passes), "gpu_launches": int(info.gpu_launches),
+                              "voxel_grid_alone": {"wall_ms_incl_download": vg_ms, "algorithmic_bytes": vg_bytes,
+                                                   "note": "16 B/point read + 8 B/point key and index + 16 B/voxel written"},
+                              "cpu_oracle_ms": cpu_ms, "cpu_cores": ncpu, "bit_identical_to_oracle": same,
+                              "clouds_per_s": 1e3 / (dev_ms / reps)}), flush=True)
+        pf.close()
     if "4" in want:
         t0 = time.perf_counter()
         case = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=8)
