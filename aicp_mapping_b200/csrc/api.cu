@@ -138,6 +138,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->pf_keys.release(); h->pf_keys_alt.release(); h->pf_vals.release(); h->pf_vals_alt.release(); h->pf_sort_tmp.release();
   h->pf_flag.release(); h->pf_slot.release(); h->pf_tiles.release(); h->pf_mask.release(); h->pf_count.release();
   h->pf_label.release(); h->pf_seed_pos.release(); h->pf_labels_out.release();
+  h->pf_mutual.release(); h->pf_parent.release(); h->pf_root.release(); h->pf_clabel.release();
   if (h->pf_meta) cudaFree(h->pf_meta);
   if (h->pf_meta_host) cudaFreeHost(h->pf_meta_host);
   for (int i = 0; i < 2; ++i) if (h->pf_ev[i]) cudaEventDestroy(h->pf_ev[i]);

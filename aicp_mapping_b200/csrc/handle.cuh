@@ -116,8 +116,8 @@ struct Handle {
   DevBuf<float4> pf_sampled;                // voxel centroids, ascending voxel index ("sampled order")
   DevBuf<float4> pf_normals, pf_normals_orig;   // (nx, ny, nz, curvature): Morton order / sampled order
   DevBuf<float4> pf_out;                    // kept clusters, concatenated
-  DevBuf<unsigned int> pf_keys, pf_keys_alt, pf_vals, pf_vals_alt, pf_sort_tmp, pf_flag, pf_slot, pf_tiles, pf_mask, pf_count;
-  DevBuf<int> pf_label, pf_seed_pos, pf_labels_out;
+  DevBuf<unsigned int> pf_keys, pf_keys_alt, pf_vals, pf_vals_alt, pf_sort_tmp, pf_flag, pf_slot, pf_tiles, pf_mask, pf_mutual, pf_count;
+  DevBuf<int> pf_label, pf_seed_pos, pf_labels_out, pf_parent, pf_root, pf_clabel;
   void* pf_meta = nullptr;                  // PfMeta, device
   void* pf_meta_host = nullptr;             // pinned
   int64_t pf_n_sampled = 0, pf_n_out = 0, pf_n_clusters = 0;

@@ -21,10 +21,14 @@
 //   u* -- it would reach v -- so u* is unlabelled when its turn comes and becomes a seed; no vertex on the path u* -> v was
 //   taken earlier, for the same reason; so v joins u*'s region.)  That is a min-label fixed point, computed data-parallel:
 //   k_pf_curv_keys + radix sort   rank of every point in (curvature, index) order
-//   k_pf_edges     15-bit mask of the neighbours that pass the smoothness test
-//   k_pf_propagate label[w] = min(label[w], label[u]) along every edge (atomicMin), plus the shortcut label[v] <-
-//                  label[seed(label[v])] (the seed's own ancestors are v's ancestors); block-local repeats; passes are
-//                  enqueued in batches until one makes no change
+//   k_pf_edges     15-bit mask of the neighbours that pass the smoothness test, and which of those edges are two-way
+//   k_pf_cc_*      points joined by two-way edges reach each other, so they share their ancestors and their final label:
+//                  components of the two-way graph by lock-free union-find (atomicCAS hooking, path halving) in ONE pass over
+//                  the edges -- a wall or the ground collapses into one component without any wave crossing it
+//   k_pf_propagate min-label propagation between components along the remaining one-way edges (atomicMin), plus the shortcut
+//                  label[c] <- label[component of seed(label[c])] (the seed's ancestors are c's ancestors); passes are enqueued
+//                  in batches until one makes no change (first version without the components: 72 passes, 1.9 ms on an
+//                  HDL-64 sweep)
 //   k_pf_count / k_pf_seed_flags / scan / k_pf_final / radix sort / k_pf_gather   cluster sizes, the [min, max] size filter,
 //                  cluster ordinals in seed order, output = clusters in seed order, ascending point index inside
 //   The curvature threshold only matters for points whose curvature exceeds it (they join a region but are not expanded);
@@ -42,7 +46,6 @@ namespace aicp {
 #define PF_FIXED 1048576.0          // 2^20: centroid fixed point (oracle contract)
 #define PF_MAX_PASSES 4096
 #define PF_BATCH 8
-#define PF_INNER 4
 #define SC_ITEMS 4
 #define SC_TILE (256 * SC_ITEMS)
 
@@ -317,48 +320,152 @@ __global__ void __launch_bounds__(256) k_pf_rank_init(const unsigned int* __rest
   seed_pos[r] = pos;
 }
 
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// mask: neighbours (of the first n_nb) that pass the smoothness test = out-edges of the directed graph;
+// mutual: those whose own list contains this point too -- the test is symmetric, so these are two-way edges
 __global__ void __launch_bounds__(256) k_pf_edges(const float4* __restrict__ normals_morton, const int* __restrict__ knn_pos, int k, int n_nb,
-                                                  int n, float cos_thr, unsigned int* __restrict__ mask) {
+                                                  int n, float cos_thr, unsigned int* __restrict__ mask, unsigned int* __restrict__ mutual) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= n) return;
   const float4 nc = __ldg(&normals_morton[pos]);
   const int* nb = knn_pos + (size_t)pos * k;
-  unsigned int mk = 0;
+  unsigned int mk = 0, mu = 0;
   for (int j = 0; j < n_nb; ++j) {
-    const float4 nn = __ldg(&normals_morton[__ldg(&nb[j])]);
+    const int w = __ldg(&nb[j]);
+    const float4 nn = __ldg(&normals_morton[w]);
     const float dot = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(nn.x, nc.x), __fmul_rn(nn.y, nc.y)), __fmul_rn(nn.z, nc.z)));
-    if (!(dot < cos_thr)) mk |= 1u << j;
+    if (dot < cos_thr) continue;
+    mk |= 1u << j;
+    if (w == pos) continue;
+    const int* nw = knn_pos + (size_t)w * k;
+    bool back = false;
+    for (int i = 0; i < n_nb; ++i) back |= __ldg(&nw[i]) == pos;
+    if (back) mu |= 1u << j;
   }
   mask[pos] = mk;
+  mutual[pos] = mu;
 }
 
-__global__ void __launch_bounds__(256) k_pf_propagate(int* label, const unsigned int* __restrict__ mask, const int* __restrict__ knn_pos,
-                                                      const int* __restrict__ seed_pos, int k, int n, unsigned int* changed, int pass) {
+// ---- strongly connected shortcut: points joined by two-way edges reach each other, hence have the same ancestors and the
+// same final label.  Components of the two-way graph by lock-free union-find (hook the larger root index under the smaller
+// with atomicCAS, path halving in find) -- one pass over the edges, no iteration.
+// Loads here are plain (L1-cacheable): a stale value is the vertex itself or an older ancestor, which only costs a failed
+// CAS or a longer walk; the flatten kernel runs after a kernel boundary and sees the final forest.
+__device__ __forceinline__ int cc_find(int* parent, int v) {
+  int curr = parent[v];
+  if (curr != v) {
+    int prev = v, next;
+    while (curr > (next = parent[curr])) {
+      parent[prev] = next;              // path halving; benign race: always an ancestor
+      prev = curr;
+      curr = next;
+    }
+  }
+  return curr;
+}
+
+// parent[v] = the smallest two-way neighbour below v (most points are hooked before the union pass starts), else v
+__global__ void __launch_bounds__(256) k_pf_cc_init(int* __restrict__ parent, int* __restrict__ crank, const unsigned int* __restrict__ mutual,
+                                                    const int* __restrict__ knn_pos, int k, int n) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  unsigned int mu = __ldg(&mutual[v]);
+  const int* nb = knn_pos + (size_t)v * k;
+  int p = v;
+  while (mu) {
+    const int j = __ffs(mu) - 1;
+    mu &= mu - 1u;
+    p = min(p, __ldg(&nb[j]));
+  }
+  parent[v] = p;
+  crank[v] = 0x7FFFFFFF;
+}
+
+__global__ void __launch_bounds__(256) k_pf_cc_union(int* parent, const unsigned int* __restrict__ mutual, const int* __restrict__ knn_pos,
+                                                     int k, int n) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  unsigned int mu = __ldg(&mutual[v]);
+  const int* nb = knn_pos + (size_t)v * k;
+  int a = cc_find(parent, v);
+  while (mu) {
+    const int j = __ffs(mu) - 1;
+    mu &= mu - 1u;
+    const int w = __ldg(&nb[j]);
+    if (w > v) continue;                // every two-way edge is seen from both ends: union from the larger one
+    int b = cc_find(parent, w);
+    bool repeat;
+    do {
+      repeat = false;
+      if (a != b) {
+        int ret;
+        if (a < b) { if ((ret = atomicCAS(&parent[b], b, a)) != b) { b = ret; repeat = true; } }
+        else       { if ((ret = atomicCAS(&parent[a], a, b)) != a) { a = ret; repeat = true; } }
+      }
+    } while (repeat);
+  }
+}
+
+// root[v] and the component's lowest rank (crank[root])
+__global__ void __launch_bounds__(256) k_pf_cc_flatten(int* parent, const int* __restrict__ rank_of, int* __restrict__ root, int* crank, int n) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int r = cc_find(parent, v);
+  root[v] = r;
+  atomicMin(&crank[r], __ldg(&rank_of[v]));
+}
+
+// out-edges that leave the component; the components' labels start at their lowest rank (crank, in place)
+__global__ void __launch_bounds__(256) k_pf_cross(const int* __restrict__ root, const unsigned int* __restrict__ mask, const int* __restrict__ knn_pos,
+                                                  int k, int n, unsigned int* __restrict__ cross) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int rv = __ldg(&root[v]);
+  unsigned int mk = __ldg(&mask[v]), cr = 0;
+  const int* nb = knn_pos + (size_t)v * k;
+  while (mk) {
+    const int j = __ffs(mk) - 1;
+    mk &= mk - 1u;
+    if (__ldg(&root[__ldg(&nb[j])]) != rv) cr |= 1u << j;
+  }
+  cross[v] = cr;
+}
+
+// min-label propagation over the condensed graph: clabel[root] = lowest rank that reaches the component.  A pass pushes
+// every component's label along its leaving edges and applies the shortcut clabel[c] <- clabel[component of seed(clabel[c])].
+__global__ void __launch_bounds__(256) k_pf_propagate(int* clabel, const int* __restrict__ root, const unsigned int* __restrict__ cross,
+                                                      const int* __restrict__ knn_pos, const int* __restrict__ seed_pos, int k, int n,
+                                                      unsigned int* changed, int pass) {
   if (pass > 0 && changed[pass - 1] == 0u) return;          // the previous pass changed nothing: fixed point reached
-  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = pos < n;
-  const unsigned int mk = active ? __ldg(&mask[pos]) : 0u;
-  const int* nb = knn_pos + (size_t)(active ? pos : 0) * k;
-  volatile int* vl = label;
-  bool block_changed = false;
-  for (int rep = 0; rep < PF_INNER; ++rep) {
-    bool any = false;
-    if (active) {
-      int l = vl[pos];
-      const int ls = vl[__ldg(&seed_pos[l])];               // the seed's ancestors are this point's ancestors
-      if (ls < l) { atomicMin(&label[pos], ls); l = ls; any = true; }
-      unsigned int mm = mk;
-      while (mm) {
-        const int j = __ffs(mm) - 1;
-        mm &= mm - 1u;
-        const int w = __ldg(&nb[j]);
-        if (vl[w] > l) { atomicMin(&label[w], l); any = true; }
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  bool any = false;
+  if (v < n) {
+    const int rv = __ldg(&root[v]);
+    unsigned int cr = __ldg(&cross[v]);
+    if (cr || rv == v) {
+      int l = ld_relaxed(&clabel[rv]);
+      const int ls = ld_relaxed(&clabel[__ldg(&root[__ldg(&seed_pos[l])])]);   // the seed's ancestors are this component's ancestors
+      if (ls < l) { atomicMin(&clabel[rv], ls); l = ls; any = true; }
+      const int* nb = knn_pos + (size_t)v * k;
+      while (cr) {
+        const int j = __ffs(cr) - 1;
+        cr &= cr - 1u;
+        const int rw = __ldg(&root[__ldg(&nb[j])]);
+        if (ld_relaxed(&clabel[rw]) > l) { atomicMin(&clabel[rw], l); any = true; }
       }
     }
-    if (!__syncthreads_or(any ? 1 : 0)) break;
-    block_changed = true;
   }
-  if (block_changed && threadIdx.x == 0) atomicOr(&changed[pass], 1u);
+  if (__syncthreads_or(any ? 1 : 0) && threadIdx.x == 0) atomicOr(&changed[pass], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_pf_labels(const int* __restrict__ clabel, const int* __restrict__ root, int n, int* __restrict__ label) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) label[v] = __ldg(&clabel[__ldg(&root[v])]);
 }
 
 // region sizes; lanes of a warp that share a label (Morton neighbours usually do) add once
@@ -499,7 +606,8 @@ int run_prefilter(Handle* h, const float4* pts, int64_t n, const aicp_b200_prefi
   if ((rc = run_knn(h, h->pf_ix, cfg->knn_normals, nullptr))) return rc;
   CUDA_TRY(h->pf_normals.reserve((size_t)m)); CUDA_TRY(h->pf_normals_orig.reserve((size_t)m));
   CUDA_TRY(h->pf_label.reserve((size_t)m)); CUDA_TRY(h->pf_seed_pos.reserve((size_t)m));
-  CUDA_TRY(h->pf_mask.reserve((size_t)m)); CUDA_TRY(h->pf_count.reserve((size_t)m));
+  CUDA_TRY(h->pf_mask.reserve((size_t)m)); CUDA_TRY(h->pf_count.reserve((size_t)m)); CUDA_TRY(h->pf_mutual.reserve((size_t)m));
+  CUDA_TRY(h->pf_parent.reserve((size_t)m)); CUDA_TRY(h->pf_root.reserve((size_t)m)); CUDA_TRY(h->pf_clabel.reserve((size_t)m));
   CUDA_TRY(h->pf_labels_out.reserve((size_t)m)); CUDA_TRY(h->pf_out.reserve((size_t)m));
   const int blocks = (m + 255) / 256;
   const float vp[3] = {viewpoint ? viewpoint[0] : 0.f, viewpoint ? viewpoint[1] : 0.f, viewpoint ? viewpoint[2] : 0.f};
@@ -511,14 +619,22 @@ int run_prefilter(Handle* h, const float4* pts, int64_t n, const aicp_b200_prefi
   if ((rc = radix_sort_pairs(h, h->pf_keys.p, h->pf_vals.p, h->pf_keys_alt.p, h->pf_vals_alt.p, m, h->pf_sort_tmp))) return rc;
   k_pf_rank_init<<<blocks, 256, 0, s>>>(h->pf_vals.p, m, h->pf_label.p, h->pf_seed_pos.p);
   const float cos_thr = cosf(cfg->smoothness_threshold);      // host libm, as RegionGrowing::validatePoint and the oracle
-  k_pf_edges<<<blocks, 256, 0, s>>>(h->pf_normals.p, h->knn_pos.p, k, cfg->n_neighbours, m, cos_thr, h->pf_mask.p);
-  h->launches += 2;
+  k_pf_edges<<<blocks, 256, 0, s>>>(h->pf_normals.p, h->knn_pos.p, k, cfg->n_neighbours, m, cos_thr, h->pf_mask.p, h->pf_mutual.p);
+  // label currently holds every point's rank; components of the two-way graph, then propagation between components
+  int* parent = h->pf_parent.p;
+  int* root = h->pf_root.p;
+  int* clabel = h->pf_clabel.p;
+  k_pf_cc_init<<<blocks, 256, 0, s>>>(parent, clabel, h->pf_mutual.p, h->knn_pos.p, k, m);
+  k_pf_cc_union<<<blocks, 256, 0, s>>>(parent, h->pf_mutual.p, h->knn_pos.p, k, m);
+  k_pf_cc_flatten<<<blocks, 256, 0, s>>>(parent, h->pf_label.p, root, clabel, m);
+  k_pf_cross<<<blocks, 256, 0, s>>>(root, h->pf_mask.p, h->knn_pos.p, k, m, h->pf_mutual.p);     // pf_mutual now: leaving edges
+  h->launches += 6;
   CUDA_TRY(cudaGetLastError());
   int passes = 0;
   bool converged = false;
   while (passes < PF_MAX_PASSES && !converged) {
     for (int b = 0; b < PF_BATCH; ++b, ++passes)
-      k_pf_propagate<<<blocks, 256, 0, s>>>(h->pf_label.p, h->pf_mask.p, h->knn_pos.p, h->pf_seed_pos.p, k, m, md->changed, passes);
+      k_pf_propagate<<<blocks, 256, 0, s>>>(clabel, root, h->pf_mutual.p, h->knn_pos.p, h->pf_seed_pos.p, k, m, md->changed, passes);
     h->launches += PF_BATCH;
     CUDA_TRY(cudaGetLastError());
     unsigned int* last = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(mh) + 192);
@@ -528,6 +644,8 @@ int run_prefilter(Handle* h, const float4* pts, int64_t n, const aicp_b200_prefi
   }
   if (!converged) return fail(h, AICP_B200_ERR_BAD_ARG, "prefilter: region growing did not reach its fixed point in %d passes", passes);
   inf.passes = passes;
+  k_pf_labels<<<blocks, 256, 0, s>>>(clabel, root, m, h->pf_label.p);
+  h->launches += 1;
   CUDA_TRY(cudaMemsetAsync(h->pf_count.p, 0, sizeof(unsigned int) * (size_t)m, s));
   k_pf_count<<<blocks, 256, 0, s>>>(h->pf_label.p, m, h->pf_count.p);
   k_pf_seed_flags<<<blocks, 256, 0, s>>>(h->pf_count.p, m, (unsigned int)cfg->min_cluster_size, (unsigned int)cfg->max_cluster_size,

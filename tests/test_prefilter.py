@@ -57,6 +57,43 @@ def min_label_regions(normals, knn, n_nb, cos_thr):
     return label, rank
 
 
+def condensed_min_label_regions(normals, knn, n_nb, cos_thr):
+    """The way csrc/prefilter.cu reaches that fixed point: points joined by TWO-WAY edges are mutually reachable, so they share
+    their ancestors and their label; components of the two-way graph first (scipy), then min-propagation between
+    components along the remaining edges."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    m = knn.shape[0]
+    order = np.lexsort((np.arange(m), normals[:, 3]))
+    rank = np.empty(m, dtype=np.int64)
+    rank[order] = np.arange(m)
+    f = np.float32
+    src = np.repeat(np.arange(m), n_nb)
+    dst = knn[:, :n_nb].reshape(-1).astype(np.int64)
+    a, b = normals[dst], normals[src]
+    dot = np.abs((a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]).astype(f) + (a[:, 2] * b[:, 2]).astype(f))
+    ok = ~(dot < f(cos_thr))
+    src, dst = src[ok], dst[ok]
+    edges = set(zip(src.tolist(), dst.tolist()))
+    two_way = np.array([(u, w) for (u, w) in edges if u != w and (w, u) in edges], dtype=np.int64).reshape(-1, 2)
+    g = coo_matrix((np.ones(len(two_way)), (two_way[:, 0], two_way[:, 1])), shape=(m, m))
+    n_comp, comp = connected_components(g, directed=False)
+    clabel = np.full(n_comp, m, dtype=np.int64)
+    np.minimum.at(clabel, comp, rank)
+    cs, cd = comp[src], comp[dst]
+    keep = cs != cd
+    cs, cd = cs[keep], cd[keep]
+    passes = 0
+    while True:
+        new = clabel.copy()
+        np.minimum.at(new, cd, clabel[cs])
+        passes += 1
+        if np.array_equal(new, clabel):
+            break
+        clabel = new
+    return clabel[comp], n_comp, passes
+
+
 def labels_from_min_label(label, min_size, max_size):
     """Cluster ordinals in seed order for regions whose size is within [min, max], else -1 (assembleRegions)."""
     seeds, counts = np.unique(label, return_counts=True)
@@ -172,6 +209,9 @@ def test_min_label_fixed_point_equals_sequential_region_growing_lidar(orc, case)
     labels, n_clusters = labels_from_min_label(label, 50, 1000000)
     assert n_clusters == o.n_clusters
     assert np.array_equal(labels, o.labels)
+    label2, n_comp, passes = condensed_min_label_regions(o.normals, knn, 15, cos_thr)
+    assert np.array_equal(label2, label)
+    assert n_comp < o.sampled.shape[0] // 2 and passes < 40        # planes collapse into few components
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -190,6 +230,7 @@ def test_min_label_fixed_point_equals_sequential_region_growing_random_digraphs(
     label, _ = min_label_regions(normals, knn, n_nb, cos_thr)
     par, n_par = labels_from_min_label(label, 1, m)
     assert n_seq == n_par and np.array_equal(seq, par)
+    assert np.array_equal(condensed_min_label_regions(normals, knn, n_nb, cos_thr)[0], label)
     seq, n_seq = orc.region_growing(normals, knn, n_nb=n_nb, min_size=5, max_size=60, cos_thr=cos_thr)
     par, n_par = labels_from_min_label(label, 5, 60)
     assert n_seq == n_par and np.array_equal(seq, par)
