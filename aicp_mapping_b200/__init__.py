@@ -4,6 +4,7 @@ The product is libaicp_b200.so (csrc/, built by build.py) behind the C ABI of in
 overlap.py mirror the reference's AbstractRegistrator / AbstractOverlapper plug-in interfaces on top of it for the
 Python harness.  There is no CPU fallback and nothing here imports the oracle.
 """
+from .classification import B200SVM, ClassificationParams, SVMParams, create_classifier  # noqa: F401
 from .filtering import (B200CropBox, B200Map, B200Prefilter, DeviceCloudView, default_prefilter_config,  # noqa: F401
                         getPointsInOrientedBox, regionGrowingUniformPlaneSegmentationFilter)
 from .overlap import B200Overlap, OverlapParams, create_overlapper  # noqa: F401

@@ -23,7 +23,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aic
            "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
            "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_prefilter_default_config", "aicp_b200_prefilter", "aicp_b200_get_prefiltered",
            "aicp_b200_prefilter_get_sampled", "aicp_b200_prefilter_get_normals", "aicp_b200_prefilter_get_labels", "aicp_b200_voxel_grid",
-           "aicp_b200_map_prefilter", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_comm_unique_id",
+           "aicp_b200_map_prefilter", "aicp_b200_svm_parse", "aicp_b200_svm_load", "aicp_b200_svm_info", "aicp_b200_svm_predict", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_comm_unique_id",
            "aicp_b200_comm_init", "aicp_b200_comm_destroy"]
 
 
@@ -60,6 +60,12 @@ class PrefilterConfig(C.Structure):
 class PrefilterInfo(C.Structure):
     _fields_ = [("n_sampled", C.c_int64), ("n_clusters", C.c_int64), ("n_out", C.c_int64), ("passes", C.c_int32),
                 ("gpu_launches", C.c_int32), ("ms_total", C.c_float)]
+
+
+class SvmSummary(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("dim", C.c_int32), ("sv_total", C.c_int32), ("sv_count", C.c_int32), ("degree", C.c_double),
+                ("gamma", C.c_double), ("coef0", C.c_double), ("rho", C.c_double), ("alpha_sum", C.c_double), ("sv_sum", C.c_double),
+                ("index_first", C.c_int32), ("index_last", C.c_int32)]
 
 
 class AicpError(RuntimeError):
@@ -124,6 +130,10 @@ def lib():
         L.aicp_b200_prefilter_get_labels.argtypes = [C.c_void_p, C.c_void_p, i64]
         L.aicp_b200_voxel_grid.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_float, C.c_void_p, C.POINTER(i64)]
         L.aicp_b200_map_prefilter.argtypes = [C.c_void_p, C.POINTER(PrefilterConfig), C.POINTER(i64), C.POINTER(PrefilterInfo)]
+        L.aicp_b200_svm_parse.argtypes = [C.c_char_p, C.POINTER(SvmSummary), C.c_char_p, C.c_int]
+        L.aicp_b200_svm_load.argtypes = [C.c_void_p, C.c_char_p]
+        L.aicp_b200_svm_info.argtypes = [C.c_void_p, ip, ip]
+        L.aicp_b200_svm_predict.argtypes = [C.c_void_p, C.POINTER(C.c_double), i64, C.c_int32, C.POINTER(C.c_double), fp]
         L.aicp_b200_autotune_ratio.argtypes = [C.c_float]
         L.aicp_b200_autotune_ratio.restype = C.c_float
         L.aicp_b200_register_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_void_p),

@@ -139,6 +139,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->pf_flag.release(); h->pf_slot.release(); h->pf_tiles.release(); h->pf_mask.release(); h->pf_count.release();
   h->pf_label.release(); h->pf_seed_pos.release(); h->pf_labels_out.release();
   h->pf_mutual.release(); h->pf_parent.release(); h->pf_root.release(); h->pf_clabel.release();
+  svm_release(h);
   if (h->pf_meta) cudaFree(h->pf_meta);
   if (h->pf_meta_host) cudaFreeHost(h->pf_meta_host);
   for (int i = 0; i < 2; ++i) if (h->pf_ev[i]) cudaEventDestroy(h->pf_ev[i]);
@@ -545,6 +546,34 @@ int aicp_b200_map_prefilter(aicp_b200_handle* hh, const aicp_b200_prefilter_conf
   h->map_n = h->pf_n_out;
   if (n_out) *n_out = h->pf_n_out;
   return AICP_B200_OK;
+}
+
+int aicp_b200_svm_parse(const char* model_xml_path, aicp_b200_svm_summary* out, char* err, int err_len) {
+  if (!model_xml_path || !out) return AICP_B200_ERR_BAD_ARG;
+  std::string e;
+  int rc = svm_parse_summary(model_xml_path, out, &e);
+  if (err && err_len > 0) { snprintf(err, (size_t)err_len, "%s", e.c_str()); }
+  return rc;
+}
+
+int aicp_b200_svm_load(aicp_b200_handle* hh, const char* model_xml_path) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!model_xml_path || !*model_xml_path) return fail(h, AICP_B200_ERR_BAD_ARG, "svm_load: empty path");
+  return svm_load(h, model_xml_path);
+}
+
+int aicp_b200_svm_info(aicp_b200_handle* hh, int32_t* dim, int32_t* sv_total) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  return svm_info(h, dim, sv_total);
+}
+
+int aicp_b200_svm_predict(aicp_b200_handle* hh, const double* features, int64_t n, int32_t dim, double* probabilities, float* raw) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n < 0 || (n > 0 && (!features || !probabilities))) return fail(h, AICP_B200_ERR_BAD_ARG, "svm_predict: bad arguments");
+  return svm_predict(h, features, n, dim, probabilities, raw);
 }
 
 float aicp_b200_autotune_ratio(float overlap_pct) {

@@ -50,6 +50,7 @@ struct SpatialIndex {
 };
 
 struct Comm;   // multi-GPU state (comm.cu)
+struct SvmModel;   // alignment-risk classifier (svm.cu)
 
 struct Handle {
   int device = 0;
@@ -125,6 +126,7 @@ struct Handle {
   cudaEvent_t pf_ev[2] = {nullptr, nullptr};
 
   Comm* comm = nullptr;
+  SvmModel* svm = nullptr;
 
   // batch workers: one child handle (own stream + buffers) per concurrent registration
   std::vector<Handle*> workers;
@@ -157,6 +159,12 @@ int run_crop_box(Handle* h, const float4* pts, int64_t n, float bmin, float bmax
 int run_voxel_grid(Handle* h, const float4* pts, int64_t n, float leaf, int64_t* n_out);
 int run_prefilter(Handle* h, const float4* pts, int64_t n, const aicp_b200_prefilter_config* cfg, const float* viewpoint,
                   aicp_b200_prefilter_info* info);
+// ---- svm.cu
+int svm_load(Handle* h, const char* path);
+int svm_parse_summary(const char* path, aicp_b200_svm_summary* out, std::string* err);
+int svm_predict(Handle* h, const double* features, int64_t n, int32_t dim, double* probabilities, float* raw);
+int svm_info(Handle* h, int32_t* dim, int32_t* sv_total);
+void svm_release(Handle* h);
 // ---- comm.cu (sharded registration; NCCL is loaded at run time, the library has no link-time dependency on it)
 int comm_allreduce_u32(Handle* h, unsigned int* buf, size_t count);
 int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count);

@@ -240,6 +240,27 @@ int aicp_b200_voxel_grid(aicp_b200_handle* h, const float* xyzw, int64_t n, floa
 /* the periodic re-filter of the merged map (app.cpp:486-493): map <- prefilter(map), all on the device */
 int aicp_b200_map_prefilter(aicp_b200_handle* h, const aicp_b200_prefilter_config* cfg, int64_t* n_out, aicp_b200_prefilter_info* info);
 
+/* ---- alignment-risk classifier ------------------------------------------------------------------
+ * replaces: aicp::SVM::load(filename)          aicp_core/src/classification/svm.cpp:103-107  (cv::ml::SVM::load)
+ *           aicp::SVM::test(data, probs)       svm.cpp:53-101: raw decision value of cv::ml::SVM::predict(sample, out, 1),
+ *                                              probability = 1.0 - 1.0 / (1.0 + exp(-raw))  (:82)
+ * as App::computeAlignmentRisk uses them on (octree overlap, alignability) (app.cpp:175-181).  model_xml_path: an OpenCV SVM
+ * file as shipped in aicp_core/data/classification/ (C_SVC, two classes, POLY or LINEAR kernel; OpenCV 3 or legacy 2.4 layout).
+ * features: n x dim doubles, row-major (converted to float32 like svm.cpp:72-74); probabilities: n doubles; raw: nullable.
+ * Training (SVM::train) is an offline tool of the reference and is not provided. */
+typedef struct {
+  int32_t kernel;                 /* 0 LINEAR, 1 POLY */
+  int32_t dim, sv_total, sv_count;
+  double  degree, gamma, coef0, rho;
+  double  alpha_sum, sv_sum;      /* plain sums in file order: a cheap fingerprint of what the reader understood */
+  int32_t index_first, index_last;
+} aicp_b200_svm_summary;
+/* parse a model file without a handle (no CUDA needed) */
+int aicp_b200_svm_parse(const char* model_xml_path, aicp_b200_svm_summary* out, char* err, int err_len);
+int aicp_b200_svm_load(aicp_b200_handle* h, const char* model_xml_path);
+int aicp_b200_svm_info(aicp_b200_handle* h, int32_t* dim, int32_t* sv_total);
+int aicp_b200_svm_predict(aicp_b200_handle* h, const double* features, int64_t n, int32_t dim, double* probabilities, float* raw);
+
 /* ---- auto-tune glue --------------------------------------------------------------------------------------------
  * replaces (for callers that do not go through a file): App::computeRegistration's clamp, app.cpp:198-202, followed by
  * the 6-significant-digit text round trip of replaceRatioConfigFile, fileIO.cpp:194-198.  Pure host code. */
