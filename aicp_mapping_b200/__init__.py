@@ -5,7 +5,7 @@ overlap.py mirror the reference's AbstractRegistrator / AbstractOverlapper plug-
 Python harness.  There is no CPU fallback and nothing here imports the oracle.
 """
 from .classification import B200SVM, ClassificationParams, SVMParams, create_classifier  # noqa: F401
-from .filtering import (B200CropBox, B200Map, B200Prefilter, DeviceCloudView, default_prefilter_config,  # noqa: F401
+from .filtering import (B200Alignability, B200CropBox, B200Map, B200Prefilter, DeviceCloudView, default_prefilter_config,  # noqa: F401
                         getPointsInOrientedBox, regionGrowingUniformPlaneSegmentationFilter)
 from .overlap import B200Overlap, OverlapParams, create_overlapper  # noqa: F401
 from .registration import (B200Registration, RegistrationParams, autotune_ratio, computeRegistration,  # noqa: F401

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "handle.cuh"
 
@@ -140,6 +141,8 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->pf_label.release(); h->pf_seed_pos.release(); h->pf_labels_out.release();
   h->pf_mutual.release(); h->pf_parent.release(); h->pf_root.release(); h->pf_clabel.release();
   svm_release(h);
+  h->al_moved.release(); h->al_mean.release(); h->al_ext.release(); h->al_sums.release(); h->al_cnt.release(); h->al_counts.release(); h->al_axes.release();
+  for (int i = 0; i < 2; ++i) { h->al_fov[i].release(); h->al_pts[i].release(); h->al_lab[i].release(); h->al_boxes[i].release(); }
   if (h->pf_meta) cudaFree(h->pf_meta);
   if (h->pf_meta_host) cudaFreeHost(h->pf_meta_host);
   for (int i = 0; i < 2; ++i) if (h->pf_ev[i]) cudaEventDestroy(h->pf_ev[i]);
@@ -545,6 +548,75 @@ int aicp_b200_map_prefilter(aicp_b200_handle* hh, const aicp_b200_prefilter_conf
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->map_n = h->pf_n_out;
   if (n_out) *n_out = h->pf_n_out;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_fov_overlap(aicp_b200_handle* hh, const float* a_xyzw, int64_t n_a, const float* b_xyzw, int64_t n_b, const double pose_a[16],
+                          const double pose_b[16], float range, float angular_view, float* out_a, float* out_b, int64_t counts[2],
+                          float* overlap_pct) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n_a < 0 || n_b < 0 || (n_a > 0 && !a_xyzw) || (n_b > 0 && !b_xyzw) || !pose_a || !pose_b || !overlap_pct)
+    return fail(h, AICP_B200_ERR_BAD_ARG, "fov_overlap: bad arguments");
+  const float4 *A = nullptr, *B = nullptr;
+  int rc;
+  if (n_a > 0 && (rc = upload_points(h, h->tmp_a, a_xyzw, n_a, &A))) return rc;
+  if (n_b > 0 && (rc = upload_points(h, h->tmp_b, b_xyzw, n_b, &B))) return rc;
+  if ((rc = run_fov_overlap(h, A, n_a, B, n_b, pose_a, pose_b, range, angular_view, overlap_pct, counts))) return rc;
+  if (out_a && h->al_fov_n[0] > 0 && (rc = download(h, out_a, h->al_fov[0].p, sizeof(float4) * (size_t)h->al_fov_n[0]))) return rc;
+  if (out_b && h->al_fov_n[1] > 0 && (rc = download(h, out_b, h->al_fov[1].p, sizeof(float4) * (size_t)h->al_fov_n[1]))) return rc;
+  return AICP_B200_OK;
+}
+
+const float* aicp_b200_get_fov_filtered(aicp_b200_handle* hh, int which, int64_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || which < 0 || which > 1) return nullptr;
+  if (n_out) *n_out = h->al_fov_n[which];
+  return reinterpret_cast<const float*>(h->al_fov[which].p);
+}
+
+int aicp_b200_alignability(aicp_b200_handle* hh, const float* a_xyzw, int64_t n_a, const float* b_xyzw, int64_t n_b, const double pose_a[16],
+                           const double pose_b[16], const aicp_b200_prefilter_config* cfg, float* alignability_pct, int32_t* matching,
+                           int64_t matching_cap, int64_t info[3]) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n_a < 0 || n_b < 0 || (n_a > 0 && !a_xyzw) || (n_b > 0 && !b_xyzw) || !pose_a || !pose_b || !alignability_pct)
+    return fail(h, AICP_B200_ERR_BAD_ARG, "alignability: bad arguments");
+  aicp_b200_prefilter_config def;
+  if (!cfg) { aicp_b200_prefilter_default_config(&def); cfg = &def; }
+  const float4 *A = nullptr, *B = nullptr;
+  int rc;
+  // the pre-filter stages host input in tmp_a itself; keep two separate staging buffers for the two clouds
+  if (n_a > 0 && (rc = upload_points(h, h->tmp_a, a_xyzw, n_a, &A))) return rc;
+  if (n_b > 0 && (rc = upload_points(h, h->tmp_b, b_xyzw, n_b, &B))) return rc;
+  int64_t inf[3] = {0, 0, 0};
+  std::vector<int32_t> m((size_t)(n_b > 0 ? n_b : 1), -1);       // one entry per kept cluster of B: never more than points
+  if ((rc = run_alignability(h, A, n_a, B, n_b, pose_a, pose_b, cfg, alignability_pct, m.data(), inf))) return rc;
+  for (int64_t j = 0; matching && j < inf[1] && j < matching_cap; ++j) matching[j] = m[(size_t)j];
+  if (info) { info[0] = inf[0]; info[1] = inf[1]; info[2] = inf[2]; }
+  return AICP_B200_OK;
+}
+
+int aicp_b200_alignment_risk(aicp_b200_handle* hh, const float* ref_xyzw, int64_t n_ref, const float* read_xyzw, int64_t n_read,
+                             const double ref_pose[16], const double read_pose[16], float range, float angular_view, float octree_overlap_pct,
+                             float* fov_overlap_pct, float* alignability_pct, double* risk) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n_ref < 1 || n_read < 1 || !ref_xyzw || !read_xyzw || !ref_pose || !read_pose || !risk)
+    return fail(h, AICP_B200_ERR_BAD_ARG, "alignment_risk: bad arguments");
+  const float4 *A, *B;
+  int rc;
+  if ((rc = upload_points(h, h->tmp_a, ref_xyzw, n_ref, &A))) return rc;
+  if ((rc = upload_points(h, h->tmp_b, read_xyzw, n_read, &B))) return rc;
+  float fov = 0.f, al = 0.f;
+  if ((rc = run_fov_overlap(h, A, n_ref, B, n_read, ref_pose, read_pose, range, angular_view, &fov, nullptr))) return rc;
+  aicp_b200_prefilter_config cfg;
+  aicp_b200_prefilter_default_config(&cfg);
+  if ((rc = run_alignability(h, h->al_fov[0].p, h->al_fov_n[0], h->al_fov[1].p, h->al_fov_n[1], ref_pose, read_pose, &cfg, &al, nullptr, nullptr))) return rc;
+  const double feat[2] = {(double)(float)octree_overlap_pct, (double)(float)al};      // app.cpp:175-176
+  if ((rc = svm_predict(h, feat, 1, 2, risk, nullptr))) return rc;
+  if (fov_overlap_pct) *fov_overlap_pct = fov;
+  if (alignability_pct) *alignability_pct = al;
   return AICP_B200_OK;
 }
 

@@ -125,6 +125,14 @@ struct Handle {
   bool pf_has_segments = false;
   cudaEvent_t pf_ev[2] = {nullptr, nullptr};
 
+  // FOV overlap filter + alignability (alignability.cu)
+  DevBuf<float4> al_moved, al_fov[2], al_pts[2], al_mean;
+  int64_t al_fov_n[2] = {0, 0};
+  DevBuf<int> al_lab[2], al_ext;
+  DevBuf<unsigned long long> al_sums;
+  DevBuf<unsigned int> al_cnt, al_counts;
+  DevBuf<float> al_axes, al_boxes[2];
+
   Comm* comm = nullptr;
   SvmModel* svm = nullptr;
 
@@ -159,6 +167,12 @@ int run_crop_box(Handle* h, const float4* pts, int64_t n, float bmin, float bmax
 int run_voxel_grid(Handle* h, const float4* pts, int64_t n, float leaf, int64_t* n_out);
 int run_prefilter(Handle* h, const float4* pts, int64_t n, const aicp_b200_prefilter_config* cfg, const float* viewpoint,
                   aicp_b200_prefilter_info* info);
+int exclusive_scan_u32(Handle* h, const unsigned int* in, unsigned int* out, int n, unsigned int* tile_scratch, unsigned int* total);
+// ---- alignability.cu
+int run_fov_overlap(Handle* h, const float4* A, int64_t nA, const float4* B, int64_t nB, const double* poseA, const double* poseB,
+                    float range, float angular_view, float* overlap_pct, int64_t* counts);
+int run_alignability(Handle* h, const float4* A, int64_t nA, const float4* B, int64_t nB, const double* poseA, const double* poseB,
+                     const aicp_b200_prefilter_config* cfg, float* out_alignability, int32_t* matching, int64_t* info);
 // ---- svm.cu
 int svm_load(Handle* h, const char* path);
 int svm_parse_summary(const char* path, aicp_b200_svm_summary* out, std::string* err);

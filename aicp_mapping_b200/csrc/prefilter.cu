@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) k_scan_apply(const unsigned int* __restri
 }
 
 // out[i] = sum of in[0..i), *total = sum of all; tile_scratch: >= ceil(n / SC_TILE) words
-static int exclusive_scan_u32(Handle* h, const unsigned int* in, unsigned int* out, int n, unsigned int* tile_scratch, unsigned int* total) {
+int exclusive_scan_u32(Handle* h, const unsigned int* in, unsigned int* out, int n, unsigned int* tile_scratch, unsigned int* total) {
   const int n_tiles = (n + SC_TILE - 1) / SC_TILE;
   k_scan_tiles<<<n_tiles, 256, 0, h->stream>>>(in, n, tile_scratch);
   k_scan_top<<<1, 256, 0, h->stream>>>(tile_scratch, n_tiles, total);

@@ -202,6 +202,79 @@ class B200Prefilter:
         return sampled, normals, labels, clusters
 
 
+def _pose16(pose):
+    """4x4 pose (numpy, row-major view of the matrix) -> 16 doubles column-major == Eigen::Isometry3d::matrix().data()."""
+    return np.ascontiguousarray(np.asarray(pose, dtype=np.float64).T).ravel()
+
+
+class B200Alignability:
+    """overlapFilter + alignabilityFilter + the SVM, i.e. what App::computeAlignmentRisk runs (app.cpp:143-185), on the GPU."""
+
+    def __init__(self, device=-1, svm_model=None):
+        self._lib = capi.lib()
+        h = C.c_void_p()
+        rc = self._lib.aicp_b200_create(None, int(device), C.byref(h))
+        if rc:
+            raise capi.AicpError(rc, self._lib.aicp_b200_last_error(None).decode())
+        self._h = h
+        if svm_model:
+            self._check(self._lib.aicp_b200_svm_load(self._h, str(svm_model).encode()))
+
+    def close(self):
+        if self._h:
+            self._lib.aicp_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise capi.AicpError(rc, self._lib.aicp_b200_last_error(self._h).decode())
+
+    def overlapFilter(self, cloudA, cloudB, poseA, poseB, sensor_range, angular_view):
+        """filteringUtils.cpp:111-193: returns (overlap_pct float32, accepted_pointsA, accepted_pointsB)."""
+        pa, na, ka = capi.ptr_and_count(cloudA)
+        pb, nb, kb = capi.ptr_and_count(cloudB)
+        outa, outb = np.zeros((max(na, 1), 4), np.float32), np.zeros((max(nb, 1), 4), np.float32)
+        counts = (C.c_int64 * 2)()
+        ov = C.c_float()
+        PA, PB = _pose16(poseA), _pose16(poseB)
+        self._check(self._lib.aicp_b200_fov_overlap(self._h, pa, na, pb, nb, PA.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    PB.ctypes.data_as(C.POINTER(C.c_double)), C.c_float(sensor_range), C.c_float(angular_view),
+                                                    C.c_void_p(outa.ctypes.data), C.c_void_p(outb.ctypes.data), counts, C.byref(ov)))
+        return np.float32(ov.value), outa[:counts[0]].copy(), outb[:counts[1]].copy()
+
+    def alignabilityFilter(self, cloudA, cloudB, poseA, poseB, cfg=None):
+        """filteringUtils.cpp:196-430: returns (alignability_pct float32, matching_indeces int32[clusters of B], (clusters A,
+        clusters B, matched))."""
+        pa, na, ka = capi.ptr_and_count(cloudA)
+        pb, nb, kb = capi.ptr_and_count(cloudB)
+        al = C.c_float()
+        cap = max(nb // 2, 1)
+        matching = np.full(cap, -1, dtype=np.int32)
+        info = (C.c_int64 * 3)()
+        PA, PB = _pose16(poseA), _pose16(poseB)
+        self._check(self._lib.aicp_b200_alignability(self._h, pa, na, pb, nb, PA.ctypes.data_as(C.POINTER(C.c_double)),
+                                                     PB.ctypes.data_as(C.POINTER(C.c_double)), C.byref(cfg) if cfg is not None else None,
+                                                     C.byref(al), matching.ctypes.data_as(C.POINTER(C.c_int32)), cap, info))
+        return np.float32(al.value), matching[:info[1]].copy(), (int(info[0]), int(info[1]), int(info[2]))
+
+    def computeAlignmentRisk(self, reference_cloud, reading_cloud, reference_pose, reading_pose, sensor_range, angular_view, octree_overlap):
+        """app.cpp:143-185: returns (fov_overlap, alignability, risk_prediction)."""
+        pa, na, ka = capi.ptr_and_count(reference_cloud)
+        pb, nb, kb = capi.ptr_and_count(reading_cloud)
+        fov, al, risk = C.c_float(), C.c_float(), C.c_double()
+        PA, PB = _pose16(reference_pose), _pose16(reading_pose)
+        self._check(self._lib.aicp_b200_alignment_risk(self._h, pa, na, pb, nb, PA.ctypes.data_as(C.POINTER(C.c_double)),
+                                                       PB.ctypes.data_as(C.POINTER(C.c_double)), C.c_float(sensor_range), C.c_float(angular_view),
+                                                       C.c_float(octree_overlap), C.byref(fov), C.byref(al), C.byref(risk)))
+        return np.float32(fov.value), np.float32(al.value), float(risk.value)
+
+
 def default_prefilter_config(**kw):
     cfg = capi.PrefilterConfig()
     capi.lib().aicp_b200_prefilter_default_config(C.byref(cfg))

@@ -240,6 +240,32 @@ int aicp_b200_voxel_grid(aicp_b200_handle* h, const float* xyzw, int64_t n, floa
 /* the periodic re-filter of the merged map (app.cpp:486-493): map <- prefilter(map), all on the device */
 int aicp_b200_map_prefilter(aicp_b200_handle* h, const aicp_b200_prefilter_config* cfg, int64_t* n_out, aicp_b200_prefilter_info* info);
 
+/* ---- FOV overlap filter + alignability ---------------------------------------------------------------
+ * replaces: overlapFilter(cloudA, cloudB, poseA, poseB, range, angularView, accepted_pointsA, accepted_pointsB)
+ *           aicp_core/src/utils/filteringUtils.cpp:111-193 (App::computeAlignmentRisk, app.cpp:153-156): the points of each cloud
+ *           that lie within the other sensor's range and horizontal field of view; returns 100 * (kept A / |A|) * (kept B / |B|).
+ * poses: 16 doubles, column-major == Eigen::Isometry3d::matrix().data().  range / angular_view: RegistrationParams.sensorRange /
+ * sensorAngularView (aicp_config.yaml:4-5).  out_a / out_b: nullable buffers of capacity n_a / n_b records (host or device); the
+ * accepted clouds also stay on the device (aicp_b200_get_fov_filtered: which = 0 for A, 1 for B) until the next call. */
+int aicp_b200_fov_overlap(aicp_b200_handle* h, const float* a_xyzw, int64_t n_a, const float* b_xyzw, int64_t n_b,
+                          const double pose_a[16], const double pose_b[16], float range, float angular_view, float* out_a,
+                          float* out_b, int64_t counts[2], float* overlap_pct);
+const float* aicp_b200_get_fov_filtered(aicp_b200_handle* h, int which, int64_t* n_out);
+/* replaces: alignabilityFilter(cloudA, cloudB, poseA, poseB, cloudA_planes, cloudB_planes, eigenvectors)  filteringUtils.cpp:196-430:
+ *           both clouds through the pre-filter (normals towards each sensor, plane clusters), clusters matched through their
+ *           oriented bounding boxes (:236-282, overlapBoxFilter :507-576), PCA of the matched normals -> 100 * lambda_min / lambda_max.
+ * cfg: NULL for the pre-filter's hard-coded parameters.  matching: nullable, receives min(clusters of B, matching_cap) entries
+ * (index of the matched cluster of A, or -1: matching_indeces of :229).  info: nullable {clusters A, clusters B, matched}. */
+int aicp_b200_alignability(aicp_b200_handle* h, const float* a_xyzw, int64_t n_a, const float* b_xyzw, int64_t n_b,
+                           const double pose_a[16], const double pose_b[16], const aicp_b200_prefilter_config* cfg,
+                           float* alignability_pct, int32_t* matching, int64_t matching_cap, int64_t info[3]);
+/* replaces: App::computeAlignmentRisk (app.cpp:143-185): FOV overlap -> alignability of the two accepted clouds -> SVM probability
+ * of (octree_overlap_pct, alignability).  Needs a loaded model (aicp_b200_svm_load).  Everything between the input clouds and the
+ * three scalars stays on the device. */
+int aicp_b200_alignment_risk(aicp_b200_handle* h, const float* ref_xyzw, int64_t n_ref, const float* read_xyzw, int64_t n_read,
+                             const double ref_pose[16], const double read_pose[16], float range, float angular_view,
+                             float octree_overlap_pct, float* fov_overlap_pct, float* alignability_pct, double* risk);
+
 /* ---- alignment-risk classifier ------------------------------------------------------------------
  * replaces: aicp::SVM::load(filename)          aicp_core/src/classification/svm.cpp:103-107  (cv::ml::SVM::load)
  *           aicp::SVM::test(data, probs)       svm.cpp:53-101: raw decision value of cv::ml::SVM::predict(sample, out, 1),

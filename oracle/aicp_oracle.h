@@ -150,6 +150,15 @@ int64_t orc_region_growing(const float* normals, const int32_t* knn, int64_t m, 
 int orc_prefilter(const float* xyzw, int64_t n, const orc_prefilter_config* cfg, const float* viewpoint, int threads,
                   float* sampled, float* normals, int32_t* labels, float* out, int64_t* counts);
 
+/* ---- FOV overlap filter + alignability (filteringUtils.cpp:111-576), see aicp_oracle_alignability.c ---- */
+/* poses: 16 doubles, column-major (Eigen::Isometry3d::matrix().data()).  counts = {accepted A, accepted B} */
+float orc_fov_overlap(const float* A, int64_t nA, const float* B, int64_t nB, const double* poseA, const double* poseB, float range,
+                      float angular_view, float* outA, float* outB, int64_t* counts);
+void orc_euler_angles_012(const float* R_rowmajor9, float* rpy);
+/* matching: nullable, one entry per kept cluster of B (index of the matched cluster of A or -1); info = {clusters A, clusters B, matched} */
+int orc_alignability(const float* A, int64_t nA, const float* B, int64_t nB, const double* poseA, const double* poseB,
+                     const orc_prefilter_config* cfg, int threads, float* out_alignability, int32_t* matching, int64_t* info);
+
 /* ---- text glue KATs ---- */
 /* app.cpp:198-202 clamp + fileIO.cpp:194-198 "%g"-style 6-digit print + float re-parse */
 float orc_autotune_ratio(float overlap_pct, char* text_out /* >=32 bytes, nullable */);

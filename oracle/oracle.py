@@ -36,7 +36,7 @@ class IcpResult(C.Structure):
 
 def build(force=False):
     """Compile the oracle with oracle/Makefile (gcc)."""
-    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle_filters.c", "aicp_oracle_prefilter.c", "aicp_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle_filters.c", "aicp_oracle_prefilter.c", "aicp_oracle_alignability.c", "aicp_oracle.h", "Makefile")]
     if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return _LIB_PATH
     subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
@@ -319,3 +319,43 @@ def prefilter(cloud, cfg=None, viewpoint=None, threads=1):
     o.n_clusters = int(counts[1])
     o.cloud = out[:counts[2]].copy()
     return o
+
+
+# ---- FOV overlap + alignability (aicp_oracle_alignability.c): filteringUtils.cpp:111-576 ----
+def _pose16(pose):
+    """4x4 (numpy, row-major view of the matrix) -> 16 doubles column-major, like Eigen::Isometry3d::matrix().data()."""
+    return np.ascontiguousarray(np.asarray(pose, dtype=np.float64).T).ravel()
+
+
+def fov_overlap(cloudA, cloudB, poseA, poseB, sensor_range, angular_view):
+    """overlapFilter: returns (overlap_pct float32, accepted A n x 4, accepted B n x 4)."""
+    a, b = to_xyzw(cloudA), to_xyzw(cloudB)
+    outa, outb = np.zeros((max(a.shape[0], 1), 4), np.float32), np.zeros((max(b.shape[0], 1), 4), np.float32)
+    counts = np.zeros(2, dtype=np.int64)
+    pa, pb = _pose16(poseA), _pose16(poseB)
+    L = lib()
+    L.orc_fov_overlap.restype = C.c_float
+    ov = L.orc_fov_overlap(_ptr(a), C.c_int64(a.shape[0]), _ptr(b), C.c_int64(b.shape[0]), _ptr(pa, C.c_double), _ptr(pb, C.c_double),
+                           C.c_float(sensor_range), C.c_float(angular_view), _ptr(outa), _ptr(outb), _ptr(counts, C.c_int64))
+    return np.float32(ov), outa[:counts[0]].copy(), outb[:counts[1]].copy()
+
+
+def euler_angles_012(R):
+    R = np.ascontiguousarray(R, dtype=np.float32)
+    out = np.zeros(3, dtype=np.float32)
+    lib().orc_euler_angles_012(_ptr(R), _ptr(out))
+    return out
+
+
+def alignability(cloudA, cloudB, poseA, poseB, cfg=None, threads=1):
+    """alignabilityFilter: returns (alignability_pct float32, matching int32[n clusters of B], (clusters A, clusters B, matched))."""
+    a, b = to_xyzw(cloudA), to_xyzw(cloudB)
+    cfg = cfg or prefilter_default_config()
+    pa, pb = _pose16(poseA), _pose16(poseB)
+    al = C.c_float()
+    matching = np.full(max(b.shape[0], 1), -1, dtype=np.int32)
+    info = np.zeros(3, dtype=np.int64)
+    rc = lib().orc_alignability(_ptr(a), C.c_int64(a.shape[0]), _ptr(b), C.c_int64(b.shape[0]), _ptr(pa, C.c_double), _ptr(pb, C.c_double),
+                                C.byref(cfg), int(threads), C.byref(al), _ptr(matching, C.c_int32), _ptr(info, C.c_int64))
+    _check(rc, "alignability")
+    return np.float32(al.value), matching[:info[1]].copy(), tuple(int(x) for x in info)

@@ -1,0 +1,180 @@
+"""overlapFilter + alignabilityFilter (aicp_core/src/utils/filteringUtils.cpp:111-576) and App::computeAlignmentRisk
+(app.cpp:143-185), SURVEY.md 8(f) rank 2.
+not gpu: the oracle (oracle/aicp_oracle_alignability.c) on analytic scenes and against an independent numpy statement of the
+         field-of-view test.
+gpu    : the CUDA path through the C ABI against the oracle: accepted clouds bit for bit and in order, alignability bit for
+         bit, the cluster matching, and the whole computeAlignmentRisk chain."""
+import os
+
+import numpy as np
+import pytest
+
+import aicp_mapping_b200 as ab
+from aicp_mapping_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEFAULT_MODEL = os.path.join(GOLDEN, "svm_models", "svm_1000training_thresh50_cross_validation_opencv3.xml")
+
+
+def pose(t, yaw=0.0):
+    return synth.rigid(t[0], t[1], t[2], 0.0, 0.0, yaw)
+
+
+def corridor(rng, n=40000, end_wall=False, shift=(0.0, 0.0, 0.0)):
+    w1 = np.c_[rng.uniform(0, 20, n), np.full(n, -1.0), rng.uniform(0, 2.5, n)]
+    w2 = np.c_[rng.uniform(0, 20, n), np.full(n, 1.0), rng.uniform(0, 2.5, n)]
+    fl = np.c_[rng.uniform(0, 20, n), rng.uniform(-1, 1, n), np.zeros(n)]
+    parts = [w1, w2, fl]
+    if end_wall:
+        parts.append(np.c_[np.full(n // 2, 20.0), rng.uniform(-1, 1, n // 2), rng.uniform(0, 2.5, n // 2)])
+    pts = np.concatenate(parts, 0)
+    return (pts + rng.normal(0.0, 0.01, pts.shape) + np.asarray(shift)).astype(np.float32)      # 1 cm range noise: a noise-free
+    # plane has a zero-thickness bounding box that the other cloud's points miss by rounding
+
+
+def room_box(rng, n=30000, shift=(0.0, 0.0, 0.0)):
+    """Three mutually perpendicular planes, seen from inside the corner."""
+    a = np.c_[rng.uniform(0, 6, n), rng.uniform(0, 6, n), np.zeros(n)]
+    b = np.c_[rng.uniform(0, 6, n), np.zeros(n), rng.uniform(0, 3, n)]
+    c = np.c_[np.zeros(n), rng.uniform(0, 6, n), rng.uniform(0, 3, n)]
+    pts = np.concatenate([a, b, c], 0)
+    return (pts + rng.normal(0.0, 0.01, pts.shape) + np.asarray(shift)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_oracle_fov_overlap_matches_numpy_statement(orc):
+    rng = np.random.default_rng(11)
+    A = rng.uniform(-40, 40, (20000, 3)).astype(np.float32)
+    B = rng.uniform(-40, 40, (15000, 3)).astype(np.float32)
+    PA, PB = pose([1.0, -2.0, 0.5], 0.3), pose([-3.0, 1.0, 0.7], -1.1)
+    for rng_m, view in ((30.0, 270.0), (100.0, 360.0), (25.0, 180.0)):
+        ov, a, b = orc.fov_overlap(A, B, PA, PB, rng_m, view)
+        thresh = 180.0 - (360.0 - view) / 2.0
+
+        def accept(cloud, other):
+            local = (cloud.astype(np.float64) - other[:3, 3]) @ other[:3, :3]
+            r = np.linalg.norm(local, axis=1)
+            theta = np.degrees(np.arctan2(local[:, 1], local[:, 0]))
+            margin = np.minimum(np.abs(np.abs(theta) - thresh), np.abs(r - rng_m))
+            return (np.abs(theta) < thresh) & (r < rng_m), margin < 1e-3
+        ka, fa = accept(A, PB)
+        kb, fb = accept(B, PA)
+        # float32 / float64 can only disagree within rounding distance of the cone or the range sphere
+        assert abs(a.shape[0] - ka.sum()) <= fa.sum() and abs(b.shape[0] - kb.sum()) <= fb.sum()
+        want = np.float32(np.float32(a.shape[0]) / np.float32(A.shape[0]) * (np.float32(b.shape[0]) / np.float32(B.shape[0])))
+        assert ov == np.float32(np.float64(want) * 100.0)
+        # accepted points are the input points again, up to the float32 round trip through the other sensor's frame
+        idx = np.flatnonzero(ka & ~fa)[:50]
+        if view == 360.0 and fa.sum() == 0:
+            assert np.abs(a[:, :3] - A[ka]).max() < 2e-5
+
+
+def test_oracle_fov_overlap_analytic(orc):
+    I = np.eye(4)
+    pts = np.float32([[1, 0, 0], [0, 1, 0], [-1, 0.5, 0], [-1, 0, 0], [-1, 1.0001, 0], [50, 0, 0], [0, 0, 0]])
+    ov, a, b = orc.fov_overlap(pts, pts[:1], I, I, 30.0, 270.0)        # thresh = 135 deg: the rear 90-degree wedge is cut
+    assert np.array_equal(a[:, :3], pts[[0, 1, 4, 6]])
+    assert ov == np.float32(np.float64(np.float32(4.0 / 7.0) * np.float32(1.0)) * 100.0)
+    ov, a, b = orc.fov_overlap(pts, pts[:1], I, I, 100.0, 360.0)       # |theta| < 180: only the exact rear axis is cut
+    assert np.array_equal(a[:, :3], pts[[0, 1, 2, 4, 5, 6]])
+
+
+def test_oracle_alignability_analytic_scenes(orc):
+    rng = np.random.default_rng(0)
+    P = pose([3.0, 0.2, 1.0])
+    cor = corridor(rng)
+    al, matching, info = orc.alignability(cor, corridor(rng, shift=(0.1, 0, 0)), P, P, threads=4)
+    assert info[2] >= 3 and al < 0.5                         # no constraint along the corridor: degenerate
+    Q = pose([3.0, 3.0, 1.5])
+    al, matching, info = orc.alignability(room_box(rng), room_box(rng, shift=(0.05, 0.02, 0)), Q, Q, threads=4)
+    assert info[2] >= 3 and al > 30.0                        # three perpendicular planes: well constrained
+    # every matched pair is (cluster of A, cluster of B) with a B index used once
+    assert len(set(m for m in matching if m >= 0)) == info[2]
+    # nothing to match: two unrelated scenes far apart
+    al, matching, info = orc.alignability(cor, room_box(rng, shift=(200.0, 0, 0)), P, Q, threads=4)
+    assert al == 0.0 and info[2] == 0
+    # empty and tiny inputs
+    al, matching, info = orc.alignability(np.zeros((0, 3), np.float32), cor, P, P)
+    assert al == 0.0 and info == (0, info[1], 0)
+
+
+def test_euler_angles_restatement_matches_python_mirror(orc):
+    from aicp_mapping_b200 import filtering
+    for seed in range(10):
+        rng = np.random.default_rng(seed)
+        R = synth.rigid(0, 0, 0, *rng.uniform(-1.4, 1.4, 3))[:3, :3].astype(np.float32)
+        got = orc.euler_angles_012(R)
+        assert np.abs(got - filtering.euler_angles_xyz(R)).max() < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def al():
+    a = ab.B200Alignability(device=0, svm_model=DEFAULT_MODEL)
+    yield a
+    a.close()
+
+
+@pytest.mark.gpu
+def test_fov_overlap_parity(orc, al, pair_cache):
+    rng = np.random.default_rng(5)
+    cases = []
+    A = rng.uniform(-40, 40, (70001, 3)).astype(np.float32)
+    B = rng.uniform(-40, 40, (4097, 3)).astype(np.float32)
+    cases.append((A, B, pose([1.0, -2.0, 0.5], 0.3), pose([-3.0, 1.0, 0.7], -1.1)))
+    p = pair_cache(2)
+    cases.append((p["ref"], p["read"], pose(p["ref_origin"]), pose(p["read_origin"], 0.05)))
+    for A, B, PA, PB in cases:
+        for rng_m, view in ((30.0, 270.0), (100.0, 360.0), (5.0, 90.0)):
+            ov, a, b = al.overlapFilter(A, B, PA, PB, rng_m, view)
+            o_ov, o_a, o_b = orc.fov_overlap(A, B, PA, PB, rng_m, view)
+            assert ov == o_ov
+            assert np.array_equal(a.view(np.uint32), o_a.view(np.uint32)) and np.array_equal(b.view(np.uint32), o_b.view(np.uint32))
+    ov, a, b = al.overlapFilter(A[:1], B[:1], np.eye(4), np.eye(4), 1e-3, 270.0)      # nothing accepted
+    assert ov == 0.0 and a.shape == (0, 4) and b.shape == (0, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["corridor", "room", "vlp16_pair", "hdl64_pair", "disjoint"])
+def test_alignability_parity(orc, al, pair_cache, case):
+    rng = np.random.default_rng(3)
+    if case == "corridor":
+        A, B = corridor(rng, end_wall=True), corridor(rng, end_wall=True, shift=(0.1, 0, 0))
+        PA = PB = pose([3.0, 0.2, 1.0])
+    elif case == "room":
+        A, B = room_box(rng), room_box(rng, shift=(0.05, 0.02, 0))
+        PA = PB = pose([3.0, 3.0, 1.5])
+    elif case == "vlp16_pair":
+        p = pair_cache(2)
+        A, B, PA, PB = p["ref"], p["read"], pose(p["ref_origin"]), pose(p["read_origin"])
+    elif case == "hdl64_pair":
+        p = pair_cache(3, 0, 60000)
+        A, B, PA, PB = p["ref"], p["read"], pose(p["ref_origin"]), pose(p["read_origin"])
+    else:
+        A, B = corridor(rng), room_box(rng, shift=(200.0, 0, 0))
+        PA, PB = pose([3.0, 0.2, 1.0]), pose([203.0, 3.0, 1.5])
+    got, matching, info = al.alignabilityFilter(A, B, PA, PB)
+    want, o_matching, o_info = orc.alignability(A, B, PA, PB, threads=8)
+    assert info == o_info
+    assert np.array_equal(matching, o_matching)
+    assert got == want, (got, want)
+    if case == "disjoint":
+        assert got == 0.0 and info[2] == 0
+
+
+@pytest.mark.gpu
+def test_compute_alignment_risk_chain(orc, al, pair_cache):
+    """app.cpp:143-185 end to end: FOV overlap -> alignability of the accepted clouds -> SVM(octree overlap, alignability)."""
+    from oracle import aicp_oracle_svm as svm_orc
+    p = pair_cache(2)
+    PA, PB = pose(p["ref_origin"]), pose(p["read_origin"])
+    o_ov, counts = orc.overlap(p["ref"], p["ref_origin"], p["read"], p["read_origin"])
+    fov, ali, risk = al.computeAlignmentRisk(p["ref"], p["read"], PA, PB, 30.0, 270.0, float(o_ov))
+    o_fov, o_a, o_b = orc.fov_overlap(p["ref"], p["read"], PA, PB, 30.0, 270.0)
+    o_ali, _, _ = orc.alignability(o_a, o_b, PA, PB, threads=8)
+    o_risk = svm_orc.test(svm_orc.load_model(DEFAULT_MODEL), np.array([[float(o_ov), float(o_ali)]]))[0]
+    assert fov == o_fov and ali == o_ali
+    assert abs(risk - o_risk) <= 1e-6 and 0.0 < risk < 1.0
+    # tiny inputs go through without clusters: alignability 0
+    fov, ali, risk = al.computeAlignmentRisk(p["ref"][:20], p["read"][:20], PA, PB, 30.0, 270.0, 50.0)
+    assert ali == 0.0
