@@ -13,7 +13,8 @@
 //   k_vg_heads     head flag of every run of equal keys; exclusive scan (k_scan_*) = output slot of the voxel
 //   k_vg_centroids one thread per voxel: exact fixed-point sums (llrint(x * 2^20), int64 -- order independent) -> centroid
 // Stage N, normals: Morton index + exact k-NN (index.cu, normals.cu: the same kernels as the ICP chain's SurfaceNormal filter),
-//   k_pf_normals   one thread per point: PCL's single-pass float32 covariance in list order, float64 Jacobi, curvature,
+//   k_pf_normals   one thread per point: PCL's single-pass float32 covariance (shifted by the first neighbour) in list order,
+//                  float64 Jacobi, curvature,
 //                  viewpoint flip
 // Stage R, region growing.  PCL grows regions sequentially from seeds in ascending-curvature order over the DIRECTED k-NN
 //   graph (edge u -> w when w is one of u's 15 neighbours and |n_u . n_w| >= cos 3 deg).  Its result is a pure function of the
@@ -255,13 +256,15 @@ __global__ void __launch_bounds__(128) k_pf_normals(IndexView ix, int k, const i
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ix.n) return;
   const int* nb = knn_pos + (size_t)i * k;
-  // pcl::computeMeanAndCovarianceMatrix: single-pass float32 accumulators in list order
+  // pcl::computeMeanAndCovarianceMatrix: single-pass float32 accumulators in list order, shifted data
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f, a8 = 0.f;
+  const float4 K = __ldg(&ix.pts[__ldg(&nb[0])]);     // shift by the first neighbour (the query point itself), as PCL >= 1.10
   for (int j = 0; j < k; ++j) {
     const float4 p = __ldg(&ix.pts[__ldg(&nb[j])]);
-    a0 = __fadd_rn(a0, __fmul_rn(p.x, p.x)); a1 = __fadd_rn(a1, __fmul_rn(p.x, p.y)); a2 = __fadd_rn(a2, __fmul_rn(p.x, p.z));
-    a3 = __fadd_rn(a3, __fmul_rn(p.y, p.y)); a4 = __fadd_rn(a4, __fmul_rn(p.y, p.z)); a5 = __fadd_rn(a5, __fmul_rn(p.z, p.z));
-    a6 = __fadd_rn(a6, p.x); a7 = __fadd_rn(a7, p.y); a8 = __fadd_rn(a8, p.z);
+    const float x = __fsub_rn(p.x, K.x), y = __fsub_rn(p.y, K.y), z = __fsub_rn(p.z, K.z);
+    a0 = __fadd_rn(a0, __fmul_rn(x, x)); a1 = __fadd_rn(a1, __fmul_rn(x, y)); a2 = __fadd_rn(a2, __fmul_rn(x, z));
+    a3 = __fadd_rn(a3, __fmul_rn(y, y)); a4 = __fadd_rn(a4, __fmul_rn(y, z)); a5 = __fadd_rn(a5, __fmul_rn(z, z));
+    a6 = __fadd_rn(a6, x); a7 = __fadd_rn(a7, y); a8 = __fadd_rn(a8, z);
   }
   const float kf = (float)k;
   a0 = __fdiv_rn(a0, kf); a1 = __fdiv_rn(a1, kf); a2 = __fdiv_rn(a2, kf); a3 = __fdiv_rn(a3, kf); a4 = __fdiv_rn(a4, kf);

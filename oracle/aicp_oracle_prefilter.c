@@ -13,7 +13,10 @@
  *   ijk = (int)(floor(p * inverse_leaf) - (float)min_b); idx = ijk . (1, div_x, div_x*div_y); points sorted by idx; one
  *   centroid per occupied voxel, emitted in ascending idx order.
  * NormalEstimation::computeFeature   k nearest neighbours of every point (itself included), computeMeanAndCovarianceMatrix
- *   = SINGLE-PASS float32 accumulators (sum xx, xy, xz, yy, yz, zz, x, y, z) / k, cov = E[ab] - E[a]E[b];
+ *   = single-pass float32 accumulators (sum xx, xy, xz, yy, yz, zz, x, y, z) / k over coordinates SHIFTED by the first
+ *   neighbour, cov = E[ab] - E[a]E[b].  (The shift is PCL >= 1.10's; PCL 1.8 accumulates the raw coordinates, which loses
+ *   the covariance of a 0.5 m neighbourhood a few tens of metres from the origin -- at 200 m every normal is noise.  The
+ *   shifted form is restated so that the result does not depend on where the world origin is.)
  *   solvePlaneParameters: eigenvector of the smallest eigenvalue, curvature = |lambda_min / trace|;
  *   flipNormalTowardsViewpoint: n -> -n when (vp - p) . n < 0.
  * RegionGrowing::extract             points sorted by curvature; the lowest-curvature unlabelled point seeds a region that
@@ -154,9 +157,10 @@ static void jacobi3(double a[3][3], double v[3][3]) {
 /* pcl::computePointNormal + flipNormalTowardsViewpoint for one point.  nb: k neighbour ids in (d2, id) order. */
 void orc_pcl_point_normal(const float* pts, const int32_t* nb, int32_t k, const float* query, const float* viewpoint, float* out4) {
   float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const float* K = pts + 4 * (int64_t)nb[0];          /* shift by the first neighbour (the query point itself) */
   for (int32_t j = 0; j < k; ++j) {
     const float* p = pts + 4 * (int64_t)nb[j];
-    const float x = p[0], y = p[1], z = p[2];
+    const float x = p[0] - K[0], y = p[1] - K[1], z = p[2] - K[2];
     acc[0] = acc[0] + x * x; acc[1] = acc[1] + x * y; acc[2] = acc[2] + x * z;
     acc[3] = acc[3] + y * y; acc[4] = acc[4] + y * z; acc[5] = acc[5] + z * z;
     acc[6] = acc[6] + x; acc[7] = acc[7] + y; acc[8] = acc[8] + z;

@@ -93,6 +93,12 @@ def test_oracle_alignability_analytic_scenes(orc):
     # nothing to match: two unrelated scenes far apart
     al, matching, info = orc.alignability(cor, room_box(rng, shift=(200.0, 0, 0)), P, Q, threads=4)
     assert al == 0.0 and info[2] == 0
+    # the result does not depend on where the world origin is (shifted covariance in the normals, exact cluster sums)
+    A, B = room_box(rng), room_box(rng, shift=(0.05, 0.02, 0))
+    near = orc.alignability(A, B, Q, Q, threads=4)
+    sh = np.float32([200.0, -150.0, 0.0])
+    far = orc.alignability(A + sh, B + sh, pose([203.0, -147.0, 1.5]), pose([203.0, -147.0, 1.5]), threads=4)
+    assert near[2] == far[2] and abs(near[0] - far[0]) < 0.05
     # empty and tiny inputs
     al, matching, info = orc.alignability(np.zeros((0, 3), np.float32), cor, P, P)
     assert al == 0.0 and info == (0, info[1], 0)

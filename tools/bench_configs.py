@@ -8,6 +8,7 @@
       (reported), then registrations/s and ms per registration with the map resident
   C5  validation sweep: 4096 registrations of 38 400-point cube pairs (16 distinct perturbations cycled), batched
   overlap  the octree-overlap parameter of the C3 pair (ms per call, voxel counts)
+  risk  App::computeAlignmentRisk (FOV overlap -> alignability -> SVM) for the C2 and C3 pairs, ms per call, CPU oracle beside it
   prefilter  regionGrowingUniformPlaneSegmentationFilter (VoxelGrid 0.08 + k-30 normals + region growing) on the raw clouds
       App feeds it: 7 accumulated VLP-16 sweeps (~200 k points) and one HDL-64 sweep (~250 k points); ms per call, the
       voxel-grid stage alone against the HBM roofline, and the CPU oracle on the host cores beside it
@@ -27,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="2,4,4crop,5,5step,overlap,prefilter")
+    ap.add_argument("--configs", default="2,4,4crop,5,5step,overlap,prefilter,risk")
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--map-points", type=int, default=10485760)
     args = ap.parse_args()
@@ -138,6 +139,37 @@ def main():
                               "cpu_oracle_ms": cpu_ms, "cpu_cores": ncpu, "bit_identical_to_oracle": same,
                               "clouds_per_s": 1e3 / (dev_ms / reps)}), flush=True)
         pf.close()
+    if "risk" in want:
+        from oracle import oracle as orc          # CPU baseline leg only
+        from oracle import aicp_oracle_svm as svm_orc
+        ncpu = os.cpu_count() or 1
+        model = os.path.join(ROOT, "tests", "golden", "svm_models", "svm_1000training_thresh50_cross_validation_opencv3.xml")
+        al = ab.B200Alignability(device=0, svm_model=model)
+        for cfgid, rng_m, view in ((2, 30.0, 270.0), (3, 100.0, 360.0)):
+            p = synth.make_pair(cfgid, 0)
+            PA, PB = synth.rigid(*p["ref_origin"]), synth.rigid(*p["read_origin"])
+            r, q = dev(p["ref"]), dev(p["read"])
+            ov_pct = float(ovl.computeOverlap(r, q, p["ref_origin"], p["read_origin"]) and ovl.getOverlap())
+            for _ in range(3):
+                res = al.computeAlignmentRisk(r, q, PA, PB, rng_m, view, ov_pct)
+            torch.cuda.synchronize()
+            reps = 20
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                res = al.computeAlignmentRisk(r, q, PA, PB, rng_m, view, ov_pct)
+            ms = (time.perf_counter() - t0) / reps * 1e3
+            t0 = time.perf_counter()
+            o_fov, o_a, o_b = orc.fov_overlap(p["ref"], p["read"], PA, PB, rng_m, view)
+            o_al, o_match, o_info = orc.alignability(o_a, o_b, PA, PB, threads=ncpu)
+            o_risk = svm_orc.test(svm_orc.load_model(model), np.array([[ov_pct, float(o_al)]]))[0]
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            print(json.dumps({"config": "computeAlignmentRisk (FOV overlap -> alignability -> SVM) of the %s" % p["name"],
+                              "metric": "ms per computeAlignmentRisk", "value": ms, "unit": "ms", "fov_overlap_pct": float(res[0]),
+                              "alignability_pct": float(res[1]), "risk": float(res[2]), "octree_overlap_pct": ov_pct,
+                              "clusters_A_B_matched": list(o_info), "cpu_oracle_ms": cpu_ms, "cpu_cores": ncpu,
+                              "identical_to_oracle": bool(res[0] == o_fov and res[1] == o_al and abs(res[2] - o_risk) < 1e-6),
+                              "inputs": "device-resident, host synchronised per call (wall clock)"}), flush=True)
+        al.close()
     if "4" in want:
         t0 = time.perf_counter()
         case = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=8)
