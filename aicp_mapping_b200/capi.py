@@ -24,7 +24,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aic
            "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_prefilter_default_config", "aicp_b200_prefilter", "aicp_b200_get_prefiltered",
            "aicp_b200_prefilter_get_sampled", "aicp_b200_prefilter_get_normals", "aicp_b200_prefilter_get_labels", "aicp_b200_voxel_grid",
            "aicp_b200_map_prefilter", "aicp_b200_fov_overlap", "aicp_b200_get_fov_filtered", "aicp_b200_alignability", "aicp_b200_alignment_risk",
-           "aicp_b200_svm_parse", "aicp_b200_svm_load", "aicp_b200_svm_info", "aicp_b200_svm_predict", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_comm_unique_id",
+           "aicp_b200_svm_parse", "aicp_b200_svm_load", "aicp_b200_svm_info", "aicp_b200_svm_predict", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_pipeline_batch", "aicp_b200_comm_unique_id",
            "aicp_b200_comm_init", "aicp_b200_comm_destroy"]
 
 
@@ -150,6 +150,10 @@ def lib():
         L.aicp_b200_aicp_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double),
                                            C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double), C.c_double, C.c_int, fp, fp,
                                            C.POINTER(Stats), C.POINTER(C.c_int32), fp]
+        L.aicp_b200_pipeline_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double),
+                                               C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double), C.c_double, C.c_float, C.c_float,
+                                               C.c_char_p, C.c_double, C.c_int, fp, fp, fp, C.POINTER(C.c_double), C.POINTER(Stats),
+                                               C.POINTER(C.c_int32), fp]
         L.aicp_b200_comm_unique_id.argtypes = [C.c_void_p]
         L.aicp_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.aicp_b200_comm_destroy.argtypes = [C.c_void_p]

@@ -661,10 +661,21 @@ float aicp_b200_autotune_ratio(float overlap_pct) {
 
 // common implementation of the two batch entry points; origins != nullptr: one AICP step per pair (overlap -> clamp and
 // 6-digit round trip -> registration with that ratio), else registration only with the given / configured ratios
+// optional alignment-risk stage of the batched pipeline (App::runAicpPipeline with failure_prediction_mode, app.cpp:232-246)
+struct RiskArgs {
+  const double* ref_poses;       // n_pairs x 16, column-major
+  const double* read_poses;
+  float range, angular_view;
+  const char* model_path;
+  double threshold;
+  float* out_alignability;
+  double* out_risk;
+};
+
 static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
                       const float* const* read_xyzw, const int64_t* n_read, const float* ratios, const double* ref_origins,
                       const double* read_origins, double resolution, int streams, float* out_T, float* out_overlap,
-                      aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
+                      aicp_b200_stats* stats, int32_t* status, float* batch_ms, const RiskArgs* risk = nullptr) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   H_CHECK(h);
   if (n_pairs < 0 || (n_pairs > 0 && (!ref_xyzw || !n_ref || !read_xyzw || !n_read || !out_T)))
@@ -692,6 +703,10 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
     wh->cfg = h->cfg; wh->cfg_from_file = false;
     wh->profiling = h->profiling; wh->trace_matches = false;
     wh->batch_worker = streams > 1; wh->knn_schedule = h->knn_schedule; wh->match_schedule = h->match_schedule;
+    if (risk && wh->svm_path != risk->model_path) {
+      if ((rc = svm_load(wh, risk->model_path))) return fail(h, rc, "pipeline_batch: %s", wh->last_error.c_str());
+      wh->svm_path = risk->model_path;
+    }
     CUDA_TRY(cudaStreamWaitEvent(wh->stream, h->batch_ev[0], 0));
   }
   std::atomic<int64_t> next(0);
@@ -705,18 +720,42 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
       if (i >= n_pairs) break;
       if (ratios) wh->cfg.ratio = ratios[i];
       int r = AICP_B200_OK;
-      if (ref_origins) {
-        // App::runAicpPipeline (app.cpp:218-247): computeOverlap, then computeRegistration with the auto-tuned ratio
-        // both clouds are staged once into the worker's own buffers and used by the overlap and by the registration
+      if (ref_origins || risk) {
+        // App::runAicpPipeline (app.cpp:218-247): computeOverlap, [computeAlignmentRisk,] then computeRegistration with the
+        // auto-tuned ratio; both clouds are staged once into the worker's own buffers and used by every stage
         float ov = 0.f;
+        double origin_a[3], origin_b[3];
+        const double* oa = ref_origins ? ref_origins + 3 * i : origin_a;
+        const double* ob = read_origins ? read_origins + 3 * i : origin_b;
+        if (risk) for (int d = 0; d < 3; ++d) { origin_a[d] = risk->ref_poses[16 * i + 12 + d]; origin_b[d] = risk->read_poses[16 * i + 12 + d]; }
         if (!ref_xyzw[i] || !read_xyzw[i] || n_ref[i] < 1 || n_read[i] < 1 || n_ref[i] > (1ll << 30) || n_read[i] > (1ll << 30))
           r = fail(wh, AICP_B200_ERR_BAD_ARG, "aicp_batch: null or empty cloud in pair %lld", (long long)i);
         if (!r) r = stage_owned(wh, wh->ref_in, ref_xyzw[i], n_ref[i]);
         if (!r) r = stage_owned(wh, wh->read_in, read_xyzw[i], n_read[i]);
-        if (!r) r = run_overlap(wh, wh->ref_in.p, n_ref[i], ref_origins + 3 * i, wh->read_in.p, n_read[i], read_origins + 3 * i,
-                                resolution, &ov, nullptr);
+        if (!r) r = run_overlap(wh, wh->ref_in.p, n_ref[i], oa, wh->read_in.p, n_read[i], ob, resolution, &ov, nullptr);
         if (out_overlap) out_overlap[i] = ov;
-        if (!r) {
+        bool skip = false;
+        if (!r && risk) {
+          // computeAlignmentRisk (app.cpp:143-185); the registration runs only when the risk is at most the threshold (:241-243)
+          float fov = 0.f, al = 0.f;
+          double rk = 0.0;
+          aicp_b200_prefilter_config pcfg;
+          aicp_b200_prefilter_default_config(&pcfg);
+          r = run_fov_overlap(wh, wh->ref_in.p, n_ref[i], wh->read_in.p, n_read[i], risk->ref_poses + 16 * i, risk->read_poses + 16 * i,
+                              risk->range, risk->angular_view, &fov, nullptr);
+          if (!r) r = run_alignability(wh, wh->al_fov[0].p, wh->al_fov_n[0], wh->al_fov[1].p, wh->al_fov_n[1], risk->ref_poses + 16 * i,
+                                       risk->read_poses + 16 * i, &pcfg, &al, nullptr, nullptr);
+          const double feat[2] = {(double)ov, (double)al};
+          if (!r) r = svm_predict(wh, feat, 1, 2, &rk, nullptr);
+          if (risk->out_alignability) risk->out_alignability[i] = al;
+          if (risk->out_risk) risk->out_risk[i] = rk;
+          skip = !r && rk > risk->threshold;
+          if (skip) {
+            for (int q = 0; q < 16; ++q) out_T[16 * i + q] = (q % 5 == 0) ? 1.f : 0.f;       // T stays the identity it was created as (app.cpp:356)
+            if (stats) memset(stats + i, 0, sizeof(aicp_b200_stats));
+          }
+        }
+        if (!r && !skip) {
           wh->cfg.ratio = aicp_b200_autotune_ratio(ov);
           wh->n_ref = n_ref[i]; wh->n_read = n_read[i];
           r = run_registration(wh, nullptr, true, stats ? stats + i : nullptr, out_T + 16 * i);

@@ -135,6 +135,7 @@ struct Handle {
 
   Comm* comm = nullptr;
   SvmModel* svm = nullptr;
+  std::string svm_path;          // model loaded into a batch worker
 
   // batch workers: one child handle (own stream + buffers) per concurrent registration
   std::vector<Handle*> workers;

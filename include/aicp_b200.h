@@ -316,6 +316,18 @@ int aicp_b200_aicp_batch(aicp_b200_handle* h, int64_t n_pairs, const float* cons
                          const double* read_origins, double resolution, int streams, float* out_T, float* out_overlap,
                          aicp_b200_stats* stats, int32_t* status, float* batch_ms);
 
+/* The same with the alignment-risk gate: App::runAicpPipeline with failure_prediction_mode (app.cpp:218-247) for many
+ * independent pairs -- BASELINE.json config 5 ("overlap + alignment-risk"): per pair the octree overlap, computeAlignmentRisk
+ * (FOV overlap -> alignability -> SVM on (overlap, alignability)), and the registration with the auto-tuned ratio ONLY when the
+ * risk is at most risk_threshold (:241-243); a skipped pair returns the identity and zeroed stats.
+ * ref_poses / read_poses: n_pairs x 16 doubles (column-major sensor poses; their translations are the overlap's ray origins).
+ * svm_model_path: OpenCV model file (see aicp_b200_svm_load).  out_overlap / out_alignability / out_risk: nullable. */
+int aicp_b200_pipeline_batch(aicp_b200_handle* h, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                             const double* ref_poses, const float* const* read_xyzw, const int64_t* n_read, const double* read_poses,
+                             double resolution, float sensor_range, float angular_view, const char* svm_model_path, double risk_threshold,
+                             int streams, float* out_T, float* out_overlap, float* out_alignability, double* out_risk,
+                             aicp_b200_stats* stats, int32_t* status, float* batch_ms);
+
 /* ---- multi-GPU single registration (BASELINE.json config 4: reading sharded, reference replicated) ---------------
  * nccl_unique_id: the 128-byte ncclUniqueId obtained on rank 0 with aicp_b200_comm_unique_id and broadcast by the
  * caller (e.g. torch.distributed).  After comm_init, aicp_b200_register* calls on every rank take that rank's SHARD of

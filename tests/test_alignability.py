@@ -184,3 +184,45 @@ def test_compute_alignment_risk_chain(orc, al, pair_cache):
     # tiny inputs go through without clusters: alignability 0
     fov, ali, risk = al.computeAlignmentRisk(p["ref"][:20], p["read"][:20], PA, PB, 30.0, 270.0, 50.0)
     assert ali == 0.0
+
+
+@pytest.mark.gpu
+def test_pipeline_batch_with_risk_gate(orc, pair_cache):
+    """aicp_b200_pipeline_batch = App::runAicpPipeline with failure_prediction_mode per pair (app.cpp:218-247): overlap ->
+    alignment risk -> registration only when risk <= threshold; every number against the oracle."""
+    from oracle import aicp_oracle_svm as svm_orc
+    rng = np.random.default_rng(9)
+    pairs, poses = [], []
+    for t in range(3):
+        p = pair_cache(2, t, 16384)
+        pairs.append((p["ref"], p["read"])); poses.append((pose(p["ref_origin"]), pose(p["read_origin"])))
+    cor = corridor(rng, 20000, end_wall=True)
+    pairs.append((cor, corridor(rng, 20000, end_wall=True, shift=(0.05, 0.01, 0)))); poses.append((pose([3.0, 0.2, 1.0]), pose([3.05, 0.21, 1.0])))
+    rb = room_box(rng, 20000)
+    pairs.append((rb, room_box(rng, 20000, shift=(0.05, 0.02, 0)))); poses.append((pose([3.0, 3.0, 1.5]), pose([3.05, 3.02, 1.5])))
+    model = svm_orc.load_model(DEFAULT_MODEL)
+    want = []
+    for (a, b), (PA, PB) in zip(pairs, poses):
+        ov, _ = orc.overlap(a, PA[:3, 3], b, PB[:3, 3])
+        _, fa, fb = orc.fov_overlap(a, b, PA, PB, 30.0, 270.0)
+        al, _, _ = orc.alignability(fa, fb, PA, PB, threads=8)
+        risk = svm_orc.test(model, np.array([[float(ov), float(al)]]))[0]
+        want.append((ov, al, risk))
+    thr = float(np.median([w[2] for w in want]))
+    reg = ab.B200Registration(device=0)
+    try:
+        for streams in (1, 3):
+            T, ov, al, risk, stats, status, ms = reg.pipelineBatch(pairs, poses, DEFAULT_MODEL, 30.0, 270.0, risk_threshold=thr, streams=streams)
+            assert not status.any() and ms > 0
+            n_skipped = 0
+            for i, ((a, b), w) in enumerate(zip(pairs, want)):
+                assert ov[i] == w[0] and al[i] == w[1] and abs(risk[i] - w[2]) <= 1e-6
+                if risk[i] > thr:
+                    n_skipped += 1
+                    assert np.array_equal(T[i], np.eye(4, dtype=np.float32)) and stats[i].iterations == 0
+                else:
+                    o = orc.icp(a, b, orc.default_config(ratio=ab.autotune_ratio(float(w[0])), threads=8))
+                    assert o.rc == 0 and stats[i].iterations == o.iterations and np.array_equal(T[i], o.T)
+            assert 0 < n_skipped < len(pairs)
+    finally:
+        reg.close()

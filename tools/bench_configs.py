@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="2,4,4crop,5,5step,overlap,prefilter,risk")
+    ap.add_argument("--configs", default="2,4,4crop,5,5step,5risk,overlap,prefilter,risk")
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--map-points", type=int, default=10485760)
     args = ap.parse_args()
@@ -84,6 +84,27 @@ def main():
                           "metric": "AICP steps/sec", "value": 4096 / (ms * 1e-3), "unit": "steps/s", "device_ms": ms, "wall_s": wall,
                           "overlap_pct_range": [float(ovp.min()), float(ovp.max())], "failed": int(np.count_nonzero(status)),
                           "streams": args.streams, "inputs": "device-resident"}), flush=True)
+    if "5risk" in want:
+        # BASELINE config 5 as written: "overlap + alignment-risk" per pair, then the registration (App::runAicpPipeline with
+        # failure_prediction_mode); threshold 1.0 so that every pair is also registered (the full cost per pair)
+        model = os.path.join(ROOT, "tests", "golden", "svm_models", "svm_1000training_thresh50_cross_validation_opencv3.xml")
+        pairs5 = [synth.make_pair(5, t) for t in range(16)]
+        d5 = [(dev(p["ref"]), dev(p["read"])) for p in pairs5]
+        poses5 = [(synth.rigid(*p["ref_origin"]), synth.rigid(*p["read_origin"])) for p in pairs5]
+        n5 = 1024
+        order = [i % 16 for i in range(n5)]
+        reg.setConfig(max_iterations=20); reg.setProfiling(0)
+        reg.pipelineBatch([d5[i] for i in order[:32]], [poses5[i] for i in order[:32]], model, 100.0, 360.0, 1.0, streams=args.streams)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        T, ovp, alp, risk, stats, status, ms = reg.pipelineBatch([d5[i] for i in order], [poses5[i] for i in order], model, 100.0, 360.0, 1.0,
+                                                                 streams=args.streams)
+        wall = time.perf_counter() - t0
+        print(json.dumps({"config": "C5 validation sweep with overlap + alignment risk: %d pipeline steps (overlap -> FOV overlap -> alignability -> SVM -> registration) of cube pairs" % n5,
+                          "metric": "AICP pipeline steps/sec", "value": n5 / (ms * 1e-3), "unit": "steps/s", "device_ms": ms, "wall_s": wall,
+                          "overlap_pct_range": [float(ovp.min()), float(ovp.max())], "alignability_pct_range": [float(alp.min()), float(alp.max())],
+                          "risk_range": [float(risk.min()), float(risk.max())], "pairs_with_risk_above_0.5": int((risk > 0.5).sum()),
+                          "failed": int(np.count_nonzero(status)), "streams": args.streams, "inputs": "device-resident"}), flush=True)
     if "overlap" in want:
         p = synth.make_pair(3, 0)
         r, q = dev(p["ref"]), dev(p["read"])
