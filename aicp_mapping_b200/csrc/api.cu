@@ -803,4 +803,15 @@ int aicp_b200_aicp_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* con
                     out_overlap, stats, status, batch_ms);
 }
 
+int aicp_b200_pipeline_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
+                             const double* ref_poses, const float* const* read_xyzw, const int64_t* n_read, const double* read_poses,
+                             double resolution, float sensor_range, float angular_view, const char* svm_model_path, double risk_threshold,
+                             int streams, float* out_T, float* out_overlap, float* out_alignability, double* out_risk,
+                             aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
+  if (!ref_poses || !read_poses || !svm_model_path || !*svm_model_path) return AICP_B200_ERR_BAD_ARG;
+  RiskArgs ra{ref_poses, read_poses, sensor_range, angular_view, svm_model_path, risk_threshold, out_alignability, out_risk};
+  return batch_impl(hh, n_pairs, ref_xyzw, n_ref, read_xyzw, n_read, nullptr, nullptr, nullptr, resolution, streams, out_T, out_overlap,
+                    stats, status, batch_ms, &ra);
+}
+
 }  // extern "C"
