@@ -141,6 +141,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->pf_label.release(); h->pf_seed_pos.release(); h->pf_labels_out.release();
   h->pf_mutual.release(); h->pf_parent.release(); h->pf_root.release(); h->pf_clabel.release();
   svm_release(h);
+  h->acc.release(); h->acc_tmp.release();
   h->al_moved.release(); h->al_mean.release(); h->al_ext.release(); h->al_sums.release(); h->al_cnt.release(); h->al_counts.release(); h->al_axes.release();
   for (int i = 0; i < 2; ++i) { h->al_fov[i].release(); h->al_pts[i].release(); h->al_lab[i].release(); h->al_boxes[i].release(); }
   if (h->pf_meta) cudaFree(h->pf_meta);
@@ -549,6 +550,60 @@ int aicp_b200_map_prefilter(aicp_b200_handle* hh, const aicp_b200_prefilter_conf
   h->map_n = h->pf_n_out;
   if (n_out) *n_out = h->pf_n_out;
   return AICP_B200_OK;
+}
+
+int aicp_b200_accumulate_sweep(aicp_b200_handle* hh, const float* sweep_xyzw, int64_t n, float box_half, const double body_pose[16],
+                               int clear_first, int64_t* n_added) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n < 0 || (n > 0 && !sweep_xyzw) || !body_pose || !(box_half > 0.f) || n > (1ll << 28))
+    return fail(h, AICP_B200_ERR_BAD_ARG, "accumulate_sweep: bad arguments");
+  const float4* pts = nullptr;
+  int rc;
+  if (n > 0 && (rc = upload_points(h, h->tmp_a, sweep_xyzw, n, &pts))) return rc;
+  int64_t added = 0;
+  rc = run_accumulate_sweep(h, pts, n, box_half, body_pose, clear_first, &added);
+  if (n_added) *n_added = added;
+  return rc;
+}
+
+const float* aicp_b200_get_accumulated(aicp_b200_handle* hh, int64_t* n_out) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return nullptr;
+  if (n_out) *n_out = h->acc_n;
+  return reinterpret_cast<const float*>(h->acc.p);
+}
+
+int aicp_b200_download_accumulated(aicp_b200_handle* hh, float* xyzw, int64_t n) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n != h->acc_n || (n > 0 && !xyzw)) return fail(h, AICP_B200_ERR_BAD_ARG, "download_accumulated: %lld points are accumulated", (long long)h->acc_n);
+  if (n == 0) return AICP_B200_OK;
+  return download(h, xyzw, h->acc.p, sizeof(float4) * (size_t)n);
+}
+
+int aicp_b200_read_pcd(const char* path, float* out_xyzw, int64_t capacity, int64_t* n_out, char* err, int err_len) {
+  if (!path || !n_out) return AICP_B200_ERR_BAD_ARG;
+  std::string e;
+  int rc = read_pcd(path, out_xyzw, capacity, n_out, &e);
+  if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
+  return rc;
+}
+
+int aicp_b200_write_pcd(const char* path, const float* xyzw, int64_t n, char* err, int err_len) {
+  if (!path || n < 0 || (n > 0 && !xyzw)) return AICP_B200_ERR_BAD_ARG;
+  std::string e;
+  int rc = write_pcd_binary(path, xyzw, n, &e);
+  if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
+  return rc;
+}
+
+int aicp_b200_read_pose_file(const char* path, int64_t* rows, double* poses, int64_t capacity, int64_t* n_out, char* err, int err_len) {
+  if (!path || !n_out) return AICP_B200_ERR_BAD_ARG;
+  std::string e;
+  int rc = read_pose_file(path, rows, poses, capacity, n_out, &e);
+  if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
+  return rc;
 }
 
 int aicp_b200_fov_overlap(aicp_b200_handle* hh, const float* a_xyzw, int64_t n_a, const float* b_xyzw, int64_t n_b, const double pose_a[16],

@@ -133,6 +133,10 @@ struct Handle {
   DevBuf<unsigned int> al_cnt, al_counts;
   DevBuf<float> al_axes, al_boxes[2];
 
+  // sweep accumulation (ingest.cu)
+  DevBuf<float4> acc, acc_tmp;
+  int64_t acc_n = 0;
+
   Comm* comm = nullptr;
   SvmModel* svm = nullptr;
   std::string svm_path;          // model loaded into a batch worker
@@ -174,6 +178,12 @@ int run_fov_overlap(Handle* h, const float4* A, int64_t nA, const float4* B, int
                     float range, float angular_view, float* overlap_pct, int64_t* counts);
 int run_alignability(Handle* h, const float4* A, int64_t nA, const float4* B, int64_t nB, const double* poseA, const double* poseB,
                      const aicp_b200_prefilter_config* cfg, float* out_alignability, int32_t* matching, int64_t* info);
+// ---- ingest.cu
+int run_accumulate_sweep(Handle* h, const float4* sweep, int64_t n, float half, const double* body_pose, int clear_first, int64_t* n_added);
+void pose_to_float_transform(const double* pose, float* T);
+int read_pcd(const char* path, float* out, int64_t cap, int64_t* n_out, std::string* err);
+int write_pcd_binary(const char* path, const float* xyzw, int64_t n, std::string* err);
+int read_pose_file(const char* path, int64_t* rows_out, double* poses_out, int64_t cap, int64_t* n_out, std::string* err);
 // ---- svm.cu
 int svm_load(Handle* h, const char* path);
 int svm_parse_summary(const char* path, aicp_b200_svm_summary* out, std::string* err);

@@ -240,6 +240,27 @@ int aicp_b200_voxel_grid(aicp_b200_handle* h, const float* xyzw, int64_t n, floa
 /* the periodic re-filter of the merged map (app.cpp:486-493): map <- prefilter(map), all on the device */
 int aicp_b200_map_prefilter(aicp_b200_handle* h, const aicp_b200_prefilter_config* cfg, int64_t* n_out, aicp_b200_prefilter_info* info);
 
+/* ---- ingest ----------------------------------------------------------------------------------------
+ * replaces: VelodyneAccumulatorROS::processLidar   aicp_ros/src/velodyne_accumulator.cpp:31-73: crop the sweep to +-box_half
+ *           (30 m, :59-60) around the sensor, transformPointCloud with (body_pose.translation().cast<float>(),
+ *           Quaternionf(body_pose.rotation().cast<float>())) (:62-63), append to the accumulated cloud (:66).
+ * body_pose: 16 doubles column-major (inertial <- sensor).  clear_first: start a new accumulation (clearCloud, :76-81).
+ * The accumulated cloud stays on the device: aicp_b200_get_accumulated returns its address (valid until the next accumulate
+ * call), to be passed to aicp_b200_prefilter / aicp_b200_register as a device cloud; download_accumulated copies it out. */
+int aicp_b200_accumulate_sweep(aicp_b200_handle* h, const float* sweep_xyzw, int64_t n, float box_half, const double body_pose[16],
+                               int clear_first, int64_t* n_added);
+const float* aicp_b200_get_accumulated(aicp_b200_handle* h, int64_t* n_out);
+int aicp_b200_download_accumulated(aicp_b200_handle* h, float* xyzw, int64_t n);
+/* replaces: pcl::io::loadPCDFile<pcl::PointXYZ>(path, cloud) as the replay uses it (app.cpp:269) and the PCD writers of the tools
+ * (cloudIO.cpp:64, create_cube_cloud.cpp:84).  PCD v0.7, DATA ascii or binary, float32 x y z fields; no handle, no CUDA.
+ * read: out_xyzw NULL returns the point count only. */
+int aicp_b200_read_pcd(const char* path, float* out_xyzw, int64_t capacity, int64_t* n_out, char* err, int err_len);
+int aicp_b200_write_pcd(const char* path, const float* xyzw, int64_t n, char* err, int err_len);
+/* replaces: PoseFileReader::readPoseFile   aicp_core/include/aicp_utils/poseFileReader.hpp:46-78 (aicp_input_poses.csv of the
+ * replay format, app.cpp:250-279): rows "counter, sec, nsec, x, y, z, qx, qy, qz, qw".  rows: n x 3 (counter, sec, nsec);
+ * poses: n x 16 doubles column-major.  rows / poses NULL returns the row count only. */
+int aicp_b200_read_pose_file(const char* path, int64_t* rows, double* poses, int64_t capacity, int64_t* n_out, char* err, int err_len);
+
 /* ---- FOV overlap filter + alignability ---------------------------------------------------------------
  * replaces: overlapFilter(cloudA, cloudB, poseA, poseB, range, angularView, accepted_pointsA, accepted_pointsB)
  *           aicp_core/src/utils/filteringUtils.cpp:111-193 (App::computeAlignmentRisk, app.cpp:153-156): the points of each cloud

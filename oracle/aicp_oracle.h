@@ -159,6 +159,10 @@ void orc_euler_angles_012(const float* R_rowmajor9, float* rpy);
 int orc_alignability(const float* A, int64_t nA, const float* B, int64_t nB, const double* poseA, const double* poseB,
                      const orc_prefilter_config* cfg, int threads, float* out_alignability, int32_t* matching, int64_t* info);
 
+/* ---- sweep accumulation (velodyne_accumulator.cpp:31-73), see aicp_oracle_ingest.c ---- */
+void orc_pose_to_float_transform(const double* pose_colmajor16, float* T_colmajor16);
+int64_t orc_accumulate_sweep(const float* sweep, int64_t n, float half, const double* body_pose, float* out);
+
 /* ---- text glue KATs ---- */
 /* app.cpp:198-202 clamp + fileIO.cpp:194-198 "%g"-style 6-digit print + float re-parse */
 float orc_autotune_ratio(float overlap_pct, char* text_out /* >=32 bytes, nullable */);

@@ -36,7 +36,7 @@ class IcpResult(C.Structure):
 
 def build(force=False):
     """Compile the oracle with oracle/Makefile (gcc)."""
-    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle_filters.c", "aicp_oracle_prefilter.c", "aicp_oracle_alignability.c", "aicp_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("aicp_oracle.c", "aicp_oracle_overlap.c", "aicp_oracle_filters.c", "aicp_oracle_prefilter.c", "aicp_oracle_alignability.c", "aicp_oracle_ingest.c", "aicp_oracle.h", "Makefile")]
     if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return _LIB_PATH
     subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
@@ -359,3 +359,26 @@ def alignability(cloudA, cloudB, poseA, poseB, cfg=None, threads=1):
                                 C.byref(cfg), int(threads), C.byref(al), _ptr(matching, C.c_int32), _ptr(info, C.c_int64))
     _check(rc, "alignability")
     return np.float32(al.value), matching[:info[1]].copy(), tuple(int(x) for x in info)
+
+
+# ---- sweep accumulation (aicp_oracle_ingest.c): velodyne_accumulator.cpp:31-73 ----
+def pose_to_float_transform(pose):
+    """Translation3f(t) * Quaternionf(R) as a 4x4 float32 matrix (numpy row-major view)."""
+    T = np.zeros(16, dtype=np.float32)
+    P = _pose16(pose)
+    lib().orc_pose_to_float_transform(_ptr(P, C.c_double), _ptr(T))
+    return T.reshape(4, 4).T.copy()
+
+
+def accumulate_sweeps(sweeps, poses, half=30.0):
+    """VelodyneAccumulatorROS::processLidar over a batch: returns the accumulated cloud (n x 4 float32)."""
+    L = lib()
+    L.orc_accumulate_sweep.restype = C.c_int64
+    parts = []
+    for sw, pose in zip(sweeps, poses):
+        a = to_xyzw(sw)
+        out = np.zeros((max(a.shape[0], 1), 4), dtype=np.float32)
+        P = _pose16(pose)
+        m = L.orc_accumulate_sweep(_ptr(a), C.c_int64(a.shape[0]), C.c_float(half), _ptr(P, C.c_double), _ptr(out))
+        parts.append(out[:m].copy())
+    return np.concatenate(parts, 0) if parts else np.zeros((0, 4), np.float32)
