@@ -402,3 +402,22 @@ def test_map_prefilter_on_device(orc):
         assert np.array_equal(m.download().view(np.uint32), o.cloud.view(np.uint32))
     finally:
         m.close()
+
+
+@pytest.mark.gpu
+def test_voxel_grid_and_prefilter_at_map_scale(orc, pf):
+    """2 M-point campus map (the C4 map generator at reduced size): parity with the oracle at a size where tiles, scans and the
+    sort run many blocks deep, plus properties that hold at any size."""
+    case = synth.make_map_case(n_map=2 * 1024 * 1024, n_read=1024, trial=1, n_poses=1)
+    cloud = case["map"]
+    got = pf.voxelGrid(cloud)
+    want = orc.voxel_grid(cloud)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    cen, counts = numpy_voxel_grid(cloud)
+    assert counts.sum() == cloud.shape[0] and got.shape[0] == counts.size
+    out = pf.filter(cloud)
+    o = orc.prefilter(cloud, threads=8)
+    assert np.array_equal(out.view(np.uint32), o.cloud.view(np.uint32))
+    sampled, normals, labels, clusters = pf.segments()
+    assert all(len(c) >= 50 for c in clusters) and sum(len(c) for c in clusters) == out.shape[0]
+    assert np.all(np.abs(np.linalg.norm(normals[:, :3], axis=1) - 1.0) < 1e-5)

@@ -8,6 +8,8 @@
       (reported), then registrations/s and ms per registration with the map resident
   C5  validation sweep: 4096 registrations of 38 400-point cube pairs (16 distinct perturbations cycled), batched
   overlap  the octree-overlap parameter of the C3 pair (ms per call, voxel counts)
+  voxelmap  the periodic re-filter of the merged map (app.cpp:486-493) at C4 size: VoxelGrid alone and the whole pre-filter on the
+      10 485 760-point map, device-resident, against the HBM roofline
   risk  App::computeAlignmentRisk (FOV overlap -> alignability -> SVM) for the C2 and C3 pairs, ms per call, CPU oracle beside it
   prefilter  regionGrowingUniformPlaneSegmentationFilter (VoxelGrid 0.08 + k-30 normals + region growing) on the raw clouds
       App feeds it: 7 accumulated VLP-16 sweeps (~200 k points) and one HDL-64 sweep (~250 k points); ms per call, the
@@ -15,6 +17,7 @@
 All inputs are device-resident when timing starts unless the line says e2e.  Single GPU; see bench.py for multi-GPU.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -28,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="2,4,4crop,5,5step,5risk,overlap,prefilter,risk")
+    ap.add_argument("--configs", default="2,4,4crop,5,5step,5risk,overlap,prefilter,risk,voxelmap")
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--map-points", type=int, default=10485760)
     args = ap.parse_args()
@@ -160,6 +163,50 @@ def main():
                               "cpu_oracle_ms": cpu_ms, "cpu_cores": ncpu, "bit_identical_to_oracle": same,
                               "clouds_per_s": 1e3 / (dev_ms / reps)}), flush=True)
         pf.close()
+    if "voxelmap" in want:
+        case = synth.make_map_case(n_map=args.map_points, n_read=1024, trial=0, n_poses=1)
+        mp = dev(case["map"])
+        n = int(mp.shape[0])
+        pf = ab.B200Prefilter(device=0)
+        out = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+        n_out = C.c_int64()
+        L = capi.lib()
+
+        def vg():
+            rc = L.aicp_b200_voxel_grid(pf._h, C.c_void_p(mp.data_ptr()), n, C.c_float(0.08), C.c_void_p(out.data_ptr()), C.byref(n_out))
+            assert rc == 0, L.aicp_b200_last_error(pf._h)
+        for _ in range(3):
+            vg()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            vg()
+        torch.cuda.synchronize()
+        vg_ms = (time.perf_counter() - t0) / reps * 1e3
+        m = int(n_out.value)
+        # algorithmic bytes: read 16 B/point, write + read the 8 B (key, index) pair once, 4 radix passes of 16 B/pair each way are
+        # the sort's own traffic (counted separately), gather 16 B/point for the centroids, 16 B/voxel written
+        alg = 16.0 * n + 8.0 * n + 16.0 * n + 16.0 * m
+        sort_bytes = 4 * 2 * 8.0 * n
+        for _ in range(2):
+            pf.filter(mp, keep_on_device=True)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            pf.filter(mp, keep_on_device=True)
+        pf_ms = (time.perf_counter() - t0) / 3 * 1e3
+        info = pf.info
+        peak = 6549.4
+        print(json.dumps({"config": "map re-filter at C4 size: %d-point map, 0.08 m voxels" % n, "metric": "ms per VoxelGrid of the map",
+                          "value": vg_ms, "unit": "ms", "voxels": m,
+                          "roofline": {"bound": "hbm", "algorithmic_bytes": alg, "achieved_GBps_wall": alg / (vg_ms * 1e-3) / 1e9, "peak_GBps": peak,
+                                       "frac_wall": alg / (vg_ms * 1e-3) / 1e9 / peak, "radix_sort_bytes_not_counted": sort_bytes,
+                                       "note": "wall clock of the synchronous C-ABI call, result left on the device"},
+                          "whole_prefilter_ms_wall": pf_ms, "whole_prefilter_device_ms": float(info.ms_total), "n_clusters": int(info.n_clusters),
+                          "n_out": int(info.n_out), "passes": int(info.passes), "inputs": "map device-resident"}), flush=True)
+        pf.close()
+        del mp, out
     if "risk" in want:
         from oracle import oracle as orc          # CPU baseline leg only
         from oracle import aicp_oracle_svm as svm_orc
