@@ -23,7 +23,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aic
            "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
            "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_prefilter_default_config", "aicp_b200_prefilter", "aicp_b200_get_prefiltered",
            "aicp_b200_prefilter_get_sampled", "aicp_b200_prefilter_get_normals", "aicp_b200_prefilter_get_labels", "aicp_b200_voxel_grid",
-           "aicp_b200_map_prefilter", "aicp_b200_accumulate_sweep", "aicp_b200_get_accumulated", "aicp_b200_download_accumulated", "aicp_b200_read_pcd",
+           "aicp_b200_map_prefilter", "aicp_b200_accumulate_sweep", "aicp_b200_get_accumulated", "aicp_b200_download_accumulated", "aicp_b200_read_pcd", "aicp_b200_read_ply",
            "aicp_b200_write_pcd", "aicp_b200_read_pose_file", "aicp_b200_fov_overlap", "aicp_b200_get_fov_filtered", "aicp_b200_alignability", "aicp_b200_alignment_risk",
            "aicp_b200_svm_parse", "aicp_b200_svm_load", "aicp_b200_svm_info", "aicp_b200_svm_predict", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_pipeline_batch", "aicp_b200_comm_unique_id",
            "aicp_b200_comm_init", "aicp_b200_comm_destroy"]
@@ -138,6 +138,7 @@ def lib():
         L.aicp_b200_get_accumulated.restype = C.c_void_p
         L.aicp_b200_download_accumulated.argtypes = [C.c_void_p, C.c_void_p, i64]
         L.aicp_b200_read_pcd.argtypes = [C.c_char_p, C.c_void_p, i64, C.POINTER(i64), C.c_char_p, C.c_int]
+        L.aicp_b200_read_ply.argtypes = [C.c_char_p, C.c_void_p, i64, C.POINTER(i64), C.c_char_p, C.c_int]
         L.aicp_b200_write_pcd.argtypes = [C.c_char_p, C.c_void_p, i64, C.c_char_p, C.c_int]
         L.aicp_b200_read_pose_file.argtypes = [C.c_char_p, C.POINTER(i64), dp, i64, C.POINTER(i64), C.c_char_p, C.c_int]
         L.aicp_b200_fov_overlap.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, dp, dp, C.c_float, C.c_float, C.c_void_p, C.c_void_p,

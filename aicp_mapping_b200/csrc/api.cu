@@ -590,6 +590,14 @@ int aicp_b200_read_pcd(const char* path, float* out_xyzw, int64_t capacity, int6
   return rc;
 }
 
+int aicp_b200_read_ply(const char* path, float* out_xyzw, int64_t capacity, int64_t* n_out, char* err, int err_len) {
+  if (!path || !n_out) return AICP_B200_ERR_BAD_ARG;
+  std::string e;
+  int rc = read_ply(path, out_xyzw, capacity, n_out, &e);
+  if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
+  return rc;
+}
+
 int aicp_b200_write_pcd(const char* path, const float* xyzw, int64_t n, char* err, int err_len) {
   if (!path || n < 0 || (n > 0 && !xyzw)) return AICP_B200_ERR_BAD_ARG;
   std::string e;

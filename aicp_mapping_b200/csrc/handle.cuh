@@ -182,6 +182,7 @@ int run_alignability(Handle* h, const float4* A, int64_t nA, const float4* B, in
 int run_accumulate_sweep(Handle* h, const float4* sweep, int64_t n, float half, const double* body_pose, int clear_first, int64_t* n_added);
 void pose_to_float_transform(const double* pose, float* T);
 int read_pcd(const char* path, float* out, int64_t cap, int64_t* n_out, std::string* err);
+int read_ply(const char* path, float* out, int64_t cap, int64_t* n_out, std::string* err);
 int write_pcd_binary(const char* path, const float* xyzw, int64_t n, std::string* err);
 int read_pose_file(const char* path, int64_t* rows_out, double* poses_out, int64_t cap, int64_t* n_out, std::string* err);
 // ---- svm.cu

@@ -10,6 +10,7 @@
 //   pcl::io::loadPCDFile<pcl::PointXYZ>  ->  read_pcd  (PCD v0.7 "ascii" and "binary" DATA, float32 x y z fields at any offset;
 //                                            "binary_compressed" is rejected with a message)
 //   PoseFileReader::readPoseFile (aicp_core/include/aicp_utils/poseFileReader.hpp:46-78)  ->  read_pose_file
+//   pcl::io::loadPLYFile<pcl::PointXYZ> of the prior map (aicp_ros/src/app_ros.cpp:301)     ->  read_ply
 // The readers are plain host code (file parsing is not GPU work); they are part of the library so that a replay needs nothing
 // else, and they are exposed without a handle so the CPU tests cover them.
 #include <math.h>
@@ -189,6 +190,98 @@ int write_pcd_binary(const char* path, const float* xyzw, int64_t n, std::string
              "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %lld\nDATA binary\n", (long long)n, (long long)n);
   for (int64_t i = 0; i < n; ++i) if (fwrite(xyzw + 4 * i, 4, 3, f) != 3) { fclose(f); *err = "short write"; return AICP_B200_ERR_CONFIG; }
   fclose(f);
+  return AICP_B200_OK;
+}
+
+// pcl::io::loadPLYFile<pcl::PointXYZ> as AppROS loads the prior map (aicp_ros/src/app_ros.cpp:301): the x, y, z properties of the
+// vertex element, "ascii" or "binary_little_endian"; the vertex element must come first (it does in every PLY PCL or CloudCompare
+// writes); elements after it (faces) are ignored.  float32 or float64 coordinates (converted to float32).
+int read_ply(const char* path, float* out, int64_t cap, int64_t* n_out, std::string* err) {
+  *n_out = 0;
+  std::ifstream f(path, std::ios::binary);
+  if (!f.good()) { *err = std::string("cannot open ") + path; return AICP_B200_ERR_CONFIG; }
+  std::string line, format;
+  long long n_vertex = -1;
+  bool in_vertex = false, seen_other_first = false, header_done = false;
+  struct Prop { std::string name; int size; char kind; };     // kind: f float, d double, i other scalar
+  std::vector<Prop> props;
+  auto type_info = [](const std::string& t, int* size, char* kind) -> bool {
+    if (t == "float" || t == "float32") { *size = 4; *kind = 'f'; return true; }
+    if (t == "double" || t == "float64") { *size = 8; *kind = 'd'; return true; }
+    if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") { *size = 1; *kind = 'i'; return true; }
+    if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") { *size = 2; *kind = 'i'; return true; }
+    if (t == "int" || t == "uint" || t == "int32" || t == "uint32") { *size = 4; *kind = 'i'; return true; }
+    return false;
+  };
+  if (!std::getline(f, line)) { *err = "PLY: empty file"; return AICP_B200_ERR_CONFIG; }
+  if (!line.empty() && line.back() == '\r') line.pop_back();
+  if (line != "ply") { *err = "PLY: missing magic line"; return AICP_B200_ERR_CONFIG; }
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    std::istringstream ls(line);
+    std::string key;
+    ls >> key;
+    if (key == "format") ls >> format;
+    else if (key == "element") {
+      std::string name; long long cnt = 0;
+      ls >> name >> cnt;
+      if (name == "vertex") { in_vertex = true; n_vertex = cnt; }
+      else { if (n_vertex < 0) seen_other_first = true; in_vertex = false; }
+    } else if (key == "property" && in_vertex) {
+      std::string t, name;
+      ls >> t;
+      if (t == "list") { *err = "PLY: list property in the vertex element"; return AICP_B200_ERR_CONFIG; }
+      ls >> name;
+      Prop p; p.name = name;
+      if (!type_info(t, &p.size, &p.kind)) { *err = "PLY: unknown property type " + t; return AICP_B200_ERR_CONFIG; }
+      props.push_back(p);
+    } else if (key == "end_header") { header_done = true; break; }
+  }
+  if (!header_done || n_vertex < 0) { *err = "PLY: header without a vertex element / end_header"; return AICP_B200_ERR_CONFIG; }
+  if (seen_other_first) { *err = "PLY: an element precedes the vertex element (not supported)"; return AICP_B200_ERR_CONFIG; }
+  int idx[3] = {-1, -1, -1}, off[3] = {0, 0, 0}, stride = 0;
+  for (size_t i = 0; i < props.size(); ++i) {
+    for (int d = 0; d < 3; ++d)
+      if (props[i].name == (d == 0 ? "x" : d == 1 ? "y" : "z")) {
+        if (props[i].kind == 'i') { *err = "PLY: x y z must be float or double properties"; return AICP_B200_ERR_CONFIG; }
+        idx[d] = (int)i; off[d] = stride;
+      }
+    stride += props[i].size;
+  }
+  if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0) { *err = "PLY: no x y z properties"; return AICP_B200_ERR_CONFIG; }
+  *n_out = n_vertex;
+  if (!out) return AICP_B200_OK;
+  if (cap < n_vertex) { *err = "PLY: output buffer too small"; return AICP_B200_ERR_BAD_ARG; }
+  if (format == "binary_little_endian") {
+    std::vector<char> rec((size_t)stride);
+    for (long long i = 0; i < n_vertex; ++i) {
+      f.read(rec.data(), stride);
+      if (f.gcount() != stride) { *err = "PLY: truncated binary data"; return AICP_B200_ERR_CONFIG; }
+      for (int d = 0; d < 3; ++d) {
+        if (props[(size_t)idx[d]].kind == 'f') memcpy(&out[4 * i + d], rec.data() + off[d], 4);
+        else { double v; memcpy(&v, rec.data() + off[d], 8); out[4 * i + d] = (float)v; }
+      }
+      out[4 * i + 3] = 1.0f;
+    }
+  } else if (format == "ascii") {
+    for (long long i = 0; i < n_vertex; ++i) {
+      if (!std::getline(f, line)) { *err = "PLY: truncated ascii data"; return AICP_B200_ERR_CONFIG; }
+      const char* p = line.c_str();
+      char* end = nullptr;
+      int got = 0;
+      for (size_t c = 0; c < props.size(); ++c) {
+        const double v = strtod(p, &end);
+        if (end == p) break;
+        for (int d = 0; d < 3; ++d) if (idx[d] == (int)c) { out[4 * i + d] = props[c].kind == 'f' ? strtof(p, nullptr) : (float)v; ++got; }
+        p = end;
+      }
+      if (got != 3) { *err = "PLY: malformed ascii vertex"; return AICP_B200_ERR_CONFIG; }
+      out[4 * i + 3] = 1.0f;
+    }
+  } else {
+    *err = "PLY: format " + format + " is not supported (ascii, binary_little_endian)";
+    return AICP_B200_ERR_CONFIG;
+  }
   return AICP_B200_OK;
 }
 

@@ -29,6 +29,19 @@ def readPCD(path):
     return out[:n.value].copy()
 
 
+def readPLY(path):
+    """pcl::io::loadPLYFile<pcl::PointXYZ> (the prior map, app_ros.cpp:301): n x 4 float32 (x, y, z, 1)."""
+    L, n, e = capi.lib(), C.c_int64(), _err()
+    rc = L.aicp_b200_read_ply(str(path).encode(), None, 0, C.byref(n), e, 512)
+    if rc:
+        raise capi.AicpError(rc, e.value.decode())
+    out = np.zeros((max(n.value, 1), 4), dtype=np.float32)
+    rc = L.aicp_b200_read_ply(str(path).encode(), C.c_void_p(out.ctypes.data), n.value, C.byref(n), e, 512)
+    if rc:
+        raise capi.AicpError(rc, e.value.decode())
+    return out[:n.value].copy()
+
+
 def writePCD(path, cloud):
     """pcl::PCDWriter::writeBinary of a pcl::PointXYZ cloud (cloudIO.cpp:64, create_cube_cloud.cpp:84)."""
     a = capi.to_xyzw(cloud)

@@ -255,6 +255,9 @@ int aicp_b200_download_accumulated(aicp_b200_handle* h, float* xyzw, int64_t n);
  * (cloudIO.cpp:64, create_cube_cloud.cpp:84).  PCD v0.7, DATA ascii or binary, float32 x y z fields; no handle, no CUDA.
  * read: out_xyzw NULL returns the point count only. */
 int aicp_b200_read_pcd(const char* path, float* out_xyzw, int64_t capacity, int64_t* n_out, char* err, int err_len);
+/* replaces: pcl::io::loadPLYFile<pcl::PointXYZ>(path, map)  aicp_ros/src/app_ros.cpp:301 (the prior map).  ascii or
+ * binary_little_endian, float / double x y z vertex properties, elements after the vertices ignored. */
+int aicp_b200_read_ply(const char* path, float* out_xyzw, int64_t capacity, int64_t* n_out, char* err, int err_len);
 int aicp_b200_write_pcd(const char* path, const float* xyzw, int64_t n, char* err, int err_len);
 /* replaces: PoseFileReader::readPoseFile   aicp_core/include/aicp_utils/poseFileReader.hpp:46-78 (aicp_input_poses.csv of the
  * replay format, app.cpp:250-279): rows "counter, sec, nsec, x, y, z, qx, qy, qz, qw".  rows: n x 3 (counter, sec, nsec);

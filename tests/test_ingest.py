@@ -78,6 +78,42 @@ def test_pcd_reader_rejects_what_it_does_not_implement(tmp_path):
         ab.readPCD(tmp_path / "missing.pcd")
 
 
+def test_ply_reader(tmp_path):
+    """The prior map is a PLY (app_ros.cpp:301): ascii and binary_little_endian, extra properties, double coordinates, faces after."""
+    rng = np.random.default_rng(6)
+    pts = rng.uniform(-80, 80, (500, 3)).astype(np.float32)
+    p = tmp_path / "a.ply"
+    with open(p, "wb") as f:
+        f.write(b"ply\nformat ascii 1.0\ncomment made by hand\nelement vertex 500\nproperty float x\nproperty float y\nproperty float z\n"
+                b"property uchar red\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n")
+        for q in pts:
+            f.write(("%r %r %r 255\n" % (float(q[0]), float(q[1]), float(q[2]))).encode())
+        f.write(b"3 0 1 2\n")
+    got = ab.readPLY(p)
+    assert got.shape == (500, 4) and np.array_equal(got[:, :3].view(np.uint32), pts.view(np.uint32)) and np.all(got[:, 3] == 1)
+    p = tmp_path / "b.ply"
+    rec = np.zeros(500, dtype=[("i", "<f4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("r", "u1")])
+    rec["x"], rec["y"], rec["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    with open(p, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 500\nproperty float intensity\nproperty float x\nproperty float y\n"
+                b"property float z\nproperty uchar ring\nend_header\n" + rec.tobytes())
+    assert np.array_equal(ab.readPLY(p)[:, :3].view(np.uint32), pts.view(np.uint32))
+    p = tmp_path / "c.ply"
+    rec = np.zeros(500, dtype=[("x", "<f8"), ("y", "<f8"), ("z", "<f8")])
+    rec["x"], rec["y"], rec["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    with open(p, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 500\nproperty double x\nproperty double y\nproperty double z\nend_header\n" + rec.tobytes())
+    assert np.array_equal(ab.readPLY(p)[:, :3], pts)
+    with open(p, "wb") as f:
+        f.write(b"ply\nformat binary_big_endian 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\nend_header\n" + b"\0" * 12)
+    with pytest.raises(ab.capi.AicpError, match="CONFIG"):
+        ab.readPLY(p)
+    with open(p, "wb") as f:
+        f.write(b"not a ply\n")
+    with pytest.raises(ab.capi.AicpError, match="CONFIG"):
+        ab.readPLY(p)
+
+
 def test_pose_file_reader_matches_scipy(tmp_path):
     from scipy.spatial.transform import Rotation
     rng = np.random.default_rng(2)
