@@ -294,6 +294,60 @@ inline bool regionGrowingUniformPlaneSegmentationFilterB200(aicp_b200_handle* h,
   return true;
 }
 
+// ---- classifier: stands where aicp::SVM stands (aicp_core/include/aicp_classification/svm.hpp:17-34) --------------------------
+// Compiled only when aicp_classification/abstract_classification.hpp has been included before this header.  The factory branch:
+//   } else if (parameters.type == "B200") { classifier.reset(new B200SVM(parameters)); }      (classification.hpp:12-16)
+#ifdef AICP_CLASSIFICATION_ABSTRACT_HPP_
+class B200SVM : public AbstractClassification {
+ public:
+  explicit B200SVM(const ClassificationParams& params) : params_(params), handle_(nullptr) {
+    if (aicp_b200_create(nullptr, -1, &handle_) != AICP_B200_OK)
+      std::cerr << "[B200] cannot create the classifier handle: " << aicp_b200_last_error(nullptr) << std::endl;
+  }
+  ~B200SVM() { if (handle_) aicp_b200_destroy(handle_); }
+
+  // cv::ml::SVM::trainAuto (svm.cpp:18-51) is the reference's offline tool; models it wrote are loaded with load()
+  virtual void train(const Eigen::MatrixXd&, const Eigen::MatrixXd&) {
+    std::cerr << "[B200] SVM::train is not provided: train with the reference's OpenCV tool and load() the saved model." << std::endl;
+  }
+  virtual void test(const Eigen::MatrixXd& testing_data, Eigen::MatrixXd* probabilities) {       // svm.cpp:46-51
+    Eigen::MatrixXd empty_labels = Eigen::MatrixXd::Zero(testing_data.rows(), 1);
+    test(testing_data, empty_labels, probabilities);
+  }
+  virtual void test(const Eigen::MatrixXd& testing_data, const Eigen::MatrixXd& labels, Eigen::MatrixXd* probabilities = NULL) {
+    if (params_.svm.saveFile.compare("") != 0) load(params_.svm.saveFile);                         // svm.cpp:61-63
+    const int64_t n = (int64_t)testing_data.rows();
+    const int32_t dim = (int32_t)testing_data.cols();
+    if (probabilities != NULL) probabilities->resize(n, 1);
+    if (n == 0 || !handle_) return;
+    std::vector<double> x((size_t)(n * dim)), p((size_t)n, 0.0);
+    for (int64_t i = 0; i < n; ++i) for (int32_t j = 0; j < dim; ++j) x[(size_t)(i * dim + j)] = testing_data(i, j);   // svm.cpp:72-74
+    const int rc = aicp_b200_svm_predict(handle_, x.data(), n, dim, p.data(), nullptr);
+    if (rc != AICP_B200_OK) { std::cerr << "[B200] SVM::test failed (" << rc << "): " << aicp_b200_last_error(handle_) << std::endl; return; }
+    unsigned int tp = 0u, fp = 0u, tn = 0u, fn = 0u;
+    const bool have_labels = !labels.isZero();
+    for (int64_t i = 0; i < n; ++i) {                                                               // svm.cpp:84-101
+      if (have_labels && p[(size_t)i] >= params_.svm.threshold) { if (labels(i, 0) == 1.0) ++tp; else ++fp; }
+      else { if (labels(i, 0) == 0.0) ++tn; else ++fn; }
+      if (probabilities != NULL) (*probabilities)(i, 0) = p[(size_t)i];
+    }
+    if (have_labels && probabilities != NULL && probabilities->rows() > 1) confusionMatrix(tp, tn, fp, fn);
+  }
+  virtual void save(const std::string&) {
+    std::cerr << "[B200] SVM::save is not provided (models are written by the reference's training tool)." << std::endl;
+  }
+  virtual void load(const std::string& filename) {                                                  // svm.cpp:103-107
+    if (!handle_) return;
+    const int rc = aicp_b200_svm_load(handle_, filename.c_str());
+    if (rc != AICP_B200_OK) std::cerr << "[B200] SVM::load failed (" << rc << "): " << aicp_b200_last_error(handle_) << std::endl;
+  }
+
+ private:
+  ClassificationParams params_;
+  aicp_b200_handle* handle_;
+};
+#endif
+
 }  // namespace aicp
 
 #endif

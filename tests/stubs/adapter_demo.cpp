@@ -2,12 +2,13 @@
 // (aicp_core/include/aicp_registration/abstract_registrator.hpp, aicp_overlap/abstract_overlapper.hpp) with stand-in
 // PCL/Eigen/octomap headers, then drives them the way App::runAicpPipeline does (app.cpp:218-247):
 //   overlap -> clamp to ratio -> rewrite YAML (done by the caller here) -> updateConfigParams -> registerClouds.
-// usage: adapter_demo <icp_yaml> <n_points>      prints "OK overlap=<pct> iterations=<n> T=<16 floats>"
+// usage: adapter_demo <icp_yaml> <n_points> [svm_model.xml]      prints "OK overlap=<pct> iterations=<n> T=<16 floats>"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
 
+#include "aicp_classification/abstract_classification.hpp"      // the reference's own header: enables B200SVM in the adapter
 #include "aicp_b200_adapter.hpp"
 
 // the two factory branches a maintainer adds to registration.hpp:11-17 / overlap.hpp:11
@@ -21,6 +22,13 @@ static std::unique_ptr<aicp::AbstractOverlapper> create_overlapper(const Overlap
   std::unique_ptr<aicp::AbstractOverlapper> o;
   if (p.type == "B200") o.reset(new aicp::B200Overlap(p));
   return o;
+}
+
+// classification.hpp:8-19 with the extra branch
+static std::unique_ptr<aicp::AbstractClassification> create_classifier(const ClassificationParams& p) {
+  std::unique_ptr<aicp::AbstractClassification> c;
+  if (p.type == "B200") c.reset(new aicp::B200SVM(p));
+  return c;
 }
 
 int main(int argc, char** argv) {
@@ -74,6 +82,17 @@ int main(int argc, char** argv) {
     aicp_b200_destroy(fh);
     if (!ok || filtered->points.empty() || filtered->points.size() > in->points.size()) return 7;
     std::printf("prefilter %zu -> %zu points\n", in->points.size(), filtered->points.size());
+  }
+  // the classifier as App::computeAlignmentRisk calls it (app.cpp:175-181): testing_data << overlap, alignability
+  if (argc > 3) {
+    ClassificationParams cp; cp.type = "B200"; cp.svm.threshold = 0.5; cp.svm.saveFile = argv[3];
+    auto classifier = create_classifier(cp);
+    if (!classifier) return 8;
+    Eigen::MatrixXd testing_data(1, 2), risk;
+    testing_data(0, 0) = 61.63; testing_data(0, 1) = 50.02;
+    classifier->test(testing_data, &risk);
+    if (risk.rows() != 1) return 9;
+    std::printf("risk %.9f\n", risk(0, 0));
   }
   auto* b = static_cast<aicp::B200Registration*>(registr.get());
   std::printf("OK overlap=%.4f iterations=%d T=", overlap, b->getStats().iterations);

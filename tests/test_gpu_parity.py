@@ -328,8 +328,14 @@ def test_cpp_adapter_demo():
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs", "build", "adapter_demo")
     if not os.path.exists(exe):
         pytest.skip("tests/stubs/build/adapter_demo was not built (needs the reference headers at build time)")
-    r = subprocess.run([exe, os.path.join(GOLDEN, "icp_autotuned_default.yaml"), "40"], capture_output=True, text=True, timeout=120)
+    model = os.path.join(GOLDEN, "svm_models", "svm_1000training_thresh50_cross_validation_opencv3.xml")
+    r = subprocess.run([exe, os.path.join(GOLDEN, "icp_autotuned_default.yaml"), "40", model], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+    # B200SVM : AbstractClassification through the factory branch, against the numpy oracle of cv::ml::SVM
+    from oracle import aicp_oracle_svm as svm_orc
+    risk = float([l for l in r.stdout.splitlines() if l.startswith("risk ")][0].split()[1])
+    assert abs(risk - svm_orc.test(svm_orc.load_model(model), np.array([[61.63, 50.02]]))[0]) <= 1e-6
+    assert "prefilter 9600 -> " in r.stdout
     line = [l for l in r.stdout.splitlines() if l.startswith("OK ")][0]
     T = np.array([float(x) for x in line.split("T=")[1].split()]).reshape(4, 4).T
     assert 4 <= int(line.split("iterations=")[1].split()[0]) <= 20
