@@ -161,8 +161,8 @@ def lib():
                                            C.POINTER(Stats), C.POINTER(C.c_int32), fp]
         L.aicp_b200_pipeline_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double),
                                                C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double), C.c_double, C.c_float, C.c_float,
-                                               C.c_char_p, C.c_double, C.c_int, fp, fp, fp, C.POINTER(C.c_double), C.POINTER(Stats),
-                                               C.POINTER(C.c_int32), fp]
+                                               C.c_char_p, C.c_double, C.c_int, C.c_int, fp, fp, fp, C.POINTER(C.c_double), C.POINTER(i64),
+                                               C.POINTER(Stats), C.POINTER(C.c_int32), fp]
         L.aicp_b200_comm_unique_id.argtypes = [C.c_void_p]
         L.aicp_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.aicp_b200_comm_destroy.argtypes = [C.c_void_p]

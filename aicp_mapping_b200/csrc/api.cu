@@ -733,6 +733,8 @@ struct RiskArgs {
   double threshold;
   float* out_alignability;
   double* out_risk;
+  int prefilter_first;           // the inputs are raw clouds: App::setAndFilterReading / filterCloud first (app.cpp:77-110)
+  int64_t* out_n_filtered;       // nullable, n_pairs x 2: points left after the pre-filter
 };
 
 static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
@@ -793,9 +795,29 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
         if (risk) for (int d = 0; d < 3; ++d) { origin_a[d] = risk->ref_poses[16 * i + 12 + d]; origin_b[d] = risk->read_poses[16 * i + 12 + d]; }
         if (!ref_xyzw[i] || !read_xyzw[i] || n_ref[i] < 1 || n_read[i] < 1 || n_ref[i] > (1ll << 30) || n_read[i] > (1ll << 30))
           r = fail(wh, AICP_B200_ERR_BAD_ARG, "aicp_batch: null or empty cloud in pair %lld", (long long)i);
-        if (!r) r = stage_owned(wh, wh->ref_in, ref_xyzw[i], n_ref[i]);
-        if (!r) r = stage_owned(wh, wh->read_in, read_xyzw[i], n_read[i]);
-        if (!r) r = run_overlap(wh, wh->ref_in.p, n_ref[i], oa, wh->read_in.p, n_read[i], ob, resolution, &ov, nullptr);
+        int64_t nr = n_ref[i], nq = n_read[i];
+        if (!r && risk && risk->prefilter_first) {
+          // both raw clouds through regionGrowingUniformPlaneSegmentationFilter; the filtered clouds never leave the device
+          aicp_b200_prefilter_config pcfg;
+          aicp_b200_prefilter_default_config(&pcfg);
+          const float* raw[2] = {ref_xyzw[i], read_xyzw[i]};
+          const int64_t raw_n[2] = {n_ref[i], n_read[i]};
+          DevBuf<float4>* dst[2] = {&wh->ref_in, &wh->read_in};
+          int64_t* cnt[2] = {&nr, &nq};
+          for (int c = 0; c < 2 && !r; ++c) {
+            const float4* pts;
+            r = upload_points(wh, wh->tmp_a, raw[c], raw_n[c], &pts);
+            if (!r) r = run_prefilter(wh, pts, raw_n[c], &pcfg, nullptr, nullptr);
+            if (!r && wh->pf_n_out < 1) r = fail(wh, AICP_B200_ERR_BAD_ARG, "pipeline_batch: the pre-filter left no points of a cloud of pair %lld", (long long)i);
+            if (!r) r = stage_owned(wh, *dst[c], reinterpret_cast<const float*>(wh->pf_out.p), wh->pf_n_out);
+            *cnt[c] = wh->pf_n_out;
+          }
+          if (risk->out_n_filtered) { risk->out_n_filtered[2 * i] = nr; risk->out_n_filtered[2 * i + 1] = nq; }
+        } else {
+          if (!r) r = stage_owned(wh, wh->ref_in, ref_xyzw[i], n_ref[i]);
+          if (!r) r = stage_owned(wh, wh->read_in, read_xyzw[i], n_read[i]);
+        }
+        if (!r) r = run_overlap(wh, wh->ref_in.p, nr, oa, wh->read_in.p, nq, ob, resolution, &ov, nullptr);
         if (out_overlap) out_overlap[i] = ov;
         bool skip = false;
         if (!r && risk) {
@@ -804,7 +826,7 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
           double rk = 0.0;
           aicp_b200_prefilter_config pcfg;
           aicp_b200_prefilter_default_config(&pcfg);
-          r = run_fov_overlap(wh, wh->ref_in.p, n_ref[i], wh->read_in.p, n_read[i], risk->ref_poses + 16 * i, risk->read_poses + 16 * i,
+          r = run_fov_overlap(wh, wh->ref_in.p, nr, wh->read_in.p, nq, risk->ref_poses + 16 * i, risk->read_poses + 16 * i,
                               risk->range, risk->angular_view, &fov, nullptr);
           if (!r) r = run_alignability(wh, wh->al_fov[0].p, wh->al_fov_n[0], wh->al_fov[1].p, wh->al_fov_n[1], risk->ref_poses + 16 * i,
                                        risk->read_poses + 16 * i, &pcfg, &al, nullptr, nullptr);
@@ -820,7 +842,7 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
         }
         if (!r && !skip) {
           wh->cfg.ratio = aicp_b200_autotune_ratio(ov);
-          wh->n_ref = n_ref[i]; wh->n_read = n_read[i];
+          wh->n_ref = nr; wh->n_read = nq;
           r = run_registration(wh, nullptr, true, stats ? stats + i : nullptr, out_T + 16 * i);
         }
       } else {
@@ -869,10 +891,11 @@ int aicp_b200_aicp_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* con
 int aicp_b200_pipeline_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
                              const double* ref_poses, const float* const* read_xyzw, const int64_t* n_read, const double* read_poses,
                              double resolution, float sensor_range, float angular_view, const char* svm_model_path, double risk_threshold,
-                             int streams, float* out_T, float* out_overlap, float* out_alignability, double* out_risk,
-                             aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
+                             int prefilter_first, int streams, float* out_T, float* out_overlap, float* out_alignability, double* out_risk,
+                             int64_t* out_n_filtered, aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
   if (!ref_poses || !read_poses || !svm_model_path || !*svm_model_path) return AICP_B200_ERR_BAD_ARG;
-  RiskArgs ra{ref_poses, read_poses, sensor_range, angular_view, svm_model_path, risk_threshold, out_alignability, out_risk};
+  RiskArgs ra{ref_poses, read_poses, sensor_range, angular_view, svm_model_path, risk_threshold, out_alignability, out_risk,
+              prefilter_first, out_n_filtered};
   return batch_impl(hh, n_pairs, ref_xyzw, n_ref, read_xyzw, n_read, nullptr, nullptr, nullptr, resolution, streams, out_T, out_overlap,
                     stats, status, batch_ms, &ra);
 }

@@ -250,9 +250,11 @@ class B200Registration:
         return (np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4)), ov, stats, status, float(ms.value)
 
     def pipelineBatch(self, pairs, poses, svm_model, sensor_range, angular_view, risk_threshold=0.5,
-                      resolution=float(np.float32(0.2)), streams=0):
+                      resolution=float(np.float32(0.2)), streams=0, prefilter_first=False):
         """aicp_b200_pipeline_batch: App::runAicpPipeline with failure_prediction_mode (app.cpp:218-247) per pair: overlap ->
         alignment risk -> registration when risk <= threshold.  `poses`: list of (ref_pose 4x4, read_pose 4x4).
+        prefilter_first: the clouds are raw; each is pre-filtered on the device first (app.cpp:77-110); self.n_filtered then holds
+        the filtered sizes [n, 2].
         Returns (T [n,4,4], overlap [n], alignability [n], risk [n], stats list, status array, batch_ms)."""
         n = len(pairs)
         keep, refs, reads = [], (C.c_void_p * n)(), (C.c_void_p * n)()
@@ -267,14 +269,16 @@ class B200Registration:
         T = np.zeros((n, 16), dtype=np.float32)
         ov, al = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
         risk = np.zeros(n, dtype=np.float64)
+        self.n_filtered = np.zeros((n, 2), dtype=np.int64)
         stats = (capi.Stats * n)()
         status = np.zeros(n, dtype=np.int32)
         ms = C.c_float()
         fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
         rc = self._lib.aicp_b200_pipeline_batch(self._h, n, refs, n_ref, pa.ctypes.data_as(dp), reads, n_read, pb.ctypes.data_as(dp),
                                                 C.c_double(resolution), C.c_float(sensor_range), C.c_float(angular_view),
-                                                str(svm_model).encode(), C.c_double(risk_threshold), int(streams), T.ctypes.data_as(fp),
-                                                ov.ctypes.data_as(fp), al.ctypes.data_as(fp), risk.ctypes.data_as(dp), stats,
+                                                str(svm_model).encode(), C.c_double(risk_threshold), int(bool(prefilter_first)), int(streams),
+                                                T.ctypes.data_as(fp), ov.ctypes.data_as(fp), al.ctypes.data_as(fp), risk.ctypes.data_as(dp),
+                                                self.n_filtered.ctypes.data_as(C.POINTER(C.c_int64)), stats,
                                                 status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
         self._check(rc)
         return ((np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4)), ov, al, risk, stats, status,

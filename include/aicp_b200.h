@@ -345,12 +345,15 @@ int aicp_b200_aicp_batch(aicp_b200_handle* h, int64_t n_pairs, const float* cons
  * (FOV overlap -> alignability -> SVM on (overlap, alignability)), and the registration with the auto-tuned ratio ONLY when the
  * risk is at most risk_threshold (:241-243); a skipped pair returns the identity and zeroed stats.
  * ref_poses / read_poses: n_pairs x 16 doubles (column-major sensor poses; their translations are the overlap's ray origins).
- * svm_model_path: OpenCV model file (see aicp_b200_svm_load).  out_overlap / out_alignability / out_risk: nullable. */
+ * svm_model_path: OpenCV model file (see aicp_b200_svm_load).  out_overlap / out_alignability / out_risk: nullable.
+ * prefilter_first != 0: the clouds are RAW (e.g. accumulated sweeps); every worker first runs the pre-filter on both
+ * (App::setAndFilterReading / filterCloud, app.cpp:77-110) and the rest of the step uses the filtered clouds, which never leave
+ * the device; out_n_filtered (nullable, n_pairs x 2) receives their sizes. */
 int aicp_b200_pipeline_batch(aicp_b200_handle* h, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
                              const double* ref_poses, const float* const* read_xyzw, const int64_t* n_read, const double* read_poses,
                              double resolution, float sensor_range, float angular_view, const char* svm_model_path, double risk_threshold,
-                             int streams, float* out_T, float* out_overlap, float* out_alignability, double* out_risk,
-                             aicp_b200_stats* stats, int32_t* status, float* batch_ms);
+                             int prefilter_first, int streams, float* out_T, float* out_overlap, float* out_alignability, double* out_risk,
+                             int64_t* out_n_filtered, aicp_b200_stats* stats, int32_t* status, float* batch_ms);
 
 /* ---- multi-GPU single registration (BASELINE.json config 4: reading sharded, reference replicated) ---------------
  * nccl_unique_id: the 128-byte ncclUniqueId obtained on rank 0 with aicp_b200_comm_unique_id and broadcast by the

@@ -226,3 +226,34 @@ def test_pipeline_batch_with_risk_gate(orc, pair_cache):
             assert 0 < n_skipped < len(pairs)
     finally:
         reg.close()
+
+
+@pytest.mark.gpu
+def test_pipeline_batch_from_raw_clouds(orc):
+    """prefilter_first: raw accumulated sweeps -> pre-filter x 2 -> overlap -> alignment risk -> registration, per pair, with the
+    filtered clouds resident on the device; every number against the oracle chain."""
+    from oracle import aicp_oracle_svm as svm_orc
+    model = svm_orc.load_model(DEFAULT_MODEL)
+    pairs, poses = [], []
+    for t in range(3):
+        a = synth.raw_sweep(2, 20 + t, n_sweeps=3)
+        E = synth.rigid(0.08, -0.05, 0.01, 0.0, 0.0, 0.02)
+        b_cloud = synth.apply_T(E, synth.raw_sweep(2, 20 + t, n_sweeps=4)["cloud"][5000:])
+        pairs.append((a["cloud"], b_cloud)); poses.append((pose(a["origin"]), pose(a["origin"] + [0.35, 0, 0])))
+    reg = ab.B200Registration(device=0)
+    try:
+        T, ov, al, risk, stats, status, ms = reg.pipelineBatch(pairs, poses, DEFAULT_MODEL, 30.0, 270.0, risk_threshold=1.0, streams=2,
+                                                               prefilter_first=True)
+        assert not status.any()
+        for i, ((a, b), (PA, PB)) in enumerate(zip(pairs, poses)):
+            fa, fb = orc.prefilter(a, threads=8).cloud, orc.prefilter(b, threads=8).cloud
+            assert list(reg.n_filtered[i]) == [fa.shape[0], fb.shape[0]]
+            o_ov, _ = orc.overlap(fa, PA[:3, 3], fb, PB[:3, 3])
+            _, ka, kb = orc.fov_overlap(fa, fb, PA, PB, 30.0, 270.0)
+            o_al, _, _ = orc.alignability(ka, kb, PA, PB, threads=8)
+            o_risk = svm_orc.test(model, np.array([[float(o_ov), float(o_al)]]))[0]
+            assert ov[i] == o_ov and al[i] == o_al and abs(risk[i] - o_risk) <= 1e-6
+            o = orc.icp(fa, fb, orc.default_config(ratio=ab.autotune_ratio(float(o_ov)), threads=8))
+            assert o.rc == 0 and stats[i].iterations == o.iterations and np.array_equal(T[i], o.T)
+    finally:
+        reg.close()

@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="2,4,4crop,5,5step,5risk,overlap,prefilter,risk,voxelmap")
+    ap.add_argument("--configs", default="2,4,4crop,5,5step,5risk,frames,overlap,prefilter,risk,voxelmap")
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--map-points", type=int, default=10485760)
     args = ap.parse_args()
@@ -108,6 +108,29 @@ def main():
                           "overlap_pct_range": [float(ovp.min()), float(ovp.max())], "alignability_pct_range": [float(alp.min()), float(alp.max())],
                           "risk_range": [float(risk.min()), float(risk.max())], "pairs_with_risk_above_0.5": int((risk > 0.5).sum()),
                           "failed": int(np.count_nonzero(status)), "streams": args.streams, "inputs": "device-resident"}), flush=True)
+    if "frames" in want:
+        # whole frames, batched: raw 7-sweep VLP-16 accumulations (201 600 points) in, per pair pre-filter x 2 -> overlap ->
+        # alignment risk -> registration, the filtered clouds never leaving the device (aicp_b200_pipeline_batch, prefilter_first)
+        model = os.path.join(ROOT, "tests", "golden", "svm_models", "svm_1000training_thresh50_cross_validation_opencv3.xml")
+        raws = [synth.raw_sweep(2, t) for t in range(4)]
+        E = synth.rigid(0.08, -0.05, 0.01, 0.0, 0.0, 0.02)
+        fr = [(dev(raws[k]["cloud"]), dev(synth.apply_T(E, raws[(k + 1) % 4]["cloud"]))) for k in range(4)]
+        fp = [(synth.rigid(*raws[k]["origin"]), synth.rigid(*raws[(k + 1) % 4]["origin"])) for k in range(4)]
+        nf = 128
+        order = [i % 4 for i in range(nf)]
+        reg.setConfig(max_iterations=20); reg.setProfiling(0)
+        reg.pipelineBatch([fr[i] for i in order[:16]], [fp[i] for i in order[:16]], model, 30.0, 270.0, 1.0, streams=args.streams, prefilter_first=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        T, ovp, alp, risk, stats, status, ms = reg.pipelineBatch([fr[i] for i in order], [fp[i] for i in order], model, 30.0, 270.0, 1.0,
+                                                                 streams=args.streams, prefilter_first=True)
+        wall = time.perf_counter() - t0
+        print(json.dumps({"config": "whole frames, batched: %d pairs of raw VLP-16 accumulations (201600 points each): pre-filter x 2 -> overlap -> alignment risk -> registration" % nf,
+                          "metric": "AICP frames/sec", "value": nf / (ms * 1e-3), "unit": "frames/s", "device_ms": ms, "wall_s": wall,
+                          "ms_per_frame": ms / nf, "filtered_points_first_pair": [int(x) for x in reg.n_filtered[0]],
+                          "overlap_pct_range": [float(ovp.min()), float(ovp.max())], "alignability_pct_range": [float(alp.min()), float(alp.max())],
+                          "iterations_mean": float(np.mean([s.iterations for s in stats])), "failed": int(np.count_nonzero(status)),
+                          "streams": args.streams, "inputs": "raw clouds device-resident"}), flush=True)
     if "overlap" in want:
         p = synth.make_pair(3, 0)
         r, q = dev(p["ref"]), dev(p["read"])
