@@ -98,5 +98,5 @@ def parse_model(filename):
     err = C.create_string_buffer(512)
     rc = capi.lib().aicp_b200_svm_parse(str(filename).encode(), C.byref(s), err, 512)
     if rc:
-        raise capi.AicpError(rc, err.value.decode())
+        raise capi.AicpError(rc, err.value.decode(errors="replace"))
     return s

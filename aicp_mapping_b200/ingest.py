@@ -21,11 +21,11 @@ def readPCD(path):
     L, n, e = capi.lib(), C.c_int64(), _err()
     rc = L.aicp_b200_read_pcd(str(path).encode(), None, 0, C.byref(n), e, 512)
     if rc:
-        raise capi.AicpError(rc, e.value.decode())
+        raise capi.AicpError(rc, e.value.decode(errors="replace"))
     out = np.zeros((max(n.value, 1), 4), dtype=np.float32)
     rc = L.aicp_b200_read_pcd(str(path).encode(), C.c_void_p(out.ctypes.data), n.value, C.byref(n), e, 512)
     if rc:
-        raise capi.AicpError(rc, e.value.decode())
+        raise capi.AicpError(rc, e.value.decode(errors="replace"))
     return out[:n.value].copy()
 
 
@@ -34,11 +34,11 @@ def readPLY(path):
     L, n, e = capi.lib(), C.c_int64(), _err()
     rc = L.aicp_b200_read_ply(str(path).encode(), None, 0, C.byref(n), e, 512)
     if rc:
-        raise capi.AicpError(rc, e.value.decode())
+        raise capi.AicpError(rc, e.value.decode(errors="replace"))
     out = np.zeros((max(n.value, 1), 4), dtype=np.float32)
     rc = L.aicp_b200_read_ply(str(path).encode(), C.c_void_p(out.ctypes.data), n.value, C.byref(n), e, 512)
     if rc:
-        raise capi.AicpError(rc, e.value.decode())
+        raise capi.AicpError(rc, e.value.decode(errors="replace"))
     return out[:n.value].copy()
 
 
@@ -48,7 +48,7 @@ def writePCD(path, cloud):
     e = _err()
     rc = capi.lib().aicp_b200_write_pcd(str(path).encode(), C.c_void_p(a.ctypes.data), a.shape[0], e, 512)
     if rc:
-        raise capi.AicpError(rc, e.value.decode())
+        raise capi.AicpError(rc, e.value.decode(errors="replace"))
 
 
 def readPoseFile(path):
@@ -56,13 +56,13 @@ def readPoseFile(path):
     L, n, e = capi.lib(), C.c_int64(), _err()
     rc = L.aicp_b200_read_pose_file(str(path).encode(), None, None, 0, C.byref(n), e, 512)
     if rc:
-        raise capi.AicpError(rc, e.value.decode())
+        raise capi.AicpError(rc, e.value.decode(errors="replace"))
     rows = np.zeros((max(n.value, 1), 3), dtype=np.int64)
     poses = np.zeros((max(n.value, 1), 16), dtype=np.float64)
     rc = L.aicp_b200_read_pose_file(str(path).encode(), rows.ctypes.data_as(C.POINTER(C.c_int64)), poses.ctypes.data_as(C.POINTER(C.c_double)),
                                     n.value, C.byref(n), e, 512)
     if rc:
-        raise capi.AicpError(rc, e.value.decode())
+        raise capi.AicpError(rc, e.value.decode(errors="replace"))
     return [(int(rows[i, 0]), int(rows[i, 1]), int(rows[i, 2]), poses[i].reshape(4, 4).T.copy()) for i in range(n.value)]
 
 
