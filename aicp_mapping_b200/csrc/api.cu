@@ -8,7 +8,6 @@
 #include <atomic>
 #include <string>
 #include <thread>
-#include <utility>
 #include <vector>
 
 #include "handle.cuh"
@@ -128,9 +127,6 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   for (Handle* w : h->workers) aicp_b200_destroy(reinterpret_cast<aicp_b200_handle*>(w));
   h->workers.clear();
   if (h->done_ev) cudaEventDestroy(h->done_ev);
-  if (h->copy_ev) cudaEventDestroy(h->copy_ev);
-  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-  h->ref_in_alt.release(); h->read_in_alt.release();
   for (int i = 0; i < 2; ++i) if (h->batch_ev[i]) cudaEventDestroy(h->batch_ev[i]);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_rec.release(); h->refc_cell.release(); h->normals.release(); h->knn_pos.release();
@@ -762,9 +758,6 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
     if (rc) return fail(h, rc, "register_batch: cannot create worker: %s", aicp_b200_last_error(nullptr));
     Handle* wh = reinterpret_cast<Handle*>(w);
     if (cudaEventCreate(&wh->done_ev) != cudaSuccess) return fail(h, AICP_B200_ERR_CUDA, "register_batch: event creation failed");
-    if (cudaStreamCreateWithFlags(&wh->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&wh->copy_ev, cudaEventDisableTiming) != cudaSuccess)
-      return fail(h, AICP_B200_ERR_CUDA, "register_batch: copy stream creation failed");
     h->workers.push_back(wh);
   }
   if (!h->batch_ev[0]) { CUDA_TRY(cudaEventCreate(&h->batch_ev[0])); CUDA_TRY(cudaEventCreate(&h->batch_ev[1])); }
@@ -780,7 +773,6 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
       wh->svm_path = risk->model_path;
     }
     CUDA_TRY(cudaStreamWaitEvent(wh->stream, h->batch_ev[0], 0));
-    if (wh->copy_stream) CUDA_TRY(cudaStreamWaitEvent(wh->copy_stream, h->batch_ev[0], 0));
   }
   std::atomic<int64_t> next(0);
   std::atomic<int> first_err(0);
@@ -788,18 +780,8 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
   auto work = [&](int w) {
     Handle* wh = h->workers[w];
     cudaSetDevice(wh->device);
-    // plain registrations from HOST buffers: while pair i runs, this worker's next pair is copied into a second set of staging
-    // buffers on a copy stream, so that no registration waits for its own 2 x n x 16 bytes of input
-    int64_t pre = -1;                 // pair claimed ahead by this worker
-    bool pre_staged = false;          // ... and already on its way into ref_in_alt / read_in_alt
-    auto valid_pair = [&](int64_t k) {
-      return ref_xyzw[k] && read_xyzw[k] && n_ref[k] >= 1 && n_read[k] >= 1 && n_ref[k] <= (1ll << 30) && n_read[k] <= (1ll << 30);
-    };
     for (;;) {
-      int64_t i;
-      bool staged = false;
-      if (pre >= 0) { i = pre; staged = pre_staged; pre = -1; pre_staged = false; }
-      else i = next.fetch_add(1);
+      int64_t i = next.fetch_add(1);
       if (i >= n_pairs) break;
       if (ratios) wh->cfg.ratio = ratios[i];
       int r = AICP_B200_OK;
@@ -864,33 +846,8 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
           r = run_registration(wh, nullptr, true, stats ? stats + i : nullptr, out_T + 16 * i);
         }
       } else {
-        if (!valid_pair(i))
-          r = fail(wh, AICP_B200_ERR_BAD_ARG, "registerClouds: null cloud or empty cloud (n_ref %lld, n_read %lld)", (long long)n_ref[i], (long long)n_read[i]);
-        if (!r) {
-          if (staged) {               // the copy was started while the previous pair ran: make the staging buffers current
-            std::swap(wh->ref_in, wh->ref_in_alt);
-            std::swap(wh->read_in, wh->read_in_alt);
-            if (cudaStreamWaitEvent(wh->stream, wh->copy_ev, 0) != cudaSuccess) r = fail(wh, AICP_B200_ERR_CUDA, "register_batch: cudaStreamWaitEvent failed");
-          } else {
-            r = stage_owned(wh, wh->ref_in, ref_xyzw[i], n_ref[i]);
-            if (!r) r = stage_owned(wh, wh->read_in, read_xyzw[i], n_read[i]);
-          }
-        }
-        // claim this worker's next pair now and start its copy (host buffers only; device inputs are copied in turn)
-        const int64_t nx = next.fetch_add(1);
-        if (nx < n_pairs) {
-          pre = nx;
-          if (wh->copy_stream && valid_pair(nx) && !is_device_ptr(ref_xyzw[nx]) && !is_device_ptr(read_xyzw[nx]) &&
-              wh->ref_in_alt.reserve((size_t)n_ref[nx]) == cudaSuccess && wh->read_in_alt.reserve((size_t)n_read[nx]) == cudaSuccess &&
-              cudaMemcpyAsync(wh->ref_in_alt.p, ref_xyzw[nx], sizeof(float4) * (size_t)n_ref[nx], cudaMemcpyHostToDevice, wh->copy_stream) == cudaSuccess &&
-              cudaMemcpyAsync(wh->read_in_alt.p, read_xyzw[nx], sizeof(float4) * (size_t)n_read[nx], cudaMemcpyHostToDevice, wh->copy_stream) == cudaSuccess &&
-              cudaEventRecord(wh->copy_ev, wh->copy_stream) == cudaSuccess)
-            pre_staged = true;
-        }
-        if (!r) {
-          wh->n_ref = n_ref[i]; wh->n_read = n_read[i];
-          r = run_registration(wh, nullptr, true, stats ? stats + i : nullptr, out_T + 16 * i);
-        }
+        r = aicp_b200_register(reinterpret_cast<aicp_b200_handle*>(wh), ref_xyzw[i], n_ref[i], read_xyzw[i], n_read[i], nullptr,
+                               out_T + 16 * i, stats ? stats + i : nullptr);
       }
       if (status) status[i] = r;
       if (r) {

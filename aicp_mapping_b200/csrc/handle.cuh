@@ -146,10 +146,6 @@ struct Handle {
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
   cudaEvent_t wait_ev = nullptr;     // set while a batch runs: the worker's first stream op waits on it
   cudaEvent_t done_ev = nullptr;
-  // batch workers, host inputs: second set of staging buffers + copy stream for the prefetch of the worker's next pair
-  DevBuf<float4> ref_in_alt, read_in_alt;
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t copy_ev = nullptr;
 };
 
 // ---- index.cu
