@@ -236,6 +236,32 @@ def test_min_label_fixed_point_equals_sequential_region_growing_random_digraphs(
     assert n_seq == n_par and np.array_equal(seq, par)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_min_label_fixed_point_equals_sequential_region_growing_geometric_digraphs(orc, seed):
+    """Between the two extremes above: k-NN graphs of clustered 2-D points (a mix of two-way and one-way edges, density jumps
+    make many edges one-way), noisy normals around a few directions so that the smoothness test cuts the graph irregularly."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(500 + seed)
+    m, k, n_nb = 4000, 12, 7
+    centres = rng.uniform(0, 10, (12, 2))
+    pts = np.concatenate([c + rng.normal(0, rng.uniform(0.05, 0.8), (m // 12 + 1, 2)) for c in centres])[:m]
+    _, knn = cKDTree(pts).query(pts, k=k)
+    knn = knn.astype(np.int32)
+    base = np.float32([[1, 0, 0], [0.9995, 0.0316, 0], [0.998, 0.0632, 0], [0, 1, 0]])
+    normals = np.zeros((m, 4), dtype=np.float32)
+    nn = base[rng.integers(0, len(base), m)] + rng.normal(0, 0.004, (m, 3)).astype(np.float32)
+    normals[:, :3] = nn / np.linalg.norm(nn, axis=1, keepdims=True)
+    normals[:, 3] = (rng.integers(0, 30, m) / 100.0).astype(np.float32)
+    cos_thr = np.float32(0.9986295)
+    for min_size, max_size in ((1, m), (20, 500)):
+        seq, n_seq = orc.region_growing(normals, knn, n_nb=n_nb, min_size=min_size, max_size=max_size, cos_thr=cos_thr)
+        label, _ = min_label_regions(normals, knn, n_nb, cos_thr)
+        par, n_par = labels_from_min_label(label, min_size, max_size)
+        assert n_seq == n_par and np.array_equal(seq, par)
+    label2, n_comp, passes = condensed_min_label_regions(normals, knn, n_nb, cos_thr)
+    assert np.array_equal(label2, label) and 1 < n_comp < m
+
+
 def test_prefilter_config_defaults_match_reference():
     """filteringUtils.cpp:12,22,27-34."""
     cfg = ab.default_prefilter_config()
