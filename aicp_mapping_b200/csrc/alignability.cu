@@ -24,6 +24,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 #include "handle.cuh"
@@ -402,8 +403,33 @@ int run_alignability(Handle* h, const float4* A, int64_t nA, const float4* B, in
   if (info) info[0] = info[1] = info[2] = 0;
   AlSide side[2];
   int rc;
-  if ((rc = al_side(h, 0, A, nA, cfg, poseA, &side[0]))) return rc;
-  if ((rc = al_side(h, 1, B, nB, cfg, poseB, &side[1]))) return rc;
+  // The two clouds are independent until the box counts, and each side is a chain of small latency-bound kernels with
+  // host round trips in between: outside a batch (where the other streams already fill the GPU) the second cloud runs on a
+  // child handle -- its own stream and buffers -- driven by a second host thread.
+  Handle* hb = h;                    // the handle that holds side 1's device buffers
+  if (!h->batch_worker) {
+    if (!h->al_child) {
+      aicp_b200_handle* c = nullptr;
+      if (aicp_b200_create(nullptr, h->device, &c) == AICP_B200_OK) h->al_child = reinterpret_cast<Handle*>(c);
+    }
+    if (h->al_child) hb = h->al_child;
+  }
+  if (hb != h) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // B may still be on its way in on this handle's stream
+    int rc1 = AICP_B200_OK;
+    std::thread tb([&]() {
+      cudaSetDevice(hb->device);
+      rc1 = al_side(hb, 1, B, nB, cfg, poseB, &side[1]);
+      if (!rc1 && cudaStreamSynchronize(hb->stream) != cudaSuccess) rc1 = fail(hb, AICP_B200_ERR_CUDA, "alignability: stream synchronisation failed");
+    });
+    rc = al_side(h, 0, A, nA, cfg, poseA, &side[0]);
+    tb.join();
+    if (rc) return rc;
+    if (rc1) return fail(h, rc1, "%s", hb->last_error.c_str());
+  } else {
+    if ((rc = al_side(h, 0, A, nA, cfg, poseA, &side[0]))) return rc;
+    if ((rc = al_side(h, 1, B, nB, cfg, poseB, &side[1]))) return rc;
+  }
   const int kA = side[0].k, kB = side[1].k;
   if (info) { info[0] = kA; info[1] = kB; }
   if (kA == 0 || kB == 0) {
@@ -416,9 +442,9 @@ int run_alignability(Handle* h, const float4* A, int64_t nA, const float4* B, in
   unsigned int* b_in_a = h->al_counts.p;            // [i * kB + j]
   unsigned int* a_in_b = h->al_counts.p + cells;    // [j * kA + i]
   CUDA_TRY(cudaMemsetAsync(h->al_counts.p, 0, sizeof(unsigned int) * 2 * cells, st));
-  k_al_pairs<<<(side[1].m + 255) / 256, 256, 0, st>>>(reinterpret_cast<const CropT*>(h->al_boxes[0].p), kA, h->al_pts[1].p, h->al_lab[1].p,
+  k_al_pairs<<<(side[1].m + 255) / 256, 256, 0, st>>>(reinterpret_cast<const CropT*>(h->al_boxes[0].p), kA, hb->al_pts[1].p, hb->al_lab[1].p,
                                                       side[1].m, kB, b_in_a);
-  k_al_pairs<<<(side[0].m + 255) / 256, 256, 0, st>>>(reinterpret_cast<const CropT*>(h->al_boxes[1].p), kB, h->al_pts[0].p, h->al_lab[0].p,
+  k_al_pairs<<<(side[0].m + 255) / 256, 256, 0, st>>>(reinterpret_cast<const CropT*>(hb->al_boxes[1].p), kB, h->al_pts[0].p, h->al_lab[0].p,
                                                       side[0].m, kA, a_in_b);
   h->launches += 2;
   CUDA_TRY(cudaGetLastError());

@@ -124,6 +124,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   if (!h) return AICP_B200_OK;
   cudaSetDevice(h->device);
   if (h->comm) aicp_b200_comm_destroy(hh);
+  if (h->al_child) { aicp_b200_destroy(reinterpret_cast<aicp_b200_handle*>(h->al_child)); h->al_child = nullptr; }
   for (Handle* w : h->workers) aicp_b200_destroy(reinterpret_cast<aicp_b200_handle*>(w));
   h->workers.clear();
   if (h->done_ev) cudaEventDestroy(h->done_ev);

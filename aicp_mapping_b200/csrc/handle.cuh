@@ -132,6 +132,7 @@ struct Handle {
   DevBuf<unsigned long long> al_sums;
   DevBuf<unsigned int> al_cnt, al_counts;
   DevBuf<float> al_axes, al_boxes[2];
+  Handle* al_child = nullptr;    // second stream + buffers for the other cloud of an alignability call (not inside batches)
 
   // sweep accumulation (ingest.cu)
   DevBuf<float4> acc, acc_tmp;
