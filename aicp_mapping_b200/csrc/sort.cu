@@ -88,11 +88,26 @@ __global__ void __launch_bounds__(256) k_radix_pass(const unsigned int* __restri
       atomicExch(&st[(size_t)tile * 256], RS_AGG | tile_count);
       long long t = (long long)tile - 1;
       while (true) {
-        const unsigned int s = *(volatile unsigned int*)&st[(size_t)t * 256];
-        if ((s >> 30) == 0u) continue;                               // predecessor running (ticket order): not published yet
-        prefix += s & RS_MASK;
-        if ((s >> 30) == 2u) break;
-        --t;
+        // four predecessors per step: the loads are independent, so one L2 round trip serves up to four hops of the walk.
+        // Tile 0 only ever publishes a PREFIX, which ends the walk, so a word below tile 0 (read as 0 = "not published") is
+        // never consumed: s1 is looked at only after s0 was an aggregate, i.e. t >= 1, and so on.
+        const unsigned int s0 = *(volatile unsigned int*)&st[(size_t)t * 256];
+        const unsigned int s1 = t >= 1 ? *(volatile unsigned int*)&st[(size_t)(t - 1) * 256] : 0u;
+        const unsigned int s2 = t >= 2 ? *(volatile unsigned int*)&st[(size_t)(t - 2) * 256] : 0u;
+        const unsigned int s3 = t >= 3 ? *(volatile unsigned int*)&st[(size_t)(t - 3) * 256] : 0u;
+        if ((s0 >> 30) == 0u) continue;                              // predecessor running (ticket order): not published yet
+        prefix += s0 & RS_MASK;
+        if ((s0 >> 30) == 2u) break;
+        if ((s1 >> 30) == 0u) { t -= 1; continue; }
+        prefix += s1 & RS_MASK;
+        if ((s1 >> 30) == 2u) break;
+        if ((s2 >> 30) == 0u) { t -= 2; continue; }
+        prefix += s2 & RS_MASK;
+        if ((s2 >> 30) == 2u) break;
+        if ((s3 >> 30) == 0u) { t -= 3; continue; }
+        prefix += s3 & RS_MASK;
+        if ((s3 >> 30) == 2u) break;
+        t -= 4;
       }
       atomicExch(&st[(size_t)tile * 256], RS_PREFIX | (prefix + tile_count));
     }
