@@ -15,10 +15,9 @@
 
 namespace aicp {
 
+#define RS_ITEMS 8
 #define RS_WARPS 8
-// pairs per thread: 8 (tiles of 2048) for large inputs; 4 (tiles of 1024) up to 2^19 pairs, where every block is alone on its SM
-// and a pass lasts as long as one block's critical path
-#define RS_SMALL_N (1 << 19)
+#define RS_TILE (RS_WARPS * 32 * RS_ITEMS)
 #define RS_AGG (1u << 30)
 #define RS_PREFIX (2u << 30)
 #define RS_MASK ((1u << 30) - 1u)
@@ -39,7 +38,6 @@ __global__ void __launch_bounds__(256) k_radix_hist(const unsigned int* __restri
     if (sh[b]) atomicAdd(&ghist[b], sh[b]);
 }
 
-template <int RS_ITEMS>
 __global__ void __launch_bounds__(256) k_radix_pass(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
                                                     unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n,
                                                     int shift, const unsigned int* __restrict__ ghist, unsigned int* status,
@@ -53,7 +51,6 @@ __global__ void __launch_bounds__(256) k_radix_pass(const unsigned int* __restri
   __syncthreads();
   const unsigned int tile = s_tile;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  constexpr int RS_TILE = RS_WARPS * 32 * RS_ITEMS;
   const long long base = (long long)tile * RS_TILE + w * (32 * RS_ITEMS);
   unsigned int key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
 #pragma unroll
@@ -146,9 +143,7 @@ __global__ void __launch_bounds__(256) k_radix_pass(const unsigned int* __restri
 int radix_sort_pairs(Handle* h, unsigned int* keys, unsigned int* vals, unsigned int* keys_alt, unsigned int* vals_alt, int n,
                      DevBuf<unsigned int>& scratch) {
   cudaStream_t s = h->stream;
-  const int items = n <= RS_SMALL_N ? 4 : 8;
-  const int tile_pairs = RS_WARPS * 32 * items;
-  const int n_tiles = (n + tile_pairs - 1) / tile_pairs;
+  const int n_tiles = (n + RS_TILE - 1) / RS_TILE;
   const size_t words = 4 * 256 + 4 + (size_t)4 * n_tiles * 256;
   CUDA_TRY(scratch.reserve(words));
   unsigned int* ghist = scratch.p;
@@ -160,10 +155,7 @@ int radix_sort_pairs(Handle* h, unsigned int* keys, unsigned int* vals, unsigned
   k_radix_hist<<<hb, 256, 0, s>>>(keys, n, ghist);
   unsigned int *ki = keys, *vi = vals, *ko = keys_alt, *vo = vals_alt;
   for (int pass = 0; pass < 4; ++pass) {
-    if (items == 4)
-      k_radix_pass<4><<<n_tiles, 256, 0, s>>>(ki, vi, ko, vo, n, 8 * pass, ghist + 256 * pass, status + (size_t)pass * n_tiles * 256, tickets + pass);
-    else
-      k_radix_pass<8><<<n_tiles, 256, 0, s>>>(ki, vi, ko, vo, n, 8 * pass, ghist + 256 * pass, status + (size_t)pass * n_tiles * 256, tickets + pass);
+    k_radix_pass<<<n_tiles, 256, 0, s>>>(ki, vi, ko, vo, n, 8 * pass, ghist + 256 * pass, status + (size_t)pass * n_tiles * 256, tickets + pass);
     unsigned int* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
   }
