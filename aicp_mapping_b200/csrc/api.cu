@@ -1,5 +1,8 @@
 // api.cu -- the C ABI of libaicp_b200.so (include/aicp_b200.h).  Thin: argument checks, host<->device staging on the
-// handle's stream, and calls into index.cu / normals.cu / icp.cu / overlap.cu.  No compute happens on the host.
+// handle's stream, and calls into index.cu / normals.cu / icp.cu / overlap.cu / crop.cu / prefilter.cu / alignability.cu / svm.cu /
+// ingest.cu.  No per-point work happens on the host; what does run there is per-call or per-cluster control logic (the 6-digit ratio
+// round trip, ~100 3x3 eigen-decompositions and the reference's greedy cluster matching in alignability.cu, file parsing in
+// ingest.cu / svm.cu / config_yaml.cpp).
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
