@@ -104,6 +104,94 @@ def test_oracle_alignability_analytic_scenes(orc):
     assert al == 0.0 and info == (0, info[1], 0)
 
 
+def numpy_alignability(sa, na, la, sb, nb, lb):
+    """Independent float64 statement of filteringUtils.cpp:229-372 written from the reference (no code shared with the oracle):
+    cluster OBBs (MomentOfInertiaEstimation::getOBB), CropBox counts through eulerAngles(0,1,2) -> Rz Ry Rx, greedy matching,
+    PCA of the matched normals and their mirror images.  Inputs: sampled clouds, normals, cluster labels of both clouds."""
+    from scipy.spatial.transform import Rotation
+
+    def boxes(pts, nrm, lab):
+        out = []
+        for c in range(lab.max() + 1):
+            p = pts[lab == c, :3].astype(np.float64)
+            mean = p.mean(0)
+            w, v = np.linalg.eigh(np.cov((p - mean).T, bias=True))
+            axes = v[:, ::-1].copy()                                   # major, middle, minor
+            for k in range(3):                                          # canonical sign: largest |component| positive
+                if axes[np.argmax(np.abs(axes[:, k])), k] < 0:
+                    axes[:, k] = -axes[:, k]
+            if np.dot(axes[:, 0], np.cross(axes[:, 1], axes[:, 2])) <= 0:
+                axes[:, 0] = -axes[:, 0]
+            proj = (p - mean) @ axes
+            lo, hi = proj.min(0), proj.max(0)
+            shift = (hi + lo) / 2
+            lo, hi, pos = lo - shift, hi - shift, mean + axes @ shift
+            lo[2], hi[2] = 3 * lo[2], 3 * hi[2]
+            a, b, g = Rotation.from_matrix(axes).as_euler("XYZ")        # R = Rx(a) Ry(b) Rz(g), b in [-pi/2, pi/2] (scipy)
+            if a < 0:                                                   # Eigen 3.3 documents the ranges [0:pi] x [-pi:pi] x [-pi:pi]:
+                a, b, g = a + np.pi, np.pi - b, g + np.pi               # the other triple of the same rotation
+                b, g = (b + np.pi) % (2 * np.pi) - np.pi, (g + np.pi) % (2 * np.pi) - np.pi
+            # the two triples describe the same Rx Ry Rz but NOT the same Rz Ry Rx: which one Eigen returns decides the box
+            Rbox = Rotation.from_euler("xyz", [a, b, g]).as_matrix()    # extrinsic xyz = Rz(g) Ry(b) Rx(a): pcl::getTransformation
+            out.append(dict(n=p.shape[0], ncen=nrm[lab == c, :3].astype(np.float64).mean(0), R=Rbox, t=pos, lo=lo, hi=hi,
+                            S=nrm[lab == c, :3].astype(np.float64).T @ nrm[lab == c, :3].astype(np.float64)))
+        return out
+
+    def count(box, pts):
+        loc = (pts[:, :3].astype(np.float64) - box["t"]) @ box["R"]
+        return np.all((loc >= box["lo"]) & (loc <= box["hi"]), axis=1)
+
+    A, B = boxes(sa, na, la), boxes(sb, nb, lb)
+    mi, mo = [-1] * len(B), [-1.0] * len(B)
+    fragile = set()                 # B clusters whose decision hangs on acos(x) with x within rounding of 1
+    for i, a in enumerate(A):
+        best, mx = -1, 0.0
+        for j, b in enumerate(B):
+            cosang = np.dot(a["ncen"], b["ncen"]) / (np.linalg.norm(a["ncen"]) * np.linalg.norm(b["ncen"]))
+            ov = (count(b, sa[la == i]).sum() / a["n"]) * (count(a, sb[lb == j]).sum() / b["n"]) * 100.0
+            if cosang > 1.0 - 1e-6 and ov > 0:
+                fragile.add(j)      # the reference takes acos of a float32 ratio that rounding can push above 1: NaN, "dist < 20" false
+            dist = np.degrees(np.arccos(np.clip(cosang, -1, 1)))
+            if ov > mx and dist < 20:
+                best, mx = j, ov
+        if mx > 0 and (mi[best] == -1 or mx > mo[best]):
+            mi[best], mo[best] = i, mx
+
+    def value(matching):
+        S = sum((A[i]["S"] for i in matching if i >= 0), np.zeros((3, 3)))
+        if not any(i >= 0 for i in matching):
+            return 0.0
+        lam = np.sort(np.linalg.eigvalsh(S))[::-1]
+        return 100.0 * lam[2] / lam[0]
+    return value, mi, fragile
+
+
+@pytest.mark.parametrize("case", ["room", "corridor", "vlp16"])
+def test_oracle_alignability_matches_independent_numpy_statement(orc, pair_cache, case):
+    rng = np.random.default_rng(21)
+    if case == "room":
+        A, B, PA = room_box(rng), room_box(rng, shift=(0.05, 0.02, 0)), pose([3.0, 3.0, 1.5])
+        PB = PA
+    elif case == "corridor":
+        A, B, PA = corridor(rng, end_wall=True), corridor(rng, end_wall=True, shift=(0.1, 0, 0)), pose([3.0, 0.2, 1.0])
+        PB = PA
+    else:
+        p = pair_cache(2, 0, 16384)
+        A, B, PA, PB = p["ref"], p["read"], pose(p["ref_origin"]), pose(p["read_origin"])
+    al, matching, info = orc.alignability(A, B, PA, PB, threads=4)
+    oa = orc.prefilter(A, viewpoint=PA[:3, 3].astype(np.float32), threads=4)
+    ob = orc.prefilter(B, viewpoint=PB[:3, 3].astype(np.float32), threads=4)
+    value, mi, fragile = numpy_alignability(oa.sampled, oa.normals, oa.labels, ob.sampled, ob.normals, ob.labels)
+    # points within float32 rounding of a box face may be counted differently; the matching is robust to that.  What is NOT robust,
+    # in the reference itself (filteringUtils.cpp:252): acos(dot / (|a| |b|)) of two mean normals that are parallel to within float32
+    # rounding is NaN when the ratio lands on 1.0000001, and NaN < 20 rejects the pair -- such clusters may legitimately differ
+    got = [int(m) for m in matching]
+    assert all(g == w for j, (g, w) in enumerate(zip(got, mi)) if j not in fragile)
+    assert all(g in (-1, w) for j, (g, w) in enumerate(zip(got, mi)) if j in fragile)
+    want = value(got)                                              # the PCA stage, from the oracle's own matching
+    assert abs(float(al) - want) <= 1e-3 * max(1.0, want)
+
+
 def test_euler_angles_restatement_matches_python_mirror(orc):
     from aicp_mapping_b200 import filtering
     for seed in range(10):
