@@ -168,6 +168,30 @@ def test_oracle_pcl_normals_on_a_tilted_plane(orc):
     assert np.array_equal(o2.cloud, o.cloud)                       # the segmentation ignores the sign
 
 
+def test_oracle_normals_match_independent_numpy_statement(orc):
+    """pcl::NormalEstimation from its definition, float64: 30 nearest neighbours (scipy cKDTree), covariance, smallest
+    eigenvector (numpy.linalg.eigh), curvature = lambda_min / trace, flipped towards the view point."""
+    from scipy.spatial import cKDTree
+    r = synth.raw_sweep(2, 2, n_sweeps=2)
+    vp = r["origin"].astype(np.float32)
+    o = orc.prefilter(r["cloud"], viewpoint=vp, threads=4)
+    pts = o.sampled[:, :3].astype(np.float64)
+    _, nn = cKDTree(pts).query(pts, k=30)
+    nb = pts[nn]                                                   # m x 30 x 3
+    d = nb - nb.mean(1, keepdims=True)
+    cov = np.einsum("mki,mkj->mij", d, d) / 30.0
+    w, v = np.linalg.eigh(cov)
+    n = v[:, :, 0]
+    n = np.where((np.einsum("mi,mi->m", vp.astype(np.float64) - pts, n) < 0)[:, None], -n, n)
+    curv = w[:, 0] / w.sum(1)
+    well = (w[:, 1] - w[:, 0]) > 1e-3 * w[:, 2]                    # the smallest eigenvector is well defined
+    cosang = np.abs(np.einsum("mi,mi->m", n, o.normals[:, :3].astype(np.float64)))
+    assert well.mean() > 0.9 and cosang[well].min() > 1.0 - 2e-5   # float32 covariance of a shifted 0.5 m neighbourhood
+    assert np.abs(curv - o.normals[:, 3])[well].max() < 2e-4
+    same_side = np.einsum("mi,mi->m", n, o.normals[:, :3].astype(np.float64)) > 0
+    assert same_side[well].mean() > 0.9999                         # flips differ only where (vp - p) . n is ~ 0
+
+
 def test_oracle_prefilter_two_planes(orc):
     pts = two_planes(np.random.default_rng(1))
     o = orc.prefilter(pts, threads=4)
