@@ -36,6 +36,39 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.Stats) == 96 + 104 * capi.MAX_ITERS   # 92 bytes of scalars, padded to the 8-byte alignment of the trace records
 
 
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """Every struct of include/aicp_b200.h that crosses the ABI: sizeof and the offset of every field, as gcc lays them out,
+    against the ctypes mirrors in capi.py."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    structs = {"aicp_b200_icp_config": capi.IcpConfig, "aicp_b200_iter_trace": capi.IterTrace, "aicp_b200_stats": capi.Stats,
+               "aicp_b200_prefilter_config": capi.PrefilterConfig, "aicp_b200_prefilter_info": capi.PrefilterInfo,
+               "aicp_b200_svm_summary": capi.SvmSummary}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "aicp_b200.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for ln in out.splitlines():
+        cname, what, val = ln.split()
+        ct = structs[cname]
+        if what == "sizeof":
+            assert C.sizeof(ct) == int(val), cname
+        else:
+            assert getattr(ct, what).offset == int(val), (cname, what)
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())
+
+
 def test_no_cpu_fallback(lib):
     import torch
     if torch.cuda.is_available():
