@@ -143,7 +143,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->pf_keys.release(); h->pf_keys_alt.release(); h->pf_vals.release(); h->pf_vals_alt.release(); h->pf_sort_tmp.release();
   h->pf_flag.release(); h->pf_slot.release(); h->pf_tiles.release(); h->pf_mask.release(); h->pf_count.release();
   h->pf_label.release(); h->pf_seed_pos.release(); h->pf_labels_out.release();
-  h->pf_mutual.release(); h->pf_parent.release(); h->pf_root.release(); h->pf_clabel.release();
+  h->pf_status.release(); h->pf_mutual.release(); h->pf_parent.release(); h->pf_root.release(); h->pf_clabel.release();
   svm_release(h);
   h->acc.release(); h->acc_tmp.release();
   h->al_moved.release(); h->al_mean.release(); h->al_ext.release(); h->al_sums.release(); h->al_cnt.release(); h->al_counts.release(); h->al_axes.release();

@@ -119,6 +119,7 @@ struct Handle {
   DevBuf<float4> pf_out;                    // kept clusters, concatenated
   DevBuf<unsigned int> pf_keys, pf_keys_alt, pf_vals, pf_vals_alt, pf_sort_tmp, pf_flag, pf_slot, pf_tiles, pf_mask, pf_mutual, pf_count;
   DevBuf<int> pf_label, pf_seed_pos, pf_labels_out, pf_parent, pf_root, pf_clabel;
+  DevBuf<unsigned long long> pf_status;     // chained-scan tile status of k_vg_fused + its ticket
   void* pf_meta = nullptr;                  // PfMeta, device
   void* pf_meta_host = nullptr;             // pinned
   int64_t pf_n_sampled = 0, pf_n_out = 0, pf_n_clusters = 0;

@@ -10,8 +10,10 @@
 //   k_vg_params    PCL's min_b / div_b / divb_mul and its "leaf size too small" overflow test, one thread
 //   k_vg_keys      voxel index of every point as a 32-bit sort key (non-finite points: 0xFFFFFFFF, sorted to the end)
 //   radix sort     (voxel index, point index), stable (sort.cu)
-//   k_vg_heads     head flag of every run of equal keys; exclusive scan (k_scan_*) = output slot of the voxel
-//   k_vg_centroids one thread per voxel: exact fixed-point sums (llrint(x * 2^20), int64 -- order independent) -> centroid
+//   k_vg_fused     one pass over the sorted pairs: heads of the runs of equal keys, their output slots (chained scan with
+//                  decoupled look-back over tiles of 2048) and, per head, the exact fixed-point sums (llrint(x * 2^20),
+//                  int64 -- order independent) -> centroid.  (k_vg_heads / k_scan_* / k_vg_centroids: the first, five-launch
+//                  version of the same step; the scan is still used by the cluster numbering and the FOV filter.)
 // Stage N, normals: Morton index + exact k-NN (index.cu, normals.cu: the same kernels as the ICP chain's SurfaceNormal filter),
 //   k_pf_normals   one thread per point: PCL's single-pass float32 covariance (shifted by the first neighbour) in list order,
 //                  float64 Jacobi, curvature,
@@ -248,6 +250,109 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const unsigned int* __rest
   const double cnt = (double)(j - i);
   const double s = 1.0 / PF_FIXED;
   out[__ldg(&slot[i])] = make_float4((float)(((double)sx / cnt) * s), (float)(((double)sy / cnt) * s), (float)(((double)sz / cnt) * s), 1.0f);
+}
+
+// Heads, their ranks and the centroids in ONE pass over the sorted pairs (replaces k_vg_heads + the three scan launches +
+// k_vg_centroids): tiles of 2048 sorted pairs (256 threads x 8 rows, row-major = sorted order); per-row warp ballots + a
+// 64-entry shared scan rank the heads inside the tile; the tile's base slot comes from a chained scan with decoupled
+// look-back over the tiles (the protocol of k_crop_box: tiles take their number from an atomic ticket, so a tile only waits
+// for tiles that are already running); the thread of a head sums its run (which may continue into the next tiles).
+#define VG_ROWS 8
+#define VG_TILE (256 * VG_ROWS)
+#define VG_AGG (1ull << 62)
+#define VG_PREFIX (2ull << 62)
+#define VG_MASK ((1ull << 62) - 1ull)
+
+__global__ void k_vg_fused_reset(unsigned long long* status, int n_tiles, unsigned int* ticket) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tiles) status[i] = 0ull;
+  if (i == 0) *ticket = 0u;
+}
+
+__global__ void __launch_bounds__(256) k_vg_fused(const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals,
+                                                  const float4* __restrict__ pts, int n, float4* __restrict__ out,
+                                                  unsigned long long* status, unsigned int* ticket, PfMeta* m) {
+  __shared__ unsigned int s_tile;
+  __shared__ int s_cnt[VG_ROWS * 8 + 1];
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const long long base = (long long)tile * VG_TILE;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned int head = 0;              // bit r: element (row r of this thread) starts a run of equal voxel indices
+  int rank[VG_ROWS];
+#pragma unroll
+  for (int r = 0; r < VG_ROWS; ++r) {
+    const long long i = base + r * 256 + threadIdx.x;
+    bool hd = false;
+    if (i < n) {
+      const unsigned int k = __ldg(&keys[i]);
+      hd = k != 0xFFFFFFFFu && (i == 0 || __ldg(&keys[i - 1]) != k);
+    }
+    const unsigned int bal = __ballot_sync(0xFFFFFFFFu, hd);
+    rank[r] = __popc(bal & ((1u << lane) - 1u));
+    if (hd) head |= 1u << r;
+    if (lane == 0) s_cnt[r * 8 + w] = __popc(bal);
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+    int incl = a + b;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    const int excl = incl - (a + b);
+    s_cnt[2 * lane] = excl; s_cnt[2 * lane + 1] = excl + a;
+    const unsigned int tile_total = (unsigned int)__shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&status[0], VG_PREFIX | (unsigned long long)tile_total);
+    } else {
+      if (lane == 0) atomicExch(&status[tile], VG_AGG | (unsigned long long)tile_total);
+      long long j0 = (long long)tile - 1;
+      while (true) {
+        const long long j = j0 - lane;
+        unsigned long long st = j >= 0 ? *(volatile unsigned long long*)&status[j] : VG_PREFIX;   // nothing before tile 0
+        while (__any_sync(0xFFFFFFFFu, (st >> 62) == 0ull))                  // predecessors are running (ticket order)
+          if ((st >> 62) == 0ull) st = *(volatile unsigned long long*)&status[j];
+        const unsigned int has_prefix = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2ull);
+        const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;
+        const unsigned int part = __reduce_add_sync(0xFFFFFFFFu, lane <= stop ? (unsigned int)(st & VG_MASK) : 0u);
+        prefix += part;
+        if (has_prefix) break;
+        j0 -= 32;
+      }
+      if (lane == 0) atomicExch(&status[tile], VG_PREFIX | (prefix + (unsigned long long)tile_total));
+    }
+    if (lane == 0) {
+      s_base = prefix;
+      if (base + VG_TILE >= n) m->n_voxels = (unsigned int)(prefix + (unsigned long long)tile_total);   // the last tile knows the answer
+    }
+  }
+  __syncthreads();
+  const unsigned long long obase = s_base;
+  const double sc = 1.0 / PF_FIXED;
+#pragma unroll
+  for (int r = 0; r < VG_ROWS; ++r) {
+    if (!(head & (1u << r))) continue;
+    const int i = (int)(base + r * 256 + threadIdx.x);
+    const unsigned int k = __ldg(&keys[i]);
+    long long sx = 0, sy = 0, sz = 0;
+    int j = i;
+    do {
+      const float4 p = __ldg(&pts[__ldg(&vals[j])]);
+      sx += __double2ll_rn((double)p.x * PF_FIXED);
+      sy += __double2ll_rn((double)p.y * PF_FIXED);
+      sz += __double2ll_rn((double)p.z * PF_FIXED);
+      ++j;
+    } while (j < n && __ldg(&keys[j]) == k);
+    const double cnt = (double)(j - i);
+    out[obase + (unsigned long long)(s_cnt[r * 8 + w] + rank[r])] =
+        make_float4((float)(((double)sx / cnt) * sc), (float)(((double)sy / cnt) * sc), (float)(((double)sz / cnt) * sc), 1.0f);
+  }
 }
 
 // ---- stage N: pcl::NormalEstimation --------------------------------------------------------------------------------------
@@ -554,11 +659,14 @@ int run_voxel_grid(Handle* h, const float4* pts, int64_t n64, float leaf, int64_
   k_vg_keys<<<blocks, 256, 0, s>>>(pts, n, m, inv, h->pf_keys.p, h->pf_vals.p);
   h->launches += 3;
   if ((rc = radix_sort_pairs(h, h->pf_keys.p, h->pf_vals.p, h->pf_keys_alt.p, h->pf_vals_alt.p, n, h->pf_sort_tmp))) return rc;
-  k_vg_heads<<<blocks, 256, 0, s>>>(h->pf_keys.p, n, h->pf_flag.p);
-  h->launches += 1;
-  if ((rc = exclusive_scan_u32(h, h->pf_flag.p, h->pf_slot.p, n, h->pf_tiles.p, &m->n_voxels))) return rc;
-  k_vg_centroids<<<blocks, 256, 0, s>>>(h->pf_keys.p, h->pf_vals.p, h->pf_flag.p, h->pf_slot.p, pts, n, h->pf_sampled.p);
-  h->launches += 1;
+  {
+    const int n_tiles = (n + VG_TILE - 1) / VG_TILE;
+    CUDA_TRY(h->pf_status.reserve((size_t)n_tiles + 1));
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(h->pf_status.p + n_tiles);
+    k_vg_fused_reset<<<(n_tiles + 255) / 256, 256, 0, s>>>(h->pf_status.p, n_tiles, ticket);
+    k_vg_fused<<<n_tiles, 256, 0, s>>>(h->pf_keys.p, h->pf_vals.p, pts, n, h->pf_sampled.p, h->pf_status.p, ticket, m);
+    h->launches += 2;
+  }
   CUDA_TRY(cudaGetLastError());
   PfMeta* mh = reinterpret_cast<PfMeta*>(h->pf_meta_host);
   CUDA_TRY(cudaMemcpyAsync(mh, m, offsetof(PfMeta, changed), cudaMemcpyDeviceToHost, s));
