@@ -16,7 +16,7 @@ ERR_NAMES = {0: "OK", 1: "BAD_ARG", 2: "KNN_TOO_LARGE", 3: "NO_VALID_MATCH", 4: 
 STOP_NONE, STOP_COUNTER, STOP_DIFFERENTIAL = 0, 1, 2
 
 # every symbol declared in include/aicp_b200.h
-EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aicp_b200_version", "aicp_b200_set_config",
+EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_wait_stream", "aicp_b200_last_error", "aicp_b200_version", "aicp_b200_set_config",
            "aicp_b200_set_config_struct", "aicp_b200_get_config", "aicp_b200_parse_icp_yaml", "aicp_b200_register",
            "aicp_b200_set_reference", "aicp_b200_register_to_reference", "aicp_b200_get_output_reading",
            "aicp_b200_get_initialized_reading", "aicp_b200_get_reference_normals", "aicp_b200_enable_match_trace",
@@ -26,7 +26,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_last_error", "aic
            "aicp_b200_map_prefilter", "aicp_b200_accumulate_sweep", "aicp_b200_get_accumulated", "aicp_b200_download_accumulated", "aicp_b200_read_pcd", "aicp_b200_read_ply",
            "aicp_b200_write_pcd", "aicp_b200_read_pose_file", "aicp_b200_fov_overlap", "aicp_b200_get_fov_filtered", "aicp_b200_alignability", "aicp_b200_alignment_risk",
            "aicp_b200_svm_parse", "aicp_b200_svm_load", "aicp_b200_svm_info", "aicp_b200_svm_predict", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_pipeline_batch", "aicp_b200_comm_unique_id",
-           "aicp_b200_comm_init", "aicp_b200_comm_destroy"]
+           "aicp_b200_comm_init", "aicp_b200_comm_destroy", "aicp_b200_comm_info"]
 
 
 class IcpConfig(C.Structure):
@@ -91,6 +91,7 @@ def lib():
         fp, ip, i64 = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int64
         L.aicp_b200_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.aicp_b200_destroy.argtypes = [C.c_void_p]
+        L.aicp_b200_wait_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.aicp_b200_last_error.argtypes = [C.c_void_p]
         L.aicp_b200_last_error.restype = C.c_char_p
         L.aicp_b200_version.restype = C.c_char_p
@@ -166,6 +167,7 @@ def lib():
         L.aicp_b200_comm_unique_id.argtypes = [C.c_void_p]
         L.aicp_b200_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.aicp_b200_comm_destroy.argtypes = [C.c_void_p]
+        L.aicp_b200_comm_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -187,6 +189,11 @@ def ptr_and_count(cloud):
     if hasattr(cloud, "data_ptr"):      # torch tensor
         if cloud.dim() != 2 or cloud.shape[1] != 4 or str(cloud.dtype) != "torch.float32" or not cloud.is_contiguous():
             raise ValueError("device clouds must be contiguous n x 4 float32 tensors")
+        if cloud.is_cuda:
+            # the library reads device inputs on its own streams (aicp_b200.h, "STREAM ORDER"): whatever torch still has in
+            # flight on the current stream of the tensor's device -- the op or copy that produces it -- must finish first
+            import torch
+            torch.cuda.current_stream(cloud.device).synchronize()
         return C.c_void_p(cloud.data_ptr()), int(cloud.shape[0]), cloud
     a = to_xyzw(cloud)
     return C.c_void_p(a.ctypes.data), int(a.shape[0]), a

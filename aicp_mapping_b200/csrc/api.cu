@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <atomic>
 #include <string>
@@ -244,7 +245,13 @@ int aicp_b200_register_to_reference(aicp_b200_handle* hh, const float* read_xyzw
   if ((rc = stage_owned(h, h->read_in, read_xyzw, n_read))) return rc;
   h->n_read = n_read;
   bool rebuild = !h->ref_ready || h->ref_knn != h->cfg.knn_normals;
-  return run_registration(h, init_T, rebuild, stats, out_T);
+  float init_host[16];
+  const float* init = nullptr;
+  if (init_T) {
+    if (is_device_ptr(init_T)) { CUDA_TRY(cudaMemcpy(init_host, init_T, sizeof(init_host), cudaMemcpyDeviceToHost)); init = init_host; }
+    else init = init_T;
+  }
+  return run_registration(h, init, rebuild, stats, out_T);
 }
 
 int aicp_b200_get_output_reading(aicp_b200_handle* hh, float* xyzw, int64_t n) {
@@ -270,6 +277,18 @@ int aicp_b200_get_reference_normals(aicp_b200_handle* hh, float* normals_xyzd, i
   int rc = scatter_normals(h, h->ref_ix.pts.p, h->normals.p, h->ref_ix.n, h->tmp_b.p);
   if (rc) return rc;
   return download(h, normals_xyzd, h->tmp_b.p, sizeof(float4) * (size_t)n);
+}
+
+int aicp_b200_wait_stream(aicp_b200_handle* hh, void* producer_stream) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  // The library reads device-pointer inputs on its own non-blocking stream(s); this orders everything it enqueues from now
+  // on after the work already enqueued on the caller's stream (the producer of those inputs).  Batch workers and child
+  // handles start behind an event of h->stream, so they inherit the dependency.
+  if (!h->wait_ev) CUDA_TRY(cudaEventCreateWithFlags(&h->wait_ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(h->wait_ev, reinterpret_cast<cudaStream_t>(producer_stream)));
+  CUDA_TRY(cudaStreamWaitEvent(h->stream, h->wait_ev, 0));
+  return AICP_B200_OK;
 }
 
 int aicp_b200_enable_match_trace(aicp_b200_handle* hh, int enable) {
@@ -366,13 +385,13 @@ int aicp_b200_overlap(aicp_b200_handle* hh, const float* ref_xyzw, int64_t n_ref
                       float* overlap_pct, int64_t counts[3]) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   H_CHECK(h);
-  if (!ref_xyzw || !read_xyzw || !ref_origin || !read_origin || !overlap_pct || n_ref < 0 || n_read < 0 ||
+  if ((n_ref > 0 && !ref_xyzw) || (n_read > 0 && !read_xyzw) || !ref_origin || !read_origin || !overlap_pct || n_ref < 0 || n_read < 0 ||
       n_ref > (1ll << 30) || n_read > (1ll << 30))
     return fail(h, AICP_B200_ERR_BAD_ARG, "overlap: bad arguments");
-  const float4 *ref, *read;
-  int rc = upload_points(h, h->tmp_a, ref_xyzw, n_ref > 0 ? n_ref : 1, &ref);
-  if (rc) return rc;
-  if ((rc = upload_points(h, h->tmp_b, read_xyzw, n_read > 0 ? n_read : 1, &read))) return rc;
+  const float4 *ref = nullptr, *read = nullptr;
+  int rc;
+  if (n_ref > 0 && (rc = upload_points(h, h->tmp_a, ref_xyzw, n_ref, &ref))) return rc;
+  if (n_read > 0 && (rc = upload_points(h, h->tmp_b, read_xyzw, n_read, &read))) return rc;
   return run_overlap(h, ref, n_ref, ref_origin, read, n_read, read_origin, resolution, overlap_pct, counts);
 }
 
@@ -589,7 +608,9 @@ int aicp_b200_download_accumulated(aicp_b200_handle* hh, float* xyzw, int64_t n)
 int aicp_b200_read_pcd(const char* path, float* out_xyzw, int64_t capacity, int64_t* n_out, char* err, int err_len) {
   if (!path || !n_out) return AICP_B200_ERR_BAD_ARG;
   std::string e;
-  int rc = read_pcd(path, out_xyzw, capacity, n_out, &e);
+  int rc;
+  try { rc = read_pcd(path, out_xyzw, capacity, n_out, &e); }
+  catch (const std::exception& ex) { e = std::string("aicp_b200_read_pcd: ") + ex.what(); rc = AICP_B200_ERR_CONFIG; }      // no exception may cross the C ABI
   if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
   return rc;
 }
@@ -597,7 +618,9 @@ int aicp_b200_read_pcd(const char* path, float* out_xyzw, int64_t capacity, int6
 int aicp_b200_read_ply(const char* path, float* out_xyzw, int64_t capacity, int64_t* n_out, char* err, int err_len) {
   if (!path || !n_out) return AICP_B200_ERR_BAD_ARG;
   std::string e;
-  int rc = read_ply(path, out_xyzw, capacity, n_out, &e);
+  int rc;
+  try { rc = read_ply(path, out_xyzw, capacity, n_out, &e); }
+  catch (const std::exception& ex) { e = std::string("aicp_b200_read_ply: ") + ex.what(); rc = AICP_B200_ERR_CONFIG; }      // no exception may cross the C ABI
   if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
   return rc;
 }
@@ -605,7 +628,9 @@ int aicp_b200_read_ply(const char* path, float* out_xyzw, int64_t capacity, int6
 int aicp_b200_write_pcd(const char* path, const float* xyzw, int64_t n, char* err, int err_len) {
   if (!path || n < 0 || (n > 0 && !xyzw)) return AICP_B200_ERR_BAD_ARG;
   std::string e;
-  int rc = write_pcd_binary(path, xyzw, n, &e);
+  int rc;
+  try { rc = write_pcd_binary(path, xyzw, n, &e); }
+  catch (const std::exception& ex) { e = std::string("aicp_b200_write_pcd: ") + ex.what(); rc = AICP_B200_ERR_CONFIG; }
   if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
   return rc;
 }
@@ -613,7 +638,9 @@ int aicp_b200_write_pcd(const char* path, const float* xyzw, int64_t n, char* er
 int aicp_b200_read_pose_file(const char* path, int64_t* rows, double* poses, int64_t capacity, int64_t* n_out, char* err, int err_len) {
   if (!path || !n_out) return AICP_B200_ERR_BAD_ARG;
   std::string e;
-  int rc = read_pose_file(path, rows, poses, capacity, n_out, &e);
+  int rc;
+  try { rc = read_pose_file(path, rows, poses, capacity, n_out, &e); }
+  catch (const std::exception& ex) { e = std::string("aicp_b200_read_pose_file: ") + ex.what(); rc = AICP_B200_ERR_CONFIG; }      // no exception may cross the C ABI
   if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
   return rc;
 }

@@ -12,6 +12,7 @@
 // process), so libaicp_b200.so has no link-time dependency on it and loads on machines without NCCL.
 #include <dlfcn.h>
 
+#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -127,6 +128,15 @@ int aicp_b200_comm_init(aicp_b200_handle* hh, const uint8_t nccl_unique_id[128],
   c->rank = rank; c->n_ranks = n_ranks;
   if (c->limbs.reserve(4 * AICP_NSUM + 2) != cudaSuccess) { c->CommDestroy(c->comm); delete c; return fail(h, AICP_B200_ERR_CUDA, "comm_init: allocation failed"); }
   h->comm = c;
+  return AICP_B200_OK;
+}
+
+int aicp_b200_comm_info(aicp_b200_handle* hh, char* buf, int len) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || !buf || len < 1) return AICP_B200_ERR_BAD_ARG;
+  if (!h->comm) { snprintf(buf, (size_t)len, "no communicator"); return AICP_B200_OK; }
+  snprintf(buf, (size_t)len, "%d ranks; per iteration 3 x ncclAllReduce(uint32[2048]) for the trimmed quantile + 1 x ncclAllReduce(uint64[113]) "
+           "for the normal equations, 9 launches", h->comm->n_ranks);
   return AICP_B200_OK;
 }
 

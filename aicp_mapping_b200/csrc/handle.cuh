@@ -146,7 +146,7 @@ struct Handle {
   // batch workers: one child handle (own stream + buffers) per concurrent registration
   std::vector<Handle*> workers;
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
-  cudaEvent_t wait_ev = nullptr;     // set while a batch runs: the worker's first stream op waits on it
+  cudaEvent_t wait_ev = nullptr;     // aicp_b200_wait_stream: recorded on the caller's producer stream, waited on by h->stream
   cudaEvent_t done_ev = nullptr;
 };
 

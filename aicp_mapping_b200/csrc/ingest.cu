@@ -138,6 +138,9 @@ int read_pcd(const char* path, float* out, int64_t cap, int64_t* n_out, std::str
   if (sizes.size() != fields.size() || types.size() != fields.size() || counts.size() != fields.size()) { *err = "PCD header: FIELDS / SIZE / TYPE / COUNT disagree"; return AICP_B200_ERR_CONFIG; }
   int off[3] = {-1, -1, -1}, col[3] = {-1, -1, -1}, stride = 0, cols = 0;
   for (size_t i = 0; i < fields.size(); ++i) {
+    // header values are untrusted: a negative or huge SIZE / COUNT must not reach the record buffer or the offsets
+    if ((sizes[i] != 1 && sizes[i] != 2 && sizes[i] != 4 && sizes[i] != 8) || counts[i] < 0 || counts[i] > 4096 ||
+        stride > (1 << 20)) { *err = "PCD header: SIZE must be 1, 2, 4 or 8 and COUNT in [0, 4096]"; return AICP_B200_ERR_CONFIG; }
     for (int d = 0; d < 3; ++d)
       if (fields[i] == (d == 0 ? "x" : d == 1 ? "y" : "z")) {
         if (sizes[i] != 4 || types[i] != 'F' || counts[i] != 1) { *err = "PCD: x y z must be float32 fields"; return AICP_B200_ERR_CONFIG; }

@@ -200,8 +200,9 @@ int run_overlap(Handle* h, const float4* ref, int64_t n_ref, const double* ref_o
     CUDA_TRY(h->ovl_bits_b.reserve((size_t)n_words));
     CUDA_TRY(cudaMemsetAsync(h->ovl_bits_a.p, 0, n_words * 4, s));
     CUDA_TRY(cudaMemsetAsync(h->ovl_bits_b.p, 0, n_words * 4, s));
-    k_ray_mark<<<(unsigned)((n_ref + 127) / 128), 128, 0, s>>>(ref, (int)n_ref, ro[0], ro[1], ro[2], resolution, res_factor, g, h->ovl_bits_a.p, dcounts + 3);
-    k_ray_mark<<<(unsigned)((n_read + 127) / 128), 128, 0, s>>>(read, (int)n_read, so[0], so[1], so[2], resolution, res_factor, g, h->ovl_bits_b.p, dcounts + 3);
+    // an empty cloud has an empty tree: |A| (or |B|) = 0 and the ratio below is 0/0 = NaN, as in the reference
+    if (n_ref > 0) k_ray_mark<<<(unsigned)((n_ref + 127) / 128), 128, 0, s>>>(ref, (int)n_ref, ro[0], ro[1], ro[2], resolution, res_factor, g, h->ovl_bits_a.p, dcounts + 3);
+    if (n_read > 0) k_ray_mark<<<(unsigned)((n_read + 127) / 128), 128, 0, s>>>(read, (int)n_read, so[0], so[1], so[2], resolution, res_factor, g, h->ovl_bits_b.p, dcounts + 3);
     unsigned long long pb = (n_words + 255) / 256;
     k_popcount<<<(unsigned)(pb < 148 * 8 ? pb : 148 * 8), 256, 0, s>>>(h->ovl_bits_a.p, h->ovl_bits_b.p, n_words, dcounts);
     CUDA_TRY(cudaMemcpyAsync(hc, dcounts, sizeof(hc), cudaMemcpyDeviceToHost, s));

@@ -290,6 +290,21 @@ class B200Registration:
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         self._check(self._lib.aicp_b200_comm_init(self._h, buf, int(rank), int(n_ranks)))
 
+    def commInfo(self):
+        """aicp_b200_comm_info: what the ranks exchange per ICP iteration."""
+        buf = C.create_string_buffer(512)
+        self._check(self._lib.aicp_b200_comm_info(self._h, buf, 512))
+        return buf.value.decode()
+
+    def waitStream(self, cuda_stream=None):
+        """aicp_b200_wait_stream: order the handle's work after what is enqueued on `cuda_stream` (a torch.cuda.Stream or a
+        raw cudaStream_t; None = torch's current stream)."""
+        if cuda_stream is None:
+            import torch
+            cuda_stream = torch.cuda.current_stream()
+        ptr = getattr(cuda_stream, "cuda_stream", cuda_stream)
+        self._check(self._lib.aicp_b200_wait_stream(self._h, C.c_void_p(int(ptr))))
+
     def commDestroy(self):
         self._check(self._lib.aicp_b200_comm_destroy(self._h))
 

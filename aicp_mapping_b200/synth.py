@@ -212,10 +212,11 @@ def campus_map(n_points, rng, lx=200.0, ly=200.0, lz=12.0, n_boxes=120):
 # ----------------------------------------------------------------------------------------------------------
 # configuration pairs
 # ----------------------------------------------------------------------------------------------------------
-def make_pair(config, trial=0, n_points=None):
+def make_pair(config, trial=0, n_points=None, variants=0):
     """Returns dict(ref, read: n x 3 float32 world frame; ref_origin, read_origin: float64[3]; T_true: 4x4 float64, the
     correction that registerClouds should recover (maps the reading onto the reference); name).
-    n_points overrides the nominal cloud size (used by small parity tests)."""
+    n_points overrides the nominal cloud size (used by small parity tests).  variants = V > 0 (configs 2 and 3): a list
+    of V such dicts that share the two scans and differ in the erroneous prior pose of the reading."""
     rng = np.random.default_rng(1000 * config + trial)
     if config == 2:
         n = n_points or 32768
@@ -263,10 +264,16 @@ def make_pair(config, trial=0, n_points=None):
                     T_true=np.linalg.inv(P), name="C5 cube validation pair, %d pts" % n)
     else:
         raise ValueError("make_pair supports configs 2, 3, 5 (C1: tests/golden/c1_scans.npz, C4: make_map_case)")
-    E = _prior_error(rng)
-    read = apply_T(E, read_true)
-    return dict(ref=np.ascontiguousarray(ref, dtype=np.float32), read=read, ref_origin=np.asarray(ref_o, dtype=np.float64),
-                read_origin=(E[:3, :3] @ read_o + E[:3, 3]), T_true=np.linalg.inv(E), name=name)
+    out = []
+    for v in range(max(1, int(variants))):
+        # variant 0 draws the prior error from the scene's own stream (the pair every test and golden uses); further variants
+        # express the SAME two scans through other erroneous priors: distinct inputs with distinct ICP trajectories for
+        # the price of one ray cast (bench.py)
+        E = _prior_error(rng if v == 0 else np.random.default_rng(1000 * config + trial + 1000003 * v))
+        out.append(dict(ref=np.ascontiguousarray(ref, dtype=np.float32), read=apply_T(E, read_true),
+                        ref_origin=np.asarray(ref_o, dtype=np.float64), read_origin=(E[:3, :3] @ read_o + E[:3, 3]),
+                        T_true=np.linalg.inv(E), name=name if v == 0 else name + ", prior variant %d" % v))
+    return out if variants else out[0]
 
 
 def raw_sweep(config, trial=0, n_sweeps=None):

@@ -17,8 +17,14 @@ fill a B200; independent pairs are the unit the reference's validation sweeps an
   roofline  dominant kernel k_match (exact NN + transform + histogram): algorithmic bytes 24 B/reading point per launch
             over its CUDA-event duration, against the measured HBM copy peak.
   cpu_baseline  the CPU oracle (a restatement of the reference's libpointmatcher path; the real one cannot be built here)
-            on the same pair on this box's host cores.
-Multi-GPU: independent pairs are sharded over ranks with no data-path collective (weak scaling).
+            on the same pair set on this box's host cores.
+Every step registers the same D = 16 DISTINCT pairs (4 ray-cast scenes x 4 erroneous prior poses, separate buffers), P / D times
+each; the reference arm (--impl reference) cycles through the same D pairs with the same ratios, so both arms average over the
+same ICP trajectories.
+Multi-GPU: independent pairs are sharded over ranks with no data-path collective (weak scaling).  With more than one rank
+the line also carries "sharded": ONE registration whose reading is sharded over all ranks (BASELINE.json configs[3]) -- the C3
+pair and a 122 880-point reading against a 10 485 760-point map -- timed against the same registration on one GPU and
+checked bit for bit against it.
 """
 import argparse
 import json
@@ -38,18 +44,59 @@ N_POINTS = 131072
 CACHE = os.path.join(tempfile.gettempdir(), "aicp_b200_bench_cache")
 
 
-def load_pair(trial, n_points=N_POINTS):
+N_VARIANTS = 4          # erroneous prior poses per ray-cast scene
+D_MAX = 16              # distinct pairs per step
+
+
+def _scene_path(scene, n_points):
+    return os.path.join(CACHE, "c3_s%d_n%d_v%d.npz" % (scene, n_points, N_VARIANTS))
+
+
+def _make_scene(job):
+    scene, n_points = job
     from aicp_mapping_b200 import synth
-    os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, "c3_t%d_n%d.npz" % (trial, n_points))
+    path = _scene_path(scene, n_points)
     if os.path.exists(path):
-        z = np.load(path)
-        return dict(ref=z["ref"], read=z["read"], ref_origin=z["ref_origin"], read_origin=z["read_origin"])
-    p = synth.make_pair(3, trial, n_points)
+        return path
+    vs = synth.make_pair(3, scene, n_points, variants=N_VARIANTS)
     tmp = path + ".%d.tmp.npz" % os.getpid()
-    np.savez(tmp, ref=p["ref"], read=p["read"], ref_origin=p["ref_origin"], read_origin=p["read_origin"])
+    np.savez(tmp, ref=vs[0]["ref"], ref_origin=vs[0]["ref_origin"], read=np.stack([v["read"] for v in vs]),
+             read_origin=np.stack([v["read_origin"] for v in vs]))
     os.replace(tmp, path)
-    return p
+    return path
+
+
+def load_pairs(n_distinct, n_points=N_POINTS, generate=True):
+    """The D distinct C3 pairs of a step: pair k = scene k // 4 (one ray cast of synth.make_pair(3, scene)), prior-pose variant
+    k % 4.  Scenes are cached under the temp directory; missing ones are ray-cast in parallel by forked workers (call this
+    before CUDA is initialised).  generate=False (ranks other than local rank 0): wait for the files instead."""
+    import multiprocessing as mp
+    os.makedirs(CACHE, exist_ok=True)
+    n_scenes = (n_distinct + N_VARIANTS - 1) // N_VARIANTS
+    missing = [(sc, n_points) for sc in range(n_scenes) if not os.path.exists(_scene_path(sc, n_points))]
+    if missing and generate:
+        if len(missing) == 1:
+            _make_scene(missing[0])
+        else:
+            with mp.get_context("fork").Pool(min(len(missing), os.cpu_count() or 1)) as pool:
+                pool.map(_make_scene, missing)
+    t0 = time.time()
+    while any(not os.path.exists(_scene_path(sc, n_points)) for sc in range(n_scenes)):
+        if time.time() - t0 > 900:
+            raise RuntimeError("bench inputs were not generated within 900 s")
+        time.sleep(0.5)
+    pairs = []
+    for k in range(n_distinct):
+        z = np.load(_scene_path(k // N_VARIANTS, n_points))
+        v = k % N_VARIANTS
+        pairs.append(dict(ref=z["ref"], read=np.ascontiguousarray(z["read"][v]), ref_origin=z["ref_origin"],
+                          read_origin=z["read_origin"][v]))
+    return pairs
+
+
+def load_pair(trial, n_points=N_POINTS):
+    """Pair `trial` of the distinct set (tools/)."""
+    return load_pairs(trial + 1, n_points)[trial]
 
 
 def profiled_traffic():
@@ -122,56 +169,90 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_oracle(pair, ratio, threads, reading_normals, repeats):
+def oracle_register(pair, ratio, threads, reading_normals):
+    """One registration by the CPU oracle; returns (seconds, ICP iterations)."""
     from oracle import oracle as orc
     cfg = orc.default_config(ratio=ratio, threads=threads, reading_normals=reading_normals, use_kdtree=1)
-    times, iters = [], 0
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        out = orc.icp(pair["ref"], pair["read"], cfg, want_reading=True)
-        times.append(time.perf_counter() - t0)
-        iters = out.iterations
-        if out.rc != 0:
-            raise RuntimeError("oracle failed: " + out.error)
-    return float(np.median(times)), iters
+    t0 = time.perf_counter()
+    out = orc.icp(pair["ref"], pair["read"], cfg, want_reading=True)
+    sec = time.perf_counter() - t0
+    if out.rc != 0:
+        raise RuntimeError("oracle failed: " + out.error)
+    return sec, out.iterations
+
+
+def oracle_ratios(pairs):
+    """The auto-tuned ratio of every pair (octree overlap -> clamp -> 6-digit text round trip) from the CPU oracle; equal to
+    the GPU arm's by the overlap parity tests."""
+    from oracle import oracle as orc
+    out = []
+    for p in pairs:
+        ov, _ = orc.overlap(p["ref"], p["ref_origin"], p["read"], p["read_origin"])
+        out.append(float(orc.autotune_ratio(float(ov))[0]))
+    return out
+
+
+REF_REGS_PER_STEP = 4      # the reference arm's step: a bounded sample of the GPU arm's step (4 of its P registrations)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  libpointmatcher/libnabo/octomap cannot be built in
-    this image (no Eigen/PCL/yaml-cpp either), so this times the oracle port with every host thread it can use."""
+    this image (no Eigen/PCL/yaml-cpp either), so this times the oracle port with every host thread it can use, on the
+    GPU arm's pair set: step s registers pairs 4s .. 4s+3 (mod D) of the same D distinct pairs with the same ratios, and
+    --steps / --warmup are honoured.  The reading-side SurfaceNormal filter of the reference's chain, which PointToPlane never
+    reads and the GPU arm skips, is NOT in the timed value (it is reported beside it)."""
     if rank != 0:
         return
-    from oracle import oracle as orc
-    pair = load_pair(0)
-    ov, _ = orc.overlap(pair["ref"], pair["ref_origin"], pair["read"], pair["read_origin"])
-    ratio, _ = orc.autotune_ratio(float(ov))
-    ratio = float(ratio)
+    D = min(args.pairs, D_MAX)
+    pairs = load_pairs(D)
+    ratios = oracle_ratios(pairs)
     cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        time_oracle(pair, ratio, cores, 1, 1)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    sec, iters = time_oracle(pair, ratio, cores, 1, steps)
-    value = 1.0 / sec
-    sample = "%d registration(s) of C3 pair trial 0 (131072 x 131072 pts, ratio %.6f, %d ICP iterations), kd-tree oracle incl. the reading SurfaceNormal filter, OpenMP over queries" % (steps, ratio, iters)
+    R = REF_REGS_PER_STEP
+    k = 0
+    for _ in range(args.warmup):
+        for _ in range(R):
+            oracle_register(pairs[k % D], ratios[k % D], cores, 0)
+            k += 1
+    t_wall0 = time.perf_counter()
+    sec, iters = 0.0, 0
+    for _ in range(args.steps):
+        for _ in range(R):
+            s_, it_ = oracle_register(pairs[k % D], ratios[k % D], cores, 0)
+            sec += s_; iters += it_
+            k += 1
+    n_reg = args.steps * R
+    value = n_reg / sec
+    sec_full, _ = oracle_register(pairs[0], ratios[0], cores, 1)
+    sec_lean, _ = oracle_register(pairs[0], ratios[0], cores, 0)
+    sample = ("%d registrations per step, cycling through the GPU arm's %d distinct C3 pairs (131072 x 131072 pts, same auto-tuned "
+              "ratios, mean %.2f ICP iterations), kd-tree oracle WITHOUT the dead reading-side SurfaceNormal filter, OpenMP over "
+              "queries on %d threads" % (R, D, iters / n_reg, cores))
+    cfg = workload_config(R, "n/a (CPU)", D, iters / n_reg)
     line = {"impl": "reference", "metric": "ICP registrations/sec (128k pts)", "value": value, "unit": "registrations/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1, "n/a (CPU)"),
-            "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": "port", "sample": sample,
+                             "pair0_with_reading_normals": 1.0 / sec_full, "pair0_without_reading_normals": 1.0 / sec_lean},
             "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(pairs, l2):
+def workload_config(pairs, l2, distinct, iterations_mean):
     return {"workload": "C3: Velodyne HDL-64 KITTI-shaped synthetic clouds, ground removed, 131072 reading x 131072 reference points, "
                         "point-to-plane ICP chain of icp_autotuned.yaml (knn 20 normals, exact 1-NN epsilon 0, trimmed ratio auto-tuned "
                         "from the octree overlap, <=20 iterations, differential stop 0.001 rad / 0.01 m / 4)",
-            "pairs_per_gpu_per_step": pairs, "points_per_cloud": N_POINTS, "l2": l2, "parallelism": "independent pairs sharded over GPUs"}
+            "pairs_per_gpu_per_step": pairs, "pairs_distinct": distinct, "iterations_mean": iterations_mean,
+            "points_per_cloud": N_POINTS, "l2": l2, "parallelism": "independent pairs sharded over GPUs"}
 
 
 def run_b200(args, rank, world, local_rank):
+    P = args.pairs
+    D = min(P, D_MAX)
+    # weak scaling: every rank registers the SAME P pairs per step -- D distinct pairs (4 scenes x 4 prior poses, 5 to 9 ICP
+    # iterations), each P / D times -- so that per-GPU work is identical for every N
+    pairs = load_pairs(D, generate=(local_rank == 0))      # before CUDA is initialised: the ray casts run in forked workers
     import torch
     import aicp_mapping_b200 as ab
     from aicp_mapping_b200 import capi
@@ -181,11 +262,6 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    P = args.pairs
-    # weak scaling: every rank registers the SAME P pairs per step (the two seeded C3 pairs, 9 and 6 ICP iterations), so
-    # that per-GPU work is identical for every N; different pairs per rank would make the slowest pair set the job time
-    trials = [i % 16 for i in range(min(P, 2))]
-    pairs = [load_pair(t) for t in trials]
     reg = ab.B200Registration(device=local_rank)
     ovl = ab.B200Overlap(device=local_rank)
     reg.setMatchSchedule(args.match_schedule)
@@ -196,7 +272,7 @@ def run_b200(args, rank, world, local_rank):
         ovl.computeOverlap(p["ref"], p["read"], p["ref_origin"], p["read_origin"])
         ratios.append(ab.autotune_ratio(float(ovl.getOverlap())))
         r4, q4 = capi.to_xyzw(p["ref"]), capi.to_xyzw(p["read"])
-        dev.append((torch.from_numpy(r4).cuda(), torch.from_numpy(q4).cuda()))
+        dev.append((torch.from_numpy(r4).cuda(), torch.from_numpy(q4).cuda()))      # one buffer per pair and cloud, also for shared scans
         hr, hq = torch.from_numpy(r4).pin_memory(), torch.from_numpy(q4).pin_memory()
         host.append((hr, hq, hr.numpy(), hq.numpy()))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
@@ -287,7 +363,7 @@ def run_b200(args, rank, world, local_rank):
 
     # single-stream latency of one registration (no concurrency), for the roofline of the dominant kernel in isolation
     lat = dict(ms=0.0, match=0.0, iters=0, n=0)
-    for k in range(0 if args.profile_run else len(pairs)):
+    for k in range(0 if args.profile_run else min(4, len(pairs))):
         for j in range(4):
             reg.setConfig(ratio=ratios[k])
             flush.zero_()
@@ -319,7 +395,7 @@ def run_b200(args, rank, world, local_rank):
         line = {"metric": "ICP registrations/sec (128k pts)", "value": value, "unit": "registrations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(P, "flushed before every step (256 MiB write)"), streams_per_gpu=S),
+                "config": dict(workload_config(P, "flushed before every step (256 MiB write)", D, I), streams_per_gpu=S),
                 "roofline": {"bound": "hbm", "kernel": "k_match_tile (k_match for the cold first iteration)" if S > 1 else "k_match",
                              "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": profiled_traffic()[0], "traffic_source": profiled_traffic()[1],
@@ -343,18 +419,112 @@ def run_b200(args, rank, world, local_rank):
                 "gpu_launches": int(agg["launches"]), "clocks": clocks, "wall_s": wall_s, "ratios": ratios}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            sec_all, it_all = time_oracle(pairs[0], ratios[0], cores, 1, 3)
-            sec_one, _ = time_oracle(pairs[0], ratios[0], 1, 1, 1)
-            sec_lean, _ = time_oracle(pairs[0], ratios[0], cores, 0, 1)
-            line["cpu_baseline"] = {"value": 1.0 / sec_all, "unit": "registrations/s", "cores": cores, "kind": "port",
-                                    "sample": "3 registrations of C3 pair trial %d (131072 x 131072 pts, %d iterations) with the kd-tree "
-                                              "oracle incl. the reading SurfaceNormal filter, OpenMP over queries on all cores; "
-                                              "median" % (trials[0], it_all),
-                                    "value_1thread": 1.0 / sec_one, "value_without_reading_normals": 1.0 / sec_lean}
+            sec_all, it_all = 0.0, 0
+            for k in range(D):                  # the step's D distinct pairs once each: ~5 s on 16 cores
+                s_, i_ = oracle_register(pairs[k], ratios[k], cores, 0)
+                sec_all += s_; it_all += i_
+            sec_one, _ = oracle_register(pairs[0], ratios[0], 1, 0)
+            sec_full, _ = oracle_register(pairs[0], ratios[0], cores, 1)
+            line["cpu_baseline"] = {"value": D / sec_all, "unit": "registrations/s", "cores": cores, "kind": "port",
+                                    "sample": "one registration of each of the step's %d distinct C3 pairs (131072 x 131072 pts, mean "
+                                              "%.2f iterations) with the kd-tree oracle, OpenMP over queries on all cores, without the "
+                                              "dead reading-side SurfaceNormal filter (skipped by the GPU arm too)" % (D, it_all / D),
+                                    "value_1thread_pair0": 1.0 / sec_one, "value_pair0_with_reading_normals": 1.0 / sec_full}
+    else:
+        line = None
+    if world > 1 and not args.no_sharded and not args.profile_run:
+        # a hang of the extra leg (a rank lost, a collective mismatch) must not cost the round its headline line: after
+        # 300 s every rank gives up, rank 0 printing the line it already has
+        def give_up():
+            if line is not None:
+                line["sharded"] = {"error": "the sharded leg did not finish within 300 s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(300.0, give_up)
+        dog.daemon = True
+        dog.start()
+        res = sharded_leg(args, rank, world, local_rank, dist, dev, pairs, ratios)
+        dog.cancel()
+        if line is not None:
+            line["sharded"] = res
+    if line is not None:
         print(json.dumps(line), flush=True)
     reg.close(); ovl.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def sharded_leg(args, rank, world, local_rank, dist, dev, pairs, ratios):
+    """ONE registration with its reading sharded over all ranks (BASELINE.json configs[3]; reference shape app.cpp:41-69,
+    123-127): the reference index is replicated, every rank matches its slice of the reading, and per iteration the ranks
+    exchange the trimmed-quantile digits and the 27 normal-equation sums.  Two cases -- the C3 pair, and a 122 880-point
+    reading against a --map-points map with the index built once -- each timed against the same registration on one GPU
+    (device time of the call, max over ranks, median of the repetitions) and compared with it bit for bit."""
+    import torch
+    import aicp_mapping_b200 as ab
+    from aicp_mapping_b200 import capi, synth
+    from aicp_mapping_b200.registration import comm_unique_id
+    out = {"world": world}
+    u32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+    def vmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def all_true(ok):
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t[0]))
+
+    single = sh = None
+    try:
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        single = ab.B200Registration(device=local_rank)
+        sh = ab.B200Registration(device=local_rank)
+        sh.commInit(uid[0], rank, world)
+        out["exchange"] = sh.commInfo()
+
+        def case(ref_dev, read_dev, ratio, fixed_reference, reps=7):
+            shard = read_dev[rank::world].contiguous()
+            torch.cuda.synchronize()
+            res = {}
+            for name, r, q in (("single", single, read_dev), ("sharded", sh, shard)):
+                r.setConfig(ratio=ratio)
+                if fixed_reference:
+                    r.setReference(ref_dev)
+                ms, wall, T = [], [], None
+                for k in range(reps + 1):
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    t0 = time.perf_counter()
+                    T = r.registerToReference(q) if fixed_reference else r.registerClouds(ref_dev, q)
+                    w = time.perf_counter() - t0
+                    if k > 0:                   # the first call allocates (and, with a fixed reference, builds the map index)
+                        ms.append(vmax(r.stats.ms_total)); wall.append(vmax(w * 1e3))
+                res[name] = (float(np.median(ms)), float(np.median(wall)), T, int(r.stats.iterations))
+            same = all_true(np.array_equal(u32(res["single"][2]), u32(res["sharded"][2])) and res["single"][3] == res["sharded"][3])
+            return {"ms_per_registration": res["sharded"][0], "ms_single_gpu": res["single"][0],
+                    "speedup": res["single"][0] / res["sharded"][0], "wall_ms_per_registration": res["sharded"][1],
+                    "wall_ms_single_gpu": res["single"][1], "iterations": res["sharded"][3], "bit_identical_to_single_gpu": same,
+                    "n_reference": int(ref_dev.shape[0]), "n_reading": int(read_dev.shape[0])}
+
+        out["c3"] = case(dev[0][0], dev[0][1], ratios[0], False)
+        mp_ = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=1)
+        map_dev = torch.from_numpy(capi.to_xyzw(mp_["map"])).cuda()
+        read_dev = torch.from_numpy(capi.to_xyzw(mp_["readings"][0]["read"])).cuda()
+        out["c4"] = case(map_dev, read_dev, ab.autotune_ratio(50.0), True)      # app.cpp:123-127: overlap forced to 50 % against a prior map
+        del map_dev
+    except Exception as e:      # reported, not fatal: the headline line does not depend on this leg
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    for r in (sh, single):
+        try:
+            if r is not None:
+                r.close()
+        except Exception:
+            pass
+    return out
 
 
 def main():
@@ -366,6 +536,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=64, help="cloud pairs registered per GPU per step")
     ap.add_argument("--streams", type=int, default=8, help="concurrent registrations per GPU (CUDA streams)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded single-registration leg (world > 1)")
+    ap.add_argument("--map-points", type=int, default=10485760, help="map size of the sharded C4 case")
     ap.add_argument("--match-schedule", type=int, default=0, help="0 auto, 1 per-thread search, 2 tile search (experiments)")
     ap.add_argument("--knn-schedule", type=int, default=0, help="0 auto, 1 warp-per-query k-NN, 2 tile k-NN (experiments)")
     ap.add_argument("--no-profile", action="store_true", help="no per-stage CUDA events inside the registrations")

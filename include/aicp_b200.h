@@ -12,6 +12,10 @@
  *   - transforms: 16 floats, column-major 4x4 == Eigen::Matrix4f::data().
  *   - every pointer argument may be a host pointer or a device pointer of the handle's device; the library detects
  *     which (cudaPointerGetAttributes).  Host buffers are copied through the handle's stream.
+ *   - STREAM ORDER of device-pointer inputs: the library reads them on its own non-blocking stream(s), which are not
+ *     ordered against the caller's streams.  The data must be complete when the call is made (synchronise the producing
+ *     stream), or the caller declares the producer once with aicp_b200_wait_stream(h, stream) before the call.  Results
+ *     are complete when a call returns (every compute entry point synchronises its stream before returning).
  *   - all functions return AICP_B200_OK (0) or an error code; aicp_b200_last_error() gives the text.  Nothing here
  *     calls exit() (the reference does: pointmatcher_registration.cpp:60-64,96-100).
  *   - a handle is used by one thread at a time (same contract as the reference: app.cpp:528-550).
@@ -112,6 +116,11 @@ typedef struct {
  * icp_.setDefault() in that case, pointmatcher_registration.cpp:51-55).  device: CUDA ordinal, or -1 for the current one. */
 int aicp_b200_create(const char* icp_yaml_path, int device, aicp_b200_handle** out);
 int aicp_b200_destroy(aicp_b200_handle* h);
+/* Orders all work the handle (and its batch workers) enqueues from now on after everything already enqueued on
+ * `cuda_stream` (a cudaStream_t of the handle's device; NULL = the legacy default stream): the call to make between
+ * producing a device-resident input on another stream and handing its pointer to this library.  No reference
+ * counterpart (the reference is synchronous host code). */
+int aicp_b200_wait_stream(aicp_b200_handle* h, void* cuda_stream);
 const char* aicp_b200_last_error(const aicp_b200_handle* h);   /* h may be NULL: error of the last failed create */
 const char* aicp_b200_version(void);
 
@@ -363,6 +372,8 @@ int aicp_b200_pipeline_batch(aicp_b200_handle* h, int64_t n_pairs, const float* 
 int aicp_b200_comm_unique_id(uint8_t id_out[128]);
 int aicp_b200_comm_init(aicp_b200_handle* h, const uint8_t nccl_unique_id[128], int rank, int n_ranks);
 int aicp_b200_comm_destroy(aicp_b200_handle* h);
+/* Human-readable description of the exchange the communicator performs per ICP iteration (written to buf, NUL-terminated). */
+int aicp_b200_comm_info(aicp_b200_handle* h, char* buf, int len);
 
 #ifdef __cplusplus
 }
