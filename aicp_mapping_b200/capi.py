@@ -20,7 +20,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_wait_stream", "ai
            "aicp_b200_set_config_struct", "aicp_b200_get_config", "aicp_b200_parse_icp_yaml", "aicp_b200_register",
            "aicp_b200_set_reference", "aicp_b200_register_to_reference", "aicp_b200_get_output_reading",
            "aicp_b200_get_initialized_reading", "aicp_b200_get_reference_normals", "aicp_b200_enable_match_trace",
-           "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
+           "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_set_loop_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
            "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_prefilter_default_config", "aicp_b200_prefilter", "aicp_b200_get_prefiltered",
            "aicp_b200_prefilter_get_sampled", "aicp_b200_prefilter_get_normals", "aicp_b200_prefilter_get_labels", "aicp_b200_voxel_grid",
            "aicp_b200_map_prefilter", "aicp_b200_accumulate_sweep", "aicp_b200_get_accumulated", "aicp_b200_download_accumulated", "aicp_b200_read_pcd", "aicp_b200_read_ply",
@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("ms_setup", C.c_float), ("ms_iterations", C.c_float), ("gpu_launches", C.c_int32),
                 ("profiled", C.c_int32), ("ms_index", C.c_float), ("ms_normals", C.c_float), ("ms_match", C.c_float),
                 ("ms_select", C.c_float), ("ms_accumulate", C.c_float), ("ms_tail_pick", C.c_float), ("ms_tail_select", C.c_float),
-                ("ms_tail_solve", C.c_float), ("trace", IterTrace * MAX_ITERS)]
+                ("ms_tail_solve", C.c_float), ("ms_exchange", C.c_float), ("trace", IterTrace * MAX_ITERS)]
 
 
 class PrefilterConfig(C.Structure):
@@ -109,6 +109,7 @@ def lib():
         L.aicp_b200_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.aicp_b200_set_knn_schedule.argtypes = [C.c_void_p, C.c_int]
         L.aicp_b200_set_match_schedule.argtypes = [C.c_void_p, C.c_int]
+        L.aicp_b200_set_loop_schedule.argtypes = [C.c_void_p, C.c_int]
         L.aicp_b200_get_trace_matches.argtypes = [C.c_void_p, C.c_void_p, i64, i64]
         L.aicp_b200_surface_normals.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_int32, C.c_void_p, C.c_void_p]
         L.aicp_b200_match.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p]

@@ -319,6 +319,13 @@ int aicp_b200_set_match_schedule(aicp_b200_handle* hh, int schedule) {
   return AICP_B200_OK;
 }
 
+int aicp_b200_set_loop_schedule(aicp_b200_handle* hh, int schedule) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h || schedule < 0 || schedule > 2) return AICP_B200_ERR_BAD_ARG;
+  h->loop_schedule = schedule;
+  return AICP_B200_OK;
+}
+
 int aicp_b200_get_trace_matches(aicp_b200_handle* hh, int32_t* idx, int64_t iters, int64_t n_read) {
   Handle* h = reinterpret_cast<Handle*>(hh);
   H_CHECK(h);
@@ -798,7 +805,8 @@ static int batch_impl(aicp_b200_handle* hh, int64_t n_pairs, const float* const*
     Handle* wh = h->workers[w];
     wh->cfg = h->cfg; wh->cfg_from_file = false;
     wh->profiling = h->profiling; wh->trace_matches = false;
-    wh->batch_worker = streams > 1; wh->knn_schedule = h->knn_schedule; wh->match_schedule = h->match_schedule;
+    wh->batch_worker = streams > 1; wh->batch_streams = streams; wh->knn_schedule = h->knn_schedule; wh->match_schedule = h->match_schedule;
+    wh->loop_schedule = h->loop_schedule;
     if (risk && wh->svm_path != risk->model_path) {
       if ((rc = svm_load(wh, risk->model_path))) return fail(h, rc, "pipeline_batch: %s", wh->last_error.c_str());
       wh->svm_path = risk->model_path;

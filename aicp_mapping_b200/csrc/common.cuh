@@ -53,6 +53,11 @@ struct DeviceState {
   unsigned int ticket[4];
   unsigned int cand_n;              // candidate keys appended by k_select23
   unsigned long long tail_ns[3];    // time spent in the single-block tails: digit-1 pick, digits 2+3, solve + checkers
+  // persistent loop kernel (k_icp_loop): grid barrier words and per-phase clocks (globaltimer ns, taken by the block that
+  // runs a phase's serial section): [0] search, [1] quantile, [2] normal equations + solve, [3] peer exchanges
+  unsigned int bar_arrive, bar_release;
+  unsigned long long phase_ns[4];
+  unsigned long long t_mark;
   // normal equations, 128-bit two's complement fixed point
   unsigned long long sum_lo[AICP_NSUM];
   long long sum_hi[AICP_NSUM];
@@ -63,6 +68,27 @@ struct DeviceState {
   double ang_step[AICP_B200_MAX_ITERS + 1];   // |angularDistance(q_i, q_{i-1})|, cached so each iteration computes one
   double trn_step[AICP_B200_MAX_ITERS + 1];   // ||t_i - t_{i-1}||
   aicp_b200_iter_trace trace[AICP_B200_MAX_ITERS];
+};
+
+// ---- sharded registration over peer-mapped memory (comm.cu, icp.cu) ---------------------------------------------------
+// Every rank owns one INBOX in its own HBM; every peer maps it (CUDA IPC between processes, peer access inside one) and
+// stores its contribution for this rank there, then raises a sequence-stamped flag.  Layout of an inbox, per SOURCE rank s:
+//   flags  @ FLAGS_OFF + 64 s      three 64-bit stamps (round 0 histogram, 1 candidates, 2 sums): epoch << 24 | (4 iter + round + 1) << 1 | status
+//   sums   @ SUMS_OFF  + 512 s     28 x (lo, hi) 128-bit partial sums
+//   hist   @ HIST_OFF  + 8192 s    2048 x uint32 digit-1 histogram of the source's shard
+//   cand   @ CAND_OFF  + stride s  uint32 count, 12 bytes padding, then the source's candidate keys (capacity: its shard size)
+#define AICP_MAX_RANKS 16
+#define AICP_INBOX_FLAGS_OFF 0
+#define AICP_INBOX_SUMS_OFF 1024
+#define AICP_INBOX_HIST_OFF (AICP_INBOX_SUMS_OFF + 512 * AICP_MAX_RANKS)
+#define AICP_INBOX_CAND_OFF (AICP_INBOX_HIST_OFF + AICP_HIST_BINS * 4 * AICP_MAX_RANKS)
+#define AICP_PEER_TIMEOUT_NS 10000000000ull      // a peer that does not show up within 10 s ends the loop with AICP_B200_ERR_COMM
+
+struct PeerView {
+  int rank, n_ranks;                       // n_ranks <= 1: no exchange
+  unsigned long long epoch;                // registration sequence number, the same on every rank
+  unsigned char* inbox[AICP_MAX_RANKS];    // inbox[r] = rank r's inbox as mapped into this process (inbox[rank]: local memory)
+  size_t cand_stride;                      // bytes between two sources' candidate areas
 };
 
 struct LoopParams {

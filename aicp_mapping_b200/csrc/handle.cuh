@@ -95,6 +95,10 @@ struct Handle {
   int knn_schedule = 0;          // SurfaceNormal k-NN kernel: 0 auto, 1 warp per query (latency), 2 tile per warp (throughput)
   int match_schedule = 0;        // correspondence search kernel: 0 auto, 1 one query per thread (k_match), 2 one tile per warp (k_match_tile)
   bool batch_worker = false;     // this handle is one of the concurrent workers of aicp_b200_register_batch
+  int batch_streams = 1;         // how many such workers share the GPU (the persistent loop kernel takes 1 / batch_streams of its blocks)
+  int loop_schedule = 0;         // ICP loop: 0 auto, 1 three launches per iteration + host look-ahead, 2 one persistent cooperative kernel
+  int loop_occ[2] = {0, 0};      // co-resident blocks per SM of k_icp_loop<false / true>
+  int n_sm = 0;
   int profiling = 0;             // 0 off, 1 CUDA events around k_match only, 2 around every stage
   std::vector<cudaEvent_t> prof_ev;   // 3 setup + 4 per iteration
   int64_t trace_iters = 0, trace_n = 0;
@@ -199,6 +203,7 @@ int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count);
 unsigned long long* comm_limbs(Handle* h);
 long long comm_total_reading(Handle* h);
 int comm_begin_registration(Handle* h, long long n_read_local);
+bool comm_peer_view(Handle* h, PeerView* pv);      // true when the exchange runs over peer-mapped memory inside the loop kernel
 // ---- config_yaml.cpp
 int parse_icp_yaml(const char* path, aicp_b200_icp_config* cfg, std::string* err);
 void default_icp_config(aicp_b200_icp_config* cfg);

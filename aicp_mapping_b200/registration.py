@@ -329,6 +329,12 @@ class B200Registration:
         """0 automatic, 1 per-thread correspondence search, 2 tile search (identical results)."""
         self._check(self._lib.aicp_b200_set_match_schedule(self._h, int(schedule)))
 
+    def setLoopSchedule(self, schedule=0):
+        """0 automatic (persistent kernel for single and sharded registrations, multi-launch inside batches), 1 three launches
+        per iteration with the host staying two iterations ahead, 2 one persistent cooperative kernel for the whole loop
+        (identical results)."""
+        self._check(self._lib.aicp_b200_set_loop_schedule(self._h, int(schedule)))
+
     def getTraceMatches(self):
         it, n = int(self.stats.iterations), int(self.stats.n_read)
         out = np.zeros((it, n), dtype=np.int32)

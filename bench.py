@@ -266,6 +266,7 @@ def run_b200(args, rank, world, local_rank):
     ovl = ab.B200Overlap(device=local_rank)
     reg.setMatchSchedule(args.match_schedule)
     reg.setKnnSchedule(args.knn_schedule)
+    reg.setLoopSchedule(args.loop_schedule)
     reg.setProfiling(0 if args.no_profile else 1)     # CUDA events around k_match only inside the timed region
     dev, host, ratios = [], [], []
     for p in pairs:
@@ -540,6 +541,7 @@ def main():
     ap.add_argument("--map-points", type=int, default=10485760, help="map size of the sharded C4 case")
     ap.add_argument("--match-schedule", type=int, default=0, help="0 auto, 1 per-thread search, 2 tile search (experiments)")
     ap.add_argument("--knn-schedule", type=int, default=0, help="0 auto, 1 warp-per-query k-NN, 2 tile k-NN (experiments)")
+    ap.add_argument("--loop-schedule", type=int, default=0, help="0 persistent loop kernel, 1 three launches per iteration (experiments)")
     ap.add_argument("--no-profile", action="store_true", help="no per-stage CUDA events inside the registrations")
     ap.add_argument("--profile-run", action="store_true", help="device-resident leg only (the command profiled under ncu)")
     args = ap.parse_args()

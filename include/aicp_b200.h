@@ -83,8 +83,10 @@ typedef struct {
    * over the iterations that actually ran (level 1: ms_match only) */
   int32_t profiled;
   float   ms_index, ms_normals;       /* setup: Morton index build, SurfaceNormal filter */
-  float   ms_match, ms_select, ms_accumulate;   /* loop: k_match, k_select23, k_accumulate(+solve) */
+  float   ms_match, ms_select, ms_accumulate;   /* loop: search, trimmed quantile, normal equations + solve.  Persistent loop kernel
+                                                 * (the default): always filled, from the kernel's own phase clocks */
   float   ms_tail_pick, ms_tail_select, ms_tail_solve;   /* of which: single-block tails (device globaltimer) */
+  float   ms_exchange;                /* sharded registration: time the loop kernel spent waiting for its peers' flags */
   aicp_b200_iter_trace trace[AICP_B200_MAX_ITERS];
 } aicp_b200_stats;
 
@@ -175,6 +177,12 @@ int aicp_b200_set_knn_schedule(aicp_b200_handle* h, int schedule);
 /* kernel schedule of the ICP correspondence search (identical results): 0 automatic (tile kernel inside batched registrations), 1 one query per thread (k_match),
  * 2 one tile of 32 queries per warp with a shared tree walk (k_match_tile) */
 int aicp_b200_set_match_schedule(aicp_b200_handle* h, int schedule);
+/* how the ICP loop (ICP::compute's while(iterate)) is driven (identical results):
+ * 2 ONE persistent cooperative kernel runs every iteration -- grid barriers between the phases, loop control on the device,
+ *   the sharded exchange inside the kernel;
+ * 1 three launches per iteration with the host staying two iterations ahead of a progress word;
+ * 0 automatic: 2 for one registration at a time and for the sharded registration, 1 inside batches (measured) */
+int aicp_b200_set_loop_schedule(aicp_b200_handle* h, int schedule);
 
 /* ---- stage entry points (same kernels as aicp_b200_register; exposed for the parity tests) -----------------------
  * SurfaceNormalDataPointsFilter alone: out_normals n x 4, out_knn nullable n x knn (ids sorted by (d2, id)) */

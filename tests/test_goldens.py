@@ -57,7 +57,7 @@ def test_oracle_reproduces_golden(orc, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("schedules", [(1, 1), (2, 2)])
+@pytest.mark.parametrize("schedules", [(1, 1, 2), (2, 2, 2), (2, 2, 1)])      # (match, k-NN, loop): loop 2 persistent kernel, 1 multi-launch
 @pytest.mark.parametrize("name", sorted(GOLD))
 def test_cuda_reproduces_golden(name, schedules):
     g, p = GOLD[name], inputs(name)
@@ -68,7 +68,7 @@ def test_cuda_reproduces_golden(name, schedules):
     ovl.close()
     reg = ab.B200Registration()
     reg.setConfig(ratio=g["ratio"], **g["config"])
-    reg.setMatchSchedule(schedules[0]); reg.setKnnSchedule(schedules[1])
+    reg.setMatchSchedule(schedules[0]); reg.setKnnSchedule(schedules[1]); reg.setLoopSchedule(schedules[2])
     reg.enableMatchTrace(True)
     T = reg.registerClouds(p["ref"], p["read"])
     check(g, T, reg.stats.iterations, reg.stats.stop_reason, reg.trace(), reg.getTraceMatches(), reg.getReferenceNormals(),

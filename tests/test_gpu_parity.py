@@ -187,14 +187,31 @@ def test_icp_parity_c1_sample_scans(reg, orc):
         assert_full_parity(reg, T, o)
 
 
-@pytest.mark.parametrize("match_schedule,knn_schedule", [(1, 1), (2, 2)])
-def test_icp_parity_c2_vlp16(reg, orc, pair_cache, match_schedule, knn_schedule):
-    """Whole trajectory against the oracle with the per-thread kernels (1, 1) and with the tile kernels (2, 2)."""
-    reg.setMatchSchedule(match_schedule); reg.setKnnSchedule(knn_schedule)
+@pytest.mark.parametrize("match_schedule,knn_schedule,loop_schedule", [(1, 1, 2), (2, 2, 2), (1, 1, 1), (2, 2, 1)])
+def test_icp_parity_c2_vlp16(reg, orc, pair_cache, match_schedule, knn_schedule, loop_schedule):
+    """Whole trajectory against the oracle with the per-thread kernels (1, 1) and with the tile kernels (2, 2), driven by the
+    persistent loop kernel (2) and by three launches per iteration (1)."""
+    reg.setMatchSchedule(match_schedule); reg.setKnnSchedule(knn_schedule); reg.setLoopSchedule(loop_schedule)
     pair = pair_cache(2, 0)
     T, o = run_both(reg, orc, pair["ref"], pair["read"], 0.7)
     assert_full_parity(reg, T, o)
-    reg.setMatchSchedule(0); reg.setKnnSchedule(0)
+    reg.setMatchSchedule(0); reg.setKnnSchedule(0); reg.setLoopSchedule(0)
+
+
+def test_loop_schedules_agree_and_persistent_is_one_launch(reg, pair_cache):
+    """The persistent loop kernel and the multi-launch loop give the same bits; the persistent one costs one launch for all
+    iterations (the multi-launch loop: three per iteration), and fills the per-phase clocks of the stats."""
+    pair = pair_cache(2, 0)
+    reg.setConfig(ratio=0.7)
+    out = {}
+    for ls in (2, 1):
+        reg.setLoopSchedule(ls)
+        T = reg.registerClouds(pair["ref"], pair["read"])
+        out[ls] = (u32(T).copy(), reg.stats.iterations, reg.stats.gpu_launches, reg.stats.ms_match, u32(reg.getOutputReading()).copy())
+    reg.setLoopSchedule(0)
+    assert np.array_equal(out[2][0], out[1][0]) and out[2][1] == out[1][1] and np.array_equal(out[2][4], out[1][4])
+    assert out[1][2] - out[2][2] >= 3 * out[2][1] - 1
+    assert out[2][3] > 0.0
 
 
 @pytest.mark.parametrize("n_ref,n_qry", [(20, 7), (33, 40), (100, 31), (5000, 1000)])
@@ -402,7 +419,7 @@ def test_icp_randomised_parity_sweep(reg, orc, seed):
     P = synth.rigid(*rng.uniform(-0.05, 0.05, 3), *np.deg2rad(rng.uniform(-1.5, 1.5, 3)))
     read = synth.apply_T(P, ref[rng.integers(0, n_ref, n_read)].astype(np.float64) + 0.003 * rng.normal(size=(n_read, 3)))
     sched = 1 + seed % 2
-    reg.setMatchSchedule(sched); reg.setKnnSchedule(sched)
+    reg.setMatchSchedule(sched); reg.setKnnSchedule(sched); reg.setLoopSchedule(1 + (seed // 2) % 2)
     reg.setConfig(ratio=ratio, knn_normals=knn, max_iterations=12)
     reg.enableMatchTrace(True)
     cfg = orc.default_config(ratio=ratio, threads=NCPU, knn_normals=knn, max_iterations=12)
@@ -413,7 +430,7 @@ def test_icp_randomised_parity_sweep(reg, orc, seed):
     except capi.AicpError as e:
         T, code = None, e.code_name
     finally:
-        reg.setMatchSchedule(0); reg.setKnnSchedule(0)
+        reg.setMatchSchedule(0); reg.setKnnSchedule(0); reg.setLoopSchedule(0)
         reg.setConfig(knn_normals=20, max_iterations=20)
     assert code == o.error, (kind, n_ref, n_read, knn, ratio)
     if T is not None:
