@@ -58,6 +58,7 @@ struct DeviceState {
   unsigned int bar_arrive, bar_release;
   unsigned long long phase_ns[4];
   unsigned long long t_mark;
+  unsigned long long n_read_total;  // sharded registration: reading points over all ranks (travels with the sums)
   // normal equations, 128-bit two's complement fixed point
   unsigned long long sum_lo[AICP_NSUM];
   long long sum_hi[AICP_NSUM];
@@ -89,6 +90,7 @@ struct PeerView {
   unsigned long long epoch;                // registration sequence number, the same on every rank
   unsigned char* inbox[AICP_MAX_RANKS];    // inbox[r] = rank r's inbox as mapped into this process (inbox[rank]: local memory)
   size_t cand_stride;                      // bytes between two sources' candidate areas
+  unsigned int cand_cap;                   // keys a source's candidate area holds
 };
 
 struct LoopParams {

@@ -202,7 +202,7 @@ int comm_allreduce_u32(Handle* h, unsigned int* buf, size_t count);
 int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count);
 unsigned long long* comm_limbs(Handle* h);
 long long comm_total_reading(Handle* h);
-int comm_begin_registration(Handle* h, long long n_read_local);
+int comm_begin_registration(Handle* h, long long n_read_local, bool want_peer);
 bool comm_peer_view(Handle* h, PeerView* pv);      // true when the exchange runs over peer-mapped memory inside the loop kernel
 // ---- config_yaml.cpp
 int parse_icp_yaml(const char* path, aicp_b200_icp_config* cfg, std::string* err);

@@ -59,7 +59,7 @@ __global__ void k_loop_init(DeviceState* st, const IndexMeta* __restrict__ meta,
   for (int i = 0; i < 4; ++i) st->ticket[i] = 0;
   st->cand_n = 0;
   for (int i = 0; i < 3; ++i) st->tail_ns[i] = 0;
-  st->bar_arrive = 0; st->bar_release = 0; st->t_mark = 0;
+  st->bar_arrive = 0; st->bar_release = 0; st->t_mark = 0; st->n_read_total = 0;
   for (int i = 0; i < 4; ++i) st->phase_ns[i] = 0;
   for (int i = 0; i < AICP_NSUM; ++i) { st->sum_lo[i] = 0; st->sum_hi[i] = 0; }
   if (meta->nonfinite) { st->status = AICP_B200_ERR_NONFINITE_INPUT; st->done = 1; }
@@ -803,12 +803,17 @@ __device__ void loop_select23(DeviceState* st, unsigned int* cand, unsigned int*
   const unsigned int c_local = *(volatile unsigned int*)&st->cand_n;
   const unsigned int prefix = *(volatile unsigned int*)&st->prefix;
   if (pv.n_ranks > 1) {
+    // more candidates than a peer's inbox holds (a shard of over cand_cap points whose distances share one 11-bit digit):
+    // raised as a status, which the flag carries to every rank, so all of them end the loop together
+    const bool fits = c_local <= pv.cand_cap;
+    if (!fits && t == 0) raise_status(st, AICP_B200_ERR_COMM);
     for (int r = 0; r < pv.n_ranks; ++r) {
       if (r == pv.rank) continue;
       unsigned int* dst = reinterpret_cast<unsigned int*>(pv.inbox[r] + AICP_INBOX_CAND_OFF + (size_t)pv.rank * pv.cand_stride);
-      if (t == 0) dst[0] = c_local;
-      for (unsigned int j = t; j < c_local; j += 256) dst[4 + j] = __ldcg(&cand[j]);
+      if (t == 0) dst[0] = fits ? c_local : 0u;
+      for (unsigned int j = t; j < c_local && fits; j += 256) dst[4 + j] = __ldcg(&cand[j]);
     }
+    __syncthreads();
     peer_signal(pv, iter, 1, *(volatile int*)&st->status != 0);
     if (peer_wait(pv, st, iter, 1)) { if (t == 0) raise_status(st, AICP_B200_ERR_COMM); }
   }
@@ -881,6 +886,7 @@ __device__ void loop_fold_solve(DeviceState* st, unsigned long long* slots, cons
         if (r == pv.rank) continue;
         ulonglong2* dst = reinterpret_cast<ulonglong2*>(pv.inbox[r] + AICP_INBOX_SUMS_OFF + (size_t)pv.rank * 512);
         dst[lane] = make_ulonglong2(lo, (unsigned long long)hi);
+        if (lane == 0) dst[AICP_NSUM] = make_ulonglong2((unsigned long long)n, 0ull);      // this rank's share of the reading
       }
     }
     peer_signal(pv, iter, 2, *(volatile int*)&st->status != 0);
@@ -894,6 +900,12 @@ __device__ void loop_fold_solve(DeviceState* st, unsigned long long* slots, cons
         hi = hi + (long long)v.y + (nl < lo ? 1 : 0);
         lo = nl;
       }
+    }
+    if (threadIdx.x == 0) {
+      unsigned long long total = (unsigned long long)n;
+      for (int r = 0; r < pv.n_ranks; ++r)
+        if (r != pv.rank) total += __ldcg(reinterpret_cast<const ulonglong2*>(pv.inbox[pv.rank] + AICP_INBOX_SUMS_OFF + (size_t)r * 512) + AICP_NSUM).x;
+      st->n_read_total = total;
     }
   }
   if (w == 0 && lane < AICP_NSUM) { st->sum_lo[lane] = lo; st->sum_hi[lane] = hi; }
@@ -1297,7 +1309,9 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   const float4* read_s = h->read_ix.pts.p;
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
 
-  if (h->comm && (rc = comm_begin_registration(h, n_read))) return rc;
+  // the loop schedule is decided first (the description is at `persistent` below): it decides the carrier of a sharded exchange
+  const bool want_persistent = h->loop_schedule == 2 || (h->loop_schedule == 0 && !h->batch_worker);
+  if (h->comm && (rc = comm_begin_registration(h, n_read, want_persistent))) return rc;
   IndexView cix{h->refc_pts.p, h->refc_rec.p, h->ref_ix.owner.p, h->ref_ix.owner.p + h->ref_ix.n, h->refc_cell.p, h->ref_ix.n};
   LoopParams lp{cfg.ratio, cfg.max_iterations, cfg.min_diff_rot, cfg.min_diff_trans, cfg.smooth_length};
   const int sel_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
@@ -1321,7 +1335,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   // (the L1 stays warm across iterations).  Batch workers keep three launches per iteration: eight resident loop kernels
   // hold every register file of the GPU while they wait at their barriers, which starves the other streams' setup kernels and
   // loses the block scheduler's dynamic load balance (measured: 1905 vs 2340 registrations/s).
-  const bool persistent = (h->loop_schedule == 2 || (h->loop_schedule == 0 && !h->batch_worker)) && (!h->comm || peer_exchange);
+  const bool persistent = want_persistent && (!h->comm || peer_exchange);
   if (persistent) {
     LoopArgs la{cix, h->normals.p, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, h->cand.p, trace_idx, h->acc_slots.p, lp, pv};
     if ((rc = launch_loop(h, la, tile_match))) return rc;
@@ -1396,7 +1410,8 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     memset(stats, 0, sizeof(*stats));
     stats->iterations = hs->iter;
     stats->stop_reason = hs->stop_reason;
-    stats->weighted_point_used_ratio = (float)hs->n_used_last / (float)(h->comm ? comm_total_reading(h) : (long long)n_read);
+    const long long n_all = !h->comm ? (long long)n_read : (peer_exchange ? (long long)hs->n_read_total : comm_total_reading(h));
+    stats->weighted_point_used_ratio = (float)hs->n_used_last / (float)n_all;
     for (int d = 0; d < 3; ++d) stats->mean_ref[d] = hs->mu[d];
     stats->n_ref = n_ref; stats->n_read = n_read;
     cudaEventElapsedTime(&stats->ms_total, h->ev[0], h->ev[3]);

@@ -504,11 +504,15 @@ def sharded_leg(args, rank, world, local_rank, dist, dev, pairs, ratios):
                     w = time.perf_counter() - t0
                     if k > 0:                   # the first call allocates (and, with a fixed reference, builds the map index)
                         ms.append(vmax(r.stats.ms_total)); wall.append(vmax(w * 1e3))
-                res[name] = (float(np.median(ms)), float(np.median(wall)), T, int(r.stats.iterations))
+                st = r.stats
+                res[name] = (float(np.median(ms)), float(np.median(wall)), T, int(st.iterations),
+                             {k: round(float(getattr(st, "ms_" + k)), 4) for k in ("setup", "iterations", "match", "select", "accumulate",
+                                                                                   "exchange", "tail_pick", "tail_select", "tail_solve")})
             same = all_true(np.array_equal(u32(res["single"][2]), u32(res["sharded"][2])) and res["single"][3] == res["sharded"][3])
             return {"ms_per_registration": res["sharded"][0], "ms_single_gpu": res["single"][0],
                     "speedup": res["single"][0] / res["sharded"][0], "wall_ms_per_registration": res["sharded"][1],
                     "wall_ms_single_gpu": res["single"][1], "iterations": res["sharded"][3], "bit_identical_to_single_gpu": same,
+                    "stage_ms_rank0_last_rep": {"sharded": res["sharded"][4], "single_gpu": res["single"][4]},
                     "n_reference": int(ref_dev.shape[0]), "n_reading": int(read_dev.shape[0])}
 
         out["c3"] = case(dev[0][0], dev[0][1], ratios[0], False)

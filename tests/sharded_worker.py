@@ -99,7 +99,7 @@ def run_nccl(args):
     import torch
     import torch.distributed as dist
     import aicp_mapping_b200 as ab
-    from aicp_mapping_b200 import synth
+    from aicp_mapping_b200 import capi, synth
     from aicp_mapping_b200.registration import comm_unique_id
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -107,32 +107,61 @@ def run_nccl(args):
     rank, world = dist.get_rank(), dist.get_world_size()
     pair = synth.make_pair(args.config, args.trial, args.points)
     ratio = 0.6
-    uid = [comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
     ref_reg = ab.B200Registration(device=local)
     ref_reg.setConfig(ratio=ratio)
     T_full = ref_reg.registerClouds(pair["ref"], pair["read"])
     it_full, used_full = ref_reg.stats.iterations, ref_reg.getWeightedPointUsedRatio()
     out_full = ref_reg.getOutputReading()
-    reg = ab.B200Registration(device=local)
-    reg.setConfig(ratio=ratio)
-    reg.commInit(uid[0], rank, world)
-    shard = np.arange(rank, pair["read"].shape[0], world)
-    T = reg.registerClouds(pair["ref"], pair["read"][shard])
     u32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
-    ok = (np.array_equal(u32(T), u32(T_full)) and reg.stats.iterations == it_full and
-          np.float32(reg.getWeightedPointUsedRatio()) == np.float32(used_full) and
-          np.array_equal(u32(reg.getOutputReading()), u32(out_full[shard])))
-    # fixed-reference mode with the sharded reading (BASELINE.json config 4 shape)
-    reg.setReference(pair["ref"])
-    T2 = reg.registerToReference(pair["read"][shard])
-    ok = ok and np.array_equal(u32(T2), u32(T_full))
+    shard = np.arange(rank, pair["read"].shape[0], world)
+    ok, info = True, []
+    # both carriers of the exchange: peer-mapped inboxes inside the persistent loop kernel (default), NCCL all-reduces
+    for carrier in ("peer", "nccl"):
+        if carrier == "nccl":
+            os.environ["AICP_B200_COMM"] = "nccl"
+        else:
+            os.environ.pop("AICP_B200_COMM", None)
+        uid = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        reg = ab.B200Registration(device=local)
+        reg.setConfig(ratio=ratio)
+        reg.commInit(uid[0], rank, world)
+        desc = reg.commInfo()
+        if carrier == "peer" and "peer-mapped" not in desc:
+            info.append("peer carrier unavailable: " + desc)
+        T = reg.registerClouds(pair["ref"], pair["read"][shard])
+        ok = ok and (np.array_equal(u32(T), u32(T_full)) and reg.stats.iterations == it_full and
+                     np.float32(reg.getWeightedPointUsedRatio()) == np.float32(used_full) and
+                     np.array_equal(u32(reg.getOutputReading()), u32(out_full[shard])))
+        ms_sharded = reg.stats.ms_total
+        # fixed-reference mode with the sharded reading (BASELINE.json config 4 shape), twice: the second call reuses the index
+        reg.setReference(pair["ref"])
+        for _ in range(2):
+            T2 = reg.registerToReference(pair["read"][shard])
+            ok = ok and np.array_equal(u32(T2), u32(T_full))
+        # error path: ONE rank's shard holds a NaN -> every rank must come back with an error instead of waiting for ever
+        bad = pair["read"][shard].copy()
+        if rank == world - 1:
+            bad[0, 0] = np.nan
+        try:
+            reg.registerClouds(pair["ref"], bad)
+            err = "OK"
+        except capi.AicpError as e:
+            err = e.code_name
+        ok = ok and err == ("NONFINITE_INPUT" if rank == world - 1 else "COMM")
+        # ... and the communicator still works afterwards
+        T3 = reg.registerClouds(pair["ref"], pair["read"][shard])
+        ok = ok and np.array_equal(u32(T3), u32(T_full))
+        info.append("%s ms_sharded=%.3f err=%s" % (carrier, ms_sharded, err))
+        reg.commDestroy(); reg.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("NCCL_SHARDED_%s iterations=%d world=%d ms_sharded=%.3f ms_single=%.3f" %
-              ("OK" if int(flag) else "MISMATCH", it_full, world, reg.stats.ms_total, ref_reg.stats.ms_total))
-    reg.commDestroy(); reg.close(); ref_reg.close()
+        print("NCCL_SHARDED_%s iterations=%d world=%d ms_single=%.3f %s" %
+              ("OK" if int(flag) else "MISMATCH", it_full, world, ref_reg.stats.ms_total, " | ".join(info)))
+    else:
+        print("rank %d ok=%s %s" % (rank, ok, " | ".join(info)))
+    ref_reg.close()
     dist.destroy_process_group()
     if not int(flag):
         sys.exit(1)

@@ -24,10 +24,14 @@ def test_sharded_protocol_gloo_world2():
 
 
 @pytest.mark.gpu
-def test_sharded_registration_nccl_world2():
+def test_sharded_registration_all_gpus():
+    """One registration sharded over every GPU of the box (2, 4 or 8 ranks), both carriers of the exchange, against the
+    unsharded registration: bit-identical transform, iteration count, used-point ratio and output cloud."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
-    r = _torchrun(2, ["--backend", "nccl"], 29572)
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least two GPUs (run with gpurun --gpus 2)")
+    r = _torchrun(world, ["--backend", "nccl", "--points", "20000"], 29572)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "NCCL_SHARDED_OK" in r.stdout
+    assert "peer carrier unavailable" not in r.stdout, r.stdout[-2000:]
