@@ -190,7 +190,7 @@ def ptr_and_count(cloud):
     if hasattr(cloud, "data_ptr"):      # torch tensor
         if cloud.dim() != 2 or cloud.shape[1] != 4 or str(cloud.dtype) != "torch.float32" or not cloud.is_contiguous():
             raise ValueError("device clouds must be contiguous n x 4 float32 tensors")
-        if cloud.is_cuda:
+        if getattr(cloud, "is_cuda", False):          # duck-typed views of library-owned buffers carry no stream of their own
             # the library reads device inputs on its own streams (aicp_b200.h, "STREAM ORDER"): whatever torch still has in
             # flight on the current stream of the tensor's device -- the op or copy that produces it -- must finish first
             import torch

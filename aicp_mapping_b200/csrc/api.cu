@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <mutex>
@@ -116,6 +117,7 @@ int aicp_b200_create(const char* icp_yaml_path, int device, aicp_b200_handle** o
     return fail(nullptr, AICP_B200_ERR_CUDA, "cannot initialise CUDA device %d", device);
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&nh->ev[i]);
+  if (const char* e = getenv("AICP_B200_SPREAD")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nh->loop_spread = v; }
   (void)h;
   *out = reinterpret_cast<aicp_b200_handle*>(nh);
   return AICP_B200_OK;

@@ -96,6 +96,28 @@ int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count) {
   return AICP_B200_OK;
 }
 
+// Setup of a sharded registration: the reference is replicated, so its SurfaceNormal filter (the most expensive setup stage)
+// is split -- rank r computes the normals of Morton positions [r * per, (r + 1) * per) and the slices are all-gathered
+int comm_ranks(Handle* h) { return h->comm ? h->comm->n_ranks : 1; }
+
+int comm_slice(Handle* h, int n, int* q0, int* q1, int* per) {
+  Comm* c = h->comm;
+  const int p = ((n + c->n_ranks - 1) / c->n_ranks + 31) / 32 * 32;
+  *per = p;
+  *q0 = c->rank * p < n ? c->rank * p : n;
+  *q1 = (c->rank + 1) * p < n ? (c->rank + 1) * p : n;
+  return AICP_B200_OK;
+}
+
+int comm_allgather_bytes(Handle* h, void* buf, size_t bytes_per_rank) {
+  Comm* c = h->comm;
+  if (!c->AllGather) return fail(h, AICP_B200_ERR_COMM, "libnccl lacks ncclAllGather");
+  ncclResult_t r = c->AllGather(static_cast<unsigned char*>(buf) + (size_t)c->rank * bytes_per_rank, buf, bytes_per_rank, 0 /* ncclInt8 */, c->comm, h->stream);
+  if (r != ncclSuccess_) return nccl_fail(h, c, r, "AllGather");
+  h->launches += 1;
+  return AICP_B200_OK;
+}
+
 unsigned long long* comm_limbs(Handle* h) { return h->comm->limbs.p; }
 long long comm_total_reading(Handle* h) { return h->comm->n_read_total; }
 

@@ -97,6 +97,7 @@ struct Handle {
   bool batch_worker = false;     // this handle is one of the concurrent workers of aicp_b200_register_batch
   int batch_streams = 1;         // how many such workers share the GPU (the persistent loop kernel takes 1 / batch_streams of its blocks)
   int loop_schedule = 0;         // ICP loop: 0 auto, 1 three launches per iteration + host look-ahead, 2 one persistent cooperative kernel
+  int loop_spread = 0;           // experiments (AICP_B200_SPREAD): lanes per query in the search phase of the loop kernel, 0 = automatic
   int loop_occ[2] = {0, 0};      // co-resident blocks per SM of k_icp_loop<false / true>
   int n_sm = 0;
   int profiling = 0;             // 0 off, 1 CUDA events around k_match only, 2 around every stage
@@ -161,8 +162,8 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n, b
 int radix_sort_pairs(Handle* h, unsigned int* keys, unsigned int* vals, unsigned int* keys_alt, unsigned int* vals_alt, int n,
                      DevBuf<unsigned int>& scratch);
 // ---- normals.cu
-int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig);
-int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig);   // lists -> h->knn_pos (Morton positions)
+int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig, int q0 = 0, int q1 = -1);
+int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q0 = 0, int q1 = -1);   // lists -> h->knn_pos (Morton positions)
 // ---- icp.cu
 int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference, aicp_b200_stats* stats, float* out_T);
 int run_match_stage(Handle* h, const SpatialIndex& ix, const float4* qry, int64_t n_qry, int* out_idx, float* out_d2);
@@ -203,6 +204,9 @@ int comm_allreduce_u64(Handle* h, unsigned long long* buf, size_t count);
 unsigned long long* comm_limbs(Handle* h);
 long long comm_total_reading(Handle* h);
 int comm_begin_registration(Handle* h, long long n_read_local, bool want_peer);
+int comm_ranks(Handle* h);
+int comm_slice(Handle* h, int n, int* q0, int* q1, int* per);          // this rank's slice of n replicated items (multiples of 32)
+int comm_allgather_bytes(Handle* h, void* buf, size_t bytes_per_rank);   // in place: rank r's bytes_per_rank at offset r * bytes_per_rank
 bool comm_peer_view(Handle* h, PeerView* pv);      // true when the exchange runs over peer-mapped memory inside the loop kernel
 // ---- config_yaml.cpp
 int parse_icp_yaml(const char* path, aicp_b200_icp_config* cfg, std::string* err);

@@ -542,10 +542,65 @@ __device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams l
   if (!iterate) *(volatile int*)&st->done = 1;
 }
 
+// llrint(a * b * 2^30) of two floats: the product and the scaling are exact in double; below 2^51 the rounding to an
+// integer is done by ONE double addition (x + 1.5 * 2^52 lands in the binade where the spacing is 1, rounding to nearest
+// even as cvt.rni does), which replaces the slow F2I.S64.F64 of __double2ll_rn -- same bits
+__device__ __forceinline__ long long fixed_term_d(double a, double b, bool fast) {
+  const double x = (a * b) * AICP_FIXED_SCALE;
+  if (fast) return __double_as_longlong(x + 6755399441055744.0) - 0x4338000000000000ll;
+  return __double2ll_rn(x);
+}
+
+// warp sum of a 64-bit term through three 32-bit redux.sync (signed high word, two 16-bit halves of the low word); the
+// total is added to lane `slot`'s accumulator -- one register pair per lane holds the warp's 28 sums
+__device__ __forceinline__ void warp_add_term(long long term, int slot, int lane, long long& acc) {
+  const int hi = (int)(term >> 32);
+  const unsigned int lo = (unsigned int)term;
+  const int s_hi = __reduce_add_sync(0xFFFFFFFFu, hi);
+  const unsigned int s_l1 = __reduce_add_sync(0xFFFFFFFFu, lo >> 16);
+  const unsigned int s_l0 = __reduce_add_sync(0xFFFFFFFFu, lo & 0xFFFFu);
+  const long long tot = ((long long)s_hi << 32) + ((long long)s_l1 << 16) + (long long)s_l0;
+  if (lane == slot) acc += tot;
+}
+
+// Warp-wide: the 28 exact fixed-point terms of this lane's correspondence -- F F^T (21), F res (6), 1 -- with F = [p x n; n],
+// res = (p - q) . n (A.5) are summed over the warp and added to the lane-indexed accumulators (lane s holds slot s).
+// `in` false (outlier, padding): the lane contributes zeros.  Shared by k_accumulate and the persistent loop kernel.
+__device__ __forceinline__ void acc_point_terms(bool in, const float4& r, const float4& q, const float4& nr, const float* sT, int lane,
+                                                long long& acc) {
+  if (!__any_sync(0xFFFFFFFFu, in)) return;
+  double F[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  bool small = true;
+  if (in) {
+    const float3 p = xform_f(sT, r.x, r.y, r.z);
+    const float c0 = __fsub_rn(__fmul_rn(p.y, nr.z), __fmul_rn(p.z, nr.y));      // c = p x n
+    const float c1 = __fsub_rn(__fmul_rn(p.z, nr.x), __fmul_rn(p.x, nr.z));
+    const float c2 = __fsub_rn(__fmul_rn(p.x, nr.y), __fmul_rn(p.y, nr.x));
+    const float ddx = __fsub_rn(p.x, q.x), ddy = __fsub_rn(p.y, q.y), ddz = __fsub_rn(p.z, q.z);
+    float res = __fmul_rn(ddx, nr.x);
+    res = __fadd_rn(res, __fmul_rn(ddy, nr.y));
+    res = __fadd_rn(res, __fmul_rn(ddz, nr.z));
+    // every |factor| < 1448 = sqrt(2^21): all products stay below 2^51 after scaling by 2^30
+    small = fabsf(c0) < 1448.f && fabsf(c1) < 1448.f && fabsf(c2) < 1448.f && fabsf(nr.x) < 1448.f && fabsf(nr.y) < 1448.f &&
+            fabsf(nr.z) < 1448.f && fabsf(res) < 1448.f;
+    F[0] = c0; F[1] = c1; F[2] = c2; F[3] = nr.x; F[4] = nr.y; F[5] = nr.z; F[6] = res;
+  }
+  const bool fast = __all_sync(0xFFFFFFFFu, small);
+  int s = 0;
+#pragma unroll
+  for (int x = 0; x < 6; ++x)
+#pragma unroll
+    for (int y = x; y < 6; ++y) { warp_add_term(fixed_term_d(F[x], F[y], fast), s, lane, acc); ++s; }
+#pragma unroll
+  for (int x = 0; x < 6; ++x) { warp_add_term(fixed_term_d(F[x], F[6], fast), s, lane, acc); ++s; }
+  const unsigned int cnt = __popc(__ballot_sync(0xFFFFFFFFu, in));
+  if (lane == 27) acc += cnt;
+}
+
 #define ACC_SLOTS 64          // partial-sum slots: block b adds into slot b % ACC_SLOTS, the last block folds the slots
 #define ACC_PTS 2             // reading points per thread
 
-__global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
+__global__ void __launch_bounds__(256, 4) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
                                                     const float4* __restrict__ read0, const int* __restrict__ match_pos,
                                                     const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp, int tail,
                                                     volatile int* progress, unsigned long long* slots) {
@@ -555,6 +610,7 @@ __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict_
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T_iter[threadIdx.x];
   __syncthreads();
   const float limit = st->limit;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   // all independent loads first (distance, reading point, match), then the two gathers of the inliers: two memory
   // round trips per thread instead of four
   float d[ACC_PTS]; float4 r[ACC_PTS]; int pos[ACC_PTS]; bool in[ACC_PTS];
@@ -571,49 +627,15 @@ __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict_
     q[u] = nr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in[u]) { q[u] = __ldg(&refc[pos[u]]); nr[u] = __ldg(&normals[pos[u]]); }
   }
-  long long v[32];
+  // exact warp sums through redux.sync, one 64-bit accumulator per lane (lane s = slot s): 48 registers instead of the 128
+  // of the transposed-shuffle reduction over 32 accumulators per thread that this replaces
+  long long acc = 0;
 #pragma unroll
-  for (int s = 0; s < 32; ++s) v[s] = 0;
-#pragma unroll
-  for (int u = 0; u < ACC_PTS; ++u) {
-    if (in[u]) {
-      float3 p = xform_f(sT, r[u].x, r[u].y, r[u].z);
-      float F[6];
-      F[0] = __fsub_rn(__fmul_rn(p.y, nr[u].z), __fmul_rn(p.z, nr[u].y));      // c = p x n
-      F[1] = __fsub_rn(__fmul_rn(p.z, nr[u].x), __fmul_rn(p.x, nr[u].z));
-      F[2] = __fsub_rn(__fmul_rn(p.x, nr[u].y), __fmul_rn(p.y, nr[u].x));
-      F[3] = nr[u].x; F[4] = nr[u].y; F[5] = nr[u].z;
-      float ddx = __fsub_rn(p.x, q[u].x), ddy = __fsub_rn(p.y, q[u].y), ddz = __fsub_rn(p.z, q[u].z);
-      float res = __fmul_rn(ddx, nr[u].x);
-      res = __fadd_rn(res, __fmul_rn(ddy, nr[u].y));
-      res = __fadd_rn(res, __fmul_rn(ddz, nr[u].z));
-      int s = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = a; b < 6; ++b) v[s++] += fixed_term(F[a], F[b]);
-#pragma unroll
-      for (int a = 0; a < 6; ++a) v[s++] += fixed_term(F[a], res);
-      v[27] += 1;
-    }
-  }
-  // transposed warp reduction: after 5 exchange rounds lane L holds the warp total of slot L (31 shuffles, not 32*5)
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int s = 0; s < off; ++s) {
-      long long keep = upper ? v[s + off] : v[s];
-      long long send = upper ? v[s] : v[s + off];
-      long long recv = __shfl_xor_sync(0xFFFFFFFFu, send, off);
-      v[s] = keep + recv;
-    }
-  }
-  s_part[w][lane] = v[0];
+  for (int u = 0; u < ACC_PTS; ++u) acc_point_terms(in[u], r[u], q[u], nr[u], sT, lane, acc);
+  s_part[w][lane] = acc;
   __syncthreads();
   if (w == 0) {
-    // |term| < 2^52 and a block holds 512 points, so the block total fits in 64 bits; the slots are 128-bit
+    // |term| < 2^52.6 and a block holds 512 points, so the block total fits in 64 bits; the slots are 128-bit
     long long tot = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tot += s_part[k][lane];
@@ -914,27 +936,6 @@ __device__ void loop_fold_solve(DeviceState* st, unsigned long long* slots, cons
   if (threadIdx.x == 0 && !ld_int(&st->done)) solve_and_check(st, lp, n);
 }
 
-// llrint(a * b * 2^30) of two floats: the product and the scaling are exact in double; below 2^51 the rounding to an
-// integer is done by ONE double addition (x + 1.5 * 2^52 lands in the binade where the spacing is 1, rounding to nearest
-// even as cvt.rni does), which replaces the slow F2I.S64.F64 of __double2ll_rn -- same bits
-__device__ __forceinline__ long long fixed_term_d(double a, double b, bool fast) {
-  const double x = (a * b) * AICP_FIXED_SCALE;
-  if (fast) return __double_as_longlong(x + 6755399441055744.0) - 0x4338000000000000ll;
-  return __double2ll_rn(x);
-}
-
-// warp sum of a 64-bit term through three 32-bit redux.sync (signed high word, two 16-bit halves of the low word); the
-// total is added to lane `slot`'s accumulator -- one register pair per lane holds the warp's 28 sums
-__device__ __forceinline__ void warp_add_term(long long term, int slot, int lane, long long& acc) {
-  const int hi = (int)(term >> 32);
-  const unsigned int lo = (unsigned int)term;
-  const int s_hi = __reduce_add_sync(0xFFFFFFFFu, hi);
-  const unsigned int s_l1 = __reduce_add_sync(0xFFFFFFFFu, lo >> 16);
-  const unsigned int s_l0 = __reduce_add_sync(0xFFFFFFFFu, lo & 0xFFFFu);
-  const long long tot = ((long long)s_hi << 32) + ((long long)s_l1 << 16) + (long long)s_l0;
-  if (lane == slot) acc += tot;
-}
-
 struct LoopArgs {
   IndexView ix;                  // centred reference index
   const float4* normals;
@@ -949,6 +950,7 @@ struct LoopArgs {
   unsigned long long* slots;
   LoopParams lp;
   PeerView pv;
+  int spread;                    // search phase: one query per `spread` lanes (1, 2, 4, 8), see launch_loop
 };
 
 template <bool TILE>
@@ -962,7 +964,12 @@ __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ Loo
   DeviceState* st = a.st;
   const PeerView& pv = a.pv;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int n = a.n, n_tiles = (n + 255) / 256;
+  // a tile = the Q reading points one block handles at a time.  The search is bound by the latency of its slowest warp, and
+  // that latency by how many divergent tree walks a warp serialises -- not by throughput (65 536 queries take as long as
+  // 131 072).  When the reading is small enough to leave resident warps idle anyway, the queries are spread over more
+  // warps: one query per S lanes (S <= 8), so a warp serialises 32 / S walks.  The dense phases use the first Q threads.
+  const int S = TILE ? 1 : a.spread, Q = 256 / S;
+  const int n = a.n, n_tiles = (n + Q - 1) / Q;
   const bool sharded = pv.n_ranks > 1;
   // a rank whose setup raised a status still joins the first exchange, so that every rank ends the loop together
   const bool dead = ld_int(&st->done) != 0;
@@ -976,9 +983,8 @@ __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ Loo
     __syncthreads();
     if (!dead) {
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int i = t * 256 + tid;
-        if (TILE && it > 0) match_tile(a.ix, sT, a.read0, n, i, it, a.match_pos, a.d2, a.trace_idx, sh, s_stage[TILE ? w : 0], s_stack[TILE ? w : 0]);
-        else match_thread(a.ix, sT, a.read0, n, i, it, a.match_pos, a.d2, a.trace_idx, sh);
+        if (TILE && it > 0) match_tile(a.ix, sT, a.read0, n, t * 256 + tid, it, a.match_pos, a.d2, a.trace_idx, sh, s_stage[TILE ? w : 0], s_stack[TILE ? w : 0]);
+        else if ((tid & (S - 1)) == 0) match_thread(a.ix, sT, a.read0, n, t * Q + tid / S, it, a.match_pos, a.d2, a.trace_idx, sh);
       }
     }
     __syncthreads();
@@ -993,7 +999,7 @@ __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ Loo
     {
       const unsigned int prefix = __ldcg(&st->prefix);
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int i = t * 256 + tid;
+        const int i = tid < Q ? t * Q + tid : n;
         unsigned int key = 0;
         bool hit = false;
         if (i < n) {
@@ -1037,39 +1043,13 @@ __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ Loo
         acc = 0; held = 0;
       };
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int i = t * 256 + tid;
+        const int i = tid < Q ? t * Q + tid : n;
         bool in = false;
         int pos = 0;
         if (i < n) { in = __ldcg(&a.d2[i]) <= limit; pos = __ldcg(&a.match_pos[i]); }      // TrimmedDist weight (A.4); false for NaN
-        if (__any_sync(0xFFFFFFFFu, in)) {
-          double F[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-          bool small = true;
-          if (in) {
-            const float4 r = __ldg(&a.read0[i]), q = __ldg(&a.ix.pts[pos]), nr = __ldg(&a.normals[pos]);
-            const float3 p = xform_f(sT, r.x, r.y, r.z);
-            const float c0 = __fsub_rn(__fmul_rn(p.y, nr.z), __fmul_rn(p.z, nr.y));      // c = p x n
-            const float c1 = __fsub_rn(__fmul_rn(p.z, nr.x), __fmul_rn(p.x, nr.z));
-            const float c2 = __fsub_rn(__fmul_rn(p.x, nr.y), __fmul_rn(p.y, nr.x));
-            const float ddx = __fsub_rn(p.x, q.x), ddy = __fsub_rn(p.y, q.y), ddz = __fsub_rn(p.z, q.z);
-            float res = __fmul_rn(ddx, nr.x);
-            res = __fadd_rn(res, __fmul_rn(ddy, nr.y));
-            res = __fadd_rn(res, __fmul_rn(ddz, nr.z));
-            // every |factor| < 1448 = sqrt(2^21): all products stay below 2^51 after scaling by 2^30
-            small = fabsf(c0) < 1448.f && fabsf(c1) < 1448.f && fabsf(c2) < 1448.f && fabsf(nr.x) < 1448.f && fabsf(nr.y) < 1448.f &&
-                    fabsf(nr.z) < 1448.f && fabsf(res) < 1448.f;
-            F[0] = c0; F[1] = c1; F[2] = c2; F[3] = nr.x; F[4] = nr.y; F[5] = nr.z; F[6] = res;
-          }
-          const bool fast = __all_sync(0xFFFFFFFFu, small);
-          int s = 0;
-#pragma unroll
-          for (int x = 0; x < 6; ++x)
-#pragma unroll
-            for (int y = x; y < 6; ++y) { warp_add_term(fixed_term_d(F[x], F[y], fast), s, lane, acc); ++s; }
-#pragma unroll
-          for (int x = 0; x < 6; ++x) { warp_add_term(fixed_term_d(F[x], F[6], fast), s, lane, acc); ++s; }
-          const unsigned int cnt = __popc(__ballot_sync(0xFFFFFFFFu, in));
-          if (lane == 27) acc += cnt;
-        }
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f), q = r, nr = r;
+        if (in) { r = __ldg(&a.read0[i]); q = __ldg(&a.ix.pts[pos]); nr = __ldg(&a.normals[pos]); }
+        acc_point_terms(in, r, q, nr, sT, lane, acc);
         if (++held == 4) flush();
       }
       if (held) flush();
@@ -1224,7 +1204,12 @@ static int launch_loop(Handle* h, LoopArgs& la, bool tile) {
   int cap = h->loop_occ[tile ? 1 : 0] * h->n_sm;
   if (h->batch_worker && h->batch_streams > 1) cap /= h->batch_streams;
   if (cap < 1) cap = 1;
-  int grid = (la.n + 255) / 256;
+  int spread = 1;                                           // widest spread whose tiles are still all resident at once
+  while (!tile && spread < 8 && (la.n + 256 / (2 * spread) - 1) / (256 / (2 * spread)) <= cap) spread *= 2;
+  if (h->loop_spread > 0) spread = tile ? 1 : h->loop_spread;
+  la.spread = spread;
+  const int q = 256 / spread;
+  int grid = (la.n + q - 1) / q;
   if (grid > cap) grid = cap;
   void* params[] = {&la};
   CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), params, 0, h->stream));
@@ -1257,11 +1242,21 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     rc = build_index(h, h->ref_ix, h->ref_in.p, n_ref);
     if (rc) return rc;
     mark(1);
-    CUDA_TRY(h->normals.reserve((size_t)h->ref_ix.n));
     CUDA_TRY(h->refc_pts.reserve((size_t)h->ref_ix.n));
     CUDA_TRY(h->refc_rec.reserve((size_t)4 * h->ref_ix.n));
     CUDA_TRY(h->refc_cell.reserve((size_t)2 * h->ref_ix.n));
-    rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr);
+    if (h->comm && h->ref_ix.n >= 4096) {
+      // sharded registration: every rank holds the same reference (hence the same Morton order), computes the normals of
+      // its slice and the slices are all-gathered -- same bits as computing them all, 1 / n_ranks of the k-NN work
+      int q0, q1, per;
+      comm_slice(h, h->ref_ix.n, &q0, &q1, &per);
+      CUDA_TRY(h->normals.reserve((size_t)per * comm_ranks(h)));
+      rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr, q0, q1);
+      if (!rc) rc = comm_allgather_bytes(h, h->normals.p, (size_t)per * sizeof(float4));
+    } else {
+      CUDA_TRY(h->normals.reserve((size_t)h->ref_ix.n));
+      rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr);
+    }
     if (rc) return rc;
     h->ref_knn = cfg.knn_normals;
     mark(2);
@@ -1337,7 +1332,7 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   // loses the block scheduler's dynamic load balance (measured: 1905 vs 2340 registrations/s).
   const bool persistent = want_persistent && (!h->comm || peer_exchange);
   if (persistent) {
-    LoopArgs la{cix, h->normals.p, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, h->cand.p, trace_idx, h->acc_slots.p, lp, pv};
+    LoopArgs la{cix, h->normals.p, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, h->cand.p, trace_idx, h->acc_slots.p, lp, pv, 1};
     if ((rc = launch_loop(h, la, tile_match))) return rc;
     h->launches += 1;
   }

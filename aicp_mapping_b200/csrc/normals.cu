@@ -140,15 +140,15 @@ __device__ __forceinline__ void knn_descend(const IndexView& ix, WarpKnn& w, int
 #define KNN_RUN 16        // consecutive Morton-ordered queries handled by one warp
 
 __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k, int* __restrict__ knn_pos,
-                                                             int* __restrict__ knn_out_orig) {
+                                                             int* __restrict__ knn_out_orig, int q0, int q1) {
   __shared__ int s_a[KNN_WARPS][AICP_STACK];
   __shared__ int s_b[KNN_WARPS][AICP_STACK];
   __shared__ float s_d[KNN_WARPS][AICP_STACK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int run = blockIdx.x * KNN_WARPS + wid;
-  const int i0 = run * KNN_RUN;
-  if (i0 >= ix.n) return;
-  const int i1 = i0 + KNN_RUN < ix.n ? i0 + KNN_RUN : ix.n;
+  const int i0 = q0 + run * KNN_RUN;          // queries [q0, q1): the whole cloud, or this rank's slice of a replicated reference
+  if (i0 >= q1) return;
+  const int i1 = i0 + KNN_RUN < q1 ? i0 + KNN_RUN : q1;
   int* st_a = s_a[wid]; int* st_b = s_b[wid]; float* st_d = s_d[wid];
   WarpKnn w;
   w.k = k; w.lane = lane;
@@ -310,12 +310,12 @@ __device__ __forceinline__ void tile_scan(const IndexView& ix, float4* s_pts, in
 }
 
 __global__ void __launch_bounds__(32 * TILE_WARPS) k_knn_tile(IndexView ix, int k, int* __restrict__ knn_pos,
-                                                              int* __restrict__ knn_out_orig) {
+                                                              int* __restrict__ knn_out_orig, int q0, int q1) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tile = blockIdx.x * TILE_WARPS + wid;
-  const int i0 = tile * 32;
-  if (i0 >= ix.n) return;                                               // whole warp; no block-level barrier below
+  const int i0 = q0 + tile * 32;                                        // q0 is a multiple of 32, q1 a multiple of 32 or ix.n
+  if (i0 >= q1) return;                                                 // whole warp; no block-level barrier below
   const size_t per_warp = (size_t)k * 32 * 12 + 512 + AICP_STACK * 4;
   unsigned char* base = smem + per_warp * wid;
   unsigned long long* K = reinterpret_cast<unsigned long long*>(base) + lane;
@@ -410,9 +410,9 @@ __global__ void __launch_bounds__(32 * TILE_WARPS) k_knn_tile(IndexView ix, int 
 }
 
 __global__ void __launch_bounds__(128) k_normals_from_knn(IndexView ix, int k, const int* __restrict__ knn_pos,
-                                                          float4* __restrict__ normals_morton) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ix.n) return;
+                                                          float4* __restrict__ normals_morton, int q0, int q1) {
+  int i = q0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q1) return;
   const int* nb = knn_pos + (size_t)i * k;
   // mean and covariance in list order, float64
   double mx = 0, my = 0, mz = 0;
@@ -467,31 +467,38 @@ __global__ void __launch_bounds__(128) k_normals_from_knn(IndexView ix, int k, c
 
 // exact k-NN lists (positions in Morton order, ascending (d2, original index)) into h->knn_pos; shared by the SurfaceNormal
 // filter of the ICP chain and by the pre-filter (prefilter.cu: pcl::NormalEstimation + pcl::RegionGrowing neighbourhoods)
-int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig) {
+int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q0, int q1) {
   if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "k-NN search: knn %d outside [1,32]", knn);
   if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "k-NN search: knn %d >= %d points", knn, ix.n);
+  if (q1 < 0) q1 = ix.n;
   CUDA_TRY(h->knn_pos.reserve((size_t)ix.n * knn));
+  if (q0 >= q1) return AICP_B200_OK;
+  const int nq = q1 - q0;
   // Two schedules of the same exact search (identical output): the tile kernel executes ~45 % fewer instructions and wins
   // whenever the GPU is full (batched registrations, large clouds); the warp-per-query kernel has twice as many, shorter
   // warps and wins the latency of ONE lidar-sized cloud on an otherwise idle GPU.
-  const bool tile = h->knn_schedule == 2 || (h->knn_schedule == 0 && (h->batch_worker || ix.n >= (1 << 20)));
+  const bool tile = h->knn_schedule == 2 || (h->knn_schedule == 0 && (h->batch_worker || nq >= (1 << 20)));
   if (!tile) {
-    k_knn_warp<<<(unsigned)((ix.n + KNN_WARPS * KNN_RUN - 1) / (KNN_WARPS * KNN_RUN)), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
+    k_knn_warp<<<(unsigned)((nq + KNN_WARPS * KNN_RUN - 1) / (KNN_WARPS * KNN_RUN)), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig, q0, q1);
   } else {
     const size_t smem = ((size_t)knn * 32 * 12 + 512 + AICP_STACK * 4) * TILE_WARPS;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = (ix.n + 31) / 32;
-    k_knn_tile<<<(unsigned)((tiles + TILE_WARPS - 1) / TILE_WARPS), 32 * TILE_WARPS, smem, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig);
+    const int tiles = (nq + 31) / 32;
+    k_knn_tile<<<(unsigned)((tiles + TILE_WARPS - 1) / TILE_WARPS), 32 * TILE_WARPS, smem, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig, q0, q1);
   }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return AICP_B200_OK;
 }
 
-int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig) {
-  int rc = run_knn(h, ix, knn, knn_out_orig);
+// [q0, q1): the Morton positions whose normals are computed (q1 < 0: all) -- a sharded registration gives every rank one
+// slice of the replicated reference and all-gathers the results (icp.cu); q0 must be a multiple of 32
+int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig, int q0, int q1) {
+  if (q1 < 0) q1 = ix.n;
+  int rc = run_knn(h, ix, knn, knn_out_orig, q0, q1);
   if (rc) return rc;
-  k_normals_from_knn<<<(ix.n + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton);
+  if (q0 >= q1) return AICP_B200_OK;
+  k_normals_from_knn<<<(q1 - q0 + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton, q0, q1);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return AICP_B200_OK;

@@ -96,12 +96,25 @@ struct NnBest {
   int pos;
 };
 
+// Leaf scan.  The loads are issued AICP_SCAN_BATCH at a time before the first distance is needed: the search is bound by
+// the latency of its slowest warp (ncu: 26 of 39 stall cycles per issue are barrier waits for it, issue slots 18 % busy), and
+// a scan that waits for every point in turn is a chain of up to 16 L1/L2 round trips.  Points past the end of the range are
+// replaced by the last one (re-evaluating a point cannot change the result).
+#ifndef AICP_SCAN_BATCH
+#define AICP_SCAN_BATCH 4
+#endif
 __device__ __forceinline__ void nn_scan(const IndexView& ix, float qx, float qy, float qz, int first, int cnt, NnBest& b) {
-  for (int j = 0; j < cnt; ++j) {
-    float4 p = __ldg(&ix.pts[first + j]);
-    float d = d2_f(qx, qy, qz, p.x, p.y, p.z);
-    int id = __float_as_int(p.w);
-    if (d < b.d || (d == b.d && id < b.id)) { b.d = d; b.id = id; b.pos = first + j; }
+  const int last = first + cnt - 1;
+  for (int j = first; j <= last; j += AICP_SCAN_BATCH) {
+    float4 p[AICP_SCAN_BATCH];
+#pragma unroll
+    for (int u = 0; u < AICP_SCAN_BATCH; ++u) p[u] = __ldg(&ix.pts[min(j + u, last)]);
+#pragma unroll
+    for (int u = 0; u < AICP_SCAN_BATCH; ++u) {
+      const float d = d2_f(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+      const int id = __float_as_int(p[u].w);
+      if (d < b.d || (d == b.d && id < b.id)) { b.d = d; b.id = id; b.pos = min(j + u, last); }
+    }
   }
 }
 
