@@ -148,7 +148,7 @@ static int peer_setup(Handle* h, Comm* c, unsigned int cand_cap) {
   if (G > AICP_MAX_RANKS || !c->AllGather) return AICP_B200_OK;
   cudaStream_t s = h->stream;
   c->cand_cap = cand_cap;
-  c->cand_stride = (16 + (size_t)cand_cap * 4 + 255) / 256 * 256;
+  c->cand_stride = (8 + (size_t)cand_cap * 8 + 255) / 256 * 256;
   const size_t bytes = AICP_INBOX_CAND_OFF + (size_t)G * c->cand_stride;
   int ok = 1;
   InboxCard mine;
@@ -202,7 +202,20 @@ int comm_begin_registration(Handle* h, long long n_read_local, bool want_peer) {
   Comm* c = h->comm;
   // peer carrier: nothing to exchange up front -- the reading size travels with the sums inside the loop kernel
   c->peer_now = c->peer && want_peer;
-  if (c->peer_now) { ++c->epoch; c->n_read_total = 0; return AICP_B200_OK; }
+  if (c->peer_now) {
+    ++c->epoch; c->n_read_total = 0;
+    if ((c->epoch & 0xFFFFFull) == 0) {
+      // the 32-bit stamps (2048 per registration) come round after 2^21 registrations: long before that every rank clears
+      // its inbox, and nobody proceeds until all have (the all-reduce is the barrier) -- no stale word can ever match
+      const size_t bytes = AICP_INBOX_CAND_OFF + (size_t)c->n_ranks * c->cand_stride;
+      CUDA_TRY(cudaMemsetAsync(c->inbox, 0, bytes, h->stream));
+      unsigned int* w = reinterpret_cast<unsigned int*>(c->limbs.p);
+      ncclResult_t r = c->AllReduce(w, w, 1, ncclUint32_, ncclSum_, c->comm, h->stream);
+      if (r != ncclSuccess_) return nccl_fail(h, c, r, "AllReduce(inbox reset)");
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return AICP_B200_OK;
+  }
   unsigned long long* slot = c->limbs.p + 4 * AICP_NSUM + 1;
   unsigned long long v = (unsigned long long)n_read_local;
   CUDA_TRY(cudaMemcpyAsync(slot, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
@@ -271,9 +284,9 @@ int aicp_b200_comm_info(aicp_b200_handle* hh, char* buf, int len) {
   if (!h || !buf || len < 1) return AICP_B200_ERR_BAD_ARG;
   if (!h->comm) { snprintf(buf, (size_t)len, "no communicator"); return AICP_B200_OK; }
   if (h->comm->peer) {
-    snprintf(buf, (size_t)len, "%d ranks; peer-mapped inboxes over NVLink (CUDA IPC): per iteration 3 flag-synchronised exchanges inside the "
-             "persistent loop kernel (digit-1 histogram 8 KiB, candidate keys of the picked bin, 28 x 128-bit sums), 0 NCCL calls, 1 launch for "
-             "the whole loop", h->comm->n_ranks);
+    snprintf(buf, (size_t)len, "%d ranks; peer-mapped inboxes over NVLink (CUDA IPC): per iteration 3 exchanges inside the "
+             "persistent loop kernel, flag-in-data stores (digit-1 histogram, candidate keys of the picked bin, 28 x 128-bit sums), 0 NCCL "
+             "calls, 1 launch for the whole loop", h->comm->n_ranks);
     return AICP_B200_OK;
   }
   snprintf(buf, (size_t)len, "%d ranks; per iteration 3 x ncclAllReduce(uint32[2048]) for the trimmed quantile + 1 x ncclAllReduce(uint64[113]) "

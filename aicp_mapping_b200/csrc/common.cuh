@@ -73,16 +73,21 @@ struct DeviceState {
 
 // ---- sharded registration over peer-mapped memory (comm.cu, icp.cu) ---------------------------------------------------
 // Every rank owns one INBOX in its own HBM; every peer maps it (CUDA IPC between processes, peer access inside one) and
-// stores its contribution for this rank there, then raises a sequence-stamped flag.  Layout of an inbox, per SOURCE rank s:
-//   flags  @ FLAGS_OFF + 64 s      three 64-bit stamps (round 0 histogram, 1 candidates, 2 sums): epoch << 24 | (4 iter + round + 1) << 1 | status
-//   sums   @ SUMS_OFF  + 512 s     28 x (lo, hi) 128-bit partial sums
-//   hist   @ HIST_OFF  + 8192 s    2048 x uint32 digit-1 histogram of the source's shard
-//   cand   @ CAND_OFF  + stride s  uint32 count, 12 bytes padding, then the source's candidate keys (capacity: its shard size)
+// stores its contribution for this rank there.  The protocol is "flag in data" (what NCCL calls LL): every 64-bit word a
+// peer writes carries 32 bits of payload and, in its upper half, the 32-bit sequence stamp of the exchange
+// (2048 * epoch + 4 * iteration + round + 1); a 64-bit store is single-copy atomic, so a reader that sees the stamp sees
+// the payload -- no fence on the sending side, no separate flag, one NVLink write latency per exchange (the first version
+// used plain stores + __threadfence_system + a flag + a fence after the flag: 16 us per exchange at 8 ranks).
+// Layout of an inbox, per SOURCE rank s (all 64-bit words):
+//   sums   @ SUMS_OFF + 1024 s         28 x 4 limbs of 32 bits, 2 words n_reading, word 127 = status of the source
+//   hist   @ HIST_OFF + (2048 + 8) 8 s 2048 digit-1 bins, then one status word
+//   cand   @ CAND_OFF + stride s       header (count | status << 31), then the source's candidate keys (capacity cand_cap)
 #define AICP_MAX_RANKS 16
-#define AICP_INBOX_FLAGS_OFF 0
-#define AICP_INBOX_SUMS_OFF 1024
-#define AICP_INBOX_HIST_OFF (AICP_INBOX_SUMS_OFF + 512 * AICP_MAX_RANKS)
-#define AICP_INBOX_CAND_OFF (AICP_INBOX_HIST_OFF + AICP_HIST_BINS * 4 * AICP_MAX_RANKS)
+#define AICP_INBOX_SUMS_OFF 0
+#define AICP_INBOX_SUMS_STRIDE 1024
+#define AICP_INBOX_HIST_OFF (AICP_INBOX_SUMS_OFF + AICP_INBOX_SUMS_STRIDE * AICP_MAX_RANKS)
+#define AICP_INBOX_HIST_STRIDE ((AICP_HIST_BINS + 8) * 8)
+#define AICP_INBOX_CAND_OFF (AICP_INBOX_HIST_OFF + AICP_INBOX_HIST_STRIDE * AICP_MAX_RANKS)
 #define AICP_PEER_TIMEOUT_NS 10000000000ull      // a peer that does not show up within 10 s ends the loop with AICP_B200_ERR_COMM
 
 struct PeerView {

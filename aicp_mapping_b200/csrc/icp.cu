@@ -747,68 +747,74 @@ __device__ __forceinline__ void grid_serial(DeviceState* st, unsigned int& epoch
   __syncthreads();
 }
 
-// ---- peer exchange (sharded registration)
-__device__ __forceinline__ unsigned long long peer_stamp(const PeerView& pv, int iter, int round) {
-  return (pv.epoch << 24) | ((unsigned long long)(iter * 4 + round + 1) << 1);
+// ---- peer exchange (sharded registration): flag-in-data words, see common.cuh
+__device__ __forceinline__ unsigned int peer_stamp(const PeerView& pv, int iter, int round) {
+  return (unsigned int)(pv.epoch * 2048ull) + (unsigned int)(iter * 4 + round + 1);
 }
-__device__ __forceinline__ unsigned long long* peer_flag(unsigned char* inbox, int source, int round) {
-  return reinterpret_cast<unsigned long long*>(inbox + AICP_INBOX_FLAGS_OFF + (size_t)source * 64 + (size_t)round * 8);
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned int payload, unsigned int stamp) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)stamp << 32) | payload) : "memory");
 }
-// after the block's stores into the peers' inboxes: make them visible system-wide, then raise this rank's flag in every inbox
-__device__ __forceinline__ void peer_signal(const PeerView& pv, int iter, int round, int status) {
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < pv.n_ranks && (int)threadIdx.x != pv.rank)
-    st_release_sys_u64(peer_flag(pv.inbox[threadIdx.x], pv.rank, round), peer_stamp(pv, iter, round) | (status ? 1ull : 0ull));
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
-// wait for every peer's flag of (iter, round); returns non-zero (block-uniform) when a peer reported a status or none arrived
-// within the time limit -- the caller ends the loop with AICP_B200_ERR_COMM, identically on every rank
-__device__ __forceinline__ int peer_wait(const PeerView& pv, DeviceState* st, int iter, int round) {
-  int bad = 0;
-  const unsigned long long t0 = global_ns();
-  if ((int)threadIdx.x < pv.n_ranks && (int)threadIdx.x != pv.rank) {
-    const unsigned long long* f = peer_flag(pv.inbox[pv.rank], threadIdx.x, round);
-    const unsigned long long want = peer_stamp(pv, iter, round);
-    unsigned long long v;
+// spin until word *p carries `stamp`; false when the time limit passes first
+__device__ __forceinline__ bool ll_wait(const unsigned long long* p, unsigned int stamp, unsigned int* payload) {
+  unsigned long long v = ll_load(p);
+  if ((unsigned int)(v >> 32) != stamp) {
+    const unsigned long long t0 = global_ns();
     unsigned int spins = 0;
-    while (((v = ld_relaxed_sys_u64(f)) & ~1ull) != want) {
-      if ((++spins & 1023u) == 0 && global_ns() - t0 > AICP_PEER_TIMEOUT_NS) { bad = 2; break; }
-    }
-    if (!bad) bad = (int)(v & 1ull);
-    __threadfence_system();                          // acquire: the peer's data stores precede its flag
+    while ((unsigned int)((v = ll_load(p)) >> 32) != stamp)
+      if ((++spins & 1023u) == 0 && global_ns() - t0 > AICP_PEER_TIMEOUT_NS) return false;
   }
+  *payload = (unsigned int)v;
+  return true;
+}
+// block-wide verdict of an exchange: a peer reported a status, or some word never arrived -> every rank ends the loop
+// (AICP_B200_ERR_COMM; the rank that raised the original status keeps its own code)
+__device__ __forceinline__ void peer_verdict(DeviceState* st, int bad, unsigned long long t0) {
   bad = __syncthreads_or(bad);
-  if (threadIdx.x == 0) st->phase_ns[3] += global_ns() - t0;
-  return bad;
+  if (threadIdx.x == 0) {
+    st->phase_ns[3] += global_ns() - t0;
+    if (bad) raise_status(st, AICP_B200_ERR_COMM);
+  }
 }
 
 // serial section 1: the digit-1 histogram is complete in `hist` (and, sharded, is summed over the ranks) -> pick the digit
 __device__ void loop_pick(DeviceState* st, unsigned int* hist, float ratio, const PeerView& pv, int iter) {
   const int t = threadIdx.x;
   unsigned int h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { h[j] = __ldcg(&hist[t * 8 + j]); hist[t * 8 + j] = 0; }
   if (pv.n_ranks > 1) {
-    const uint4* src = reinterpret_cast<const uint4*>(hist);
-    const uint4 a = __ldcg(src + 2 * t), b = __ldcg(src + 2 * t + 1);
+    const unsigned int stamp = peer_stamp(pv, iter, 0);
+    const unsigned int my_status = *(volatile int*)&st->status != 0 ? 1u : 0u;
     for (int r = 0; r < pv.n_ranks; ++r) {
       if (r == pv.rank) continue;
-      uint4* dst = reinterpret_cast<uint4*>(pv.inbox[r] + AICP_INBOX_HIST_OFF + (size_t)pv.rank * (AICP_HIST_BINS * 4));
-      dst[2 * t] = a; dst[2 * t + 1] = b;
-    }
-    peer_signal(pv, iter, 0, *(volatile int*)&st->status != 0);
-    if (peer_wait(pv, st, iter, 0)) { if (t == 0) raise_status(st, AICP_B200_ERR_COMM); }
-    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
-    for (int r = 0; r < pv.n_ranks; ++r) {
-      if (r == pv.rank) continue;
-      const uint4* in = reinterpret_cast<const uint4*>(pv.inbox[pv.rank] + AICP_INBOX_HIST_OFF + (size_t)r * (AICP_HIST_BINS * 4));
-      const uint4 c = __ldcg(in + 2 * t), d = __ldcg(in + 2 * t + 1);
-      h[0] += c.x; h[1] += c.y; h[2] += c.z; h[3] += c.w; h[4] += d.x; h[5] += d.y; h[6] += d.z; h[7] += d.w;
-    }
-  } else {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(pv.inbox[r] + AICP_INBOX_HIST_OFF + (size_t)pv.rank * AICP_INBOX_HIST_STRIDE);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = __ldcg(&hist[t * 8 + j]);
+      for (int j = 0; j < 8; ++j) ll_store(dst + t * 8 + j, h[j], stamp);
+      if (t == 0) ll_store(dst + AICP_HIST_BINS, my_status, stamp);
+    }
+    const unsigned long long t0 = global_ns();
+    int bad = 0;
+    for (int r = 0; r < pv.n_ranks; ++r) {
+      if (r == pv.rank) continue;
+      const unsigned long long* in = reinterpret_cast<const unsigned long long*>(pv.inbox[pv.rank] + AICP_INBOX_HIST_OFF + (size_t)r * AICP_INBOX_HIST_STRIDE);
+      unsigned long long v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ll_load(in + t * 8 + j);              // all eight in flight; late words are re-polled below
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        unsigned int x = (unsigned int)v[j];
+        if ((unsigned int)(v[j] >> 32) != stamp && !ll_wait(in + t * 8 + j, stamp, &x)) bad = 1;
+        h[j] += x;
+      }
+      if (t == 0) { unsigned int x = 0; if (!ll_wait(in + AICP_HIST_BINS, stamp, &x) || x) bad = 1; }
+    }
+    peer_verdict(st, bad, t0);
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) hist[t * 8 + j] = 0;
   unsigned int bin; unsigned long long rem, total;
   block_pick(h, 1, ratio, 0, &bin, &rem, &total);
   if (t == 0) {
@@ -824,29 +830,50 @@ __device__ void loop_select23(DeviceState* st, unsigned int* cand, unsigned int*
   const int t = threadIdx.x;
   const unsigned int c_local = *(volatile unsigned int*)&st->cand_n;
   const unsigned int prefix = *(volatile unsigned int*)&st->prefix;
+  const unsigned int stamp = peer_stamp(pv, iter, 1);
+  __shared__ unsigned int s_cnt[AICP_MAX_RANKS];
   if (pv.n_ranks > 1) {
     // more candidates than a peer's inbox holds (a shard of over cand_cap points whose distances share one 11-bit digit):
-    // raised as a status, which the flag carries to every rank, so all of them end the loop together
+    // raised as a status, which the header carries to every rank, so all of them end the loop together
     const bool fits = c_local <= pv.cand_cap;
     if (!fits && t == 0) raise_status(st, AICP_B200_ERR_COMM);
+    const unsigned int my_status = (!fits || *(volatile int*)&st->status != 0) ? 1u : 0u;
     for (int r = 0; r < pv.n_ranks; ++r) {
       if (r == pv.rank) continue;
-      unsigned int* dst = reinterpret_cast<unsigned int*>(pv.inbox[r] + AICP_INBOX_CAND_OFF + (size_t)pv.rank * pv.cand_stride);
-      if (t == 0) dst[0] = fits ? c_local : 0u;
-      for (unsigned int j = t; j < c_local && fits; j += 256) dst[4 + j] = __ldcg(&cand[j]);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(pv.inbox[r] + AICP_INBOX_CAND_OFF + (size_t)pv.rank * pv.cand_stride);
+      if (t == 0) ll_store(dst, (fits ? c_local : 0u) | (my_status << 31), stamp);
+      for (unsigned int j = t; j < c_local && fits; j += 256) ll_store(dst + 1 + j, __ldcg(&cand[j]), stamp);
     }
-    __syncthreads();
-    peer_signal(pv, iter, 1, *(volatile int*)&st->status != 0);
-    if (peer_wait(pv, st, iter, 1)) { if (t == 0) raise_status(st, AICP_B200_ERR_COMM); }
+    const unsigned long long t0 = global_ns();
+    int bad = 0;
+    if (t < pv.n_ranks && t != pv.rank) {
+      unsigned int hdr = 0;
+      if (!ll_wait(reinterpret_cast<const unsigned long long*>(pv.inbox[pv.rank] + AICP_INBOX_CAND_OFF + (size_t)t * pv.cand_stride), stamp, &hdr) ||
+          (hdr >> 31)) bad = 1;
+      s_cnt[t] = bad ? 0u : (hdr & 0x7FFFFFFFu);
+    }
+    peer_verdict(st, bad, t0);
   }
-  // visit every key of every list: the local one, then each peer's copy in this rank's inbox
+  // visit every key of every list: the local one, then each peer's copy in this rank's inbox (words polled until stamped)
   auto for_each_key = [&](auto&& fn) {
     for (unsigned int j = t; j < c_local; j += 256) fn(__ldcg(&cand[j]));
     for (int r = 0; r < pv.n_ranks; ++r) {
       if (r == pv.rank || pv.n_ranks == 1) continue;
-      const unsigned int* in = reinterpret_cast<const unsigned int*>(pv.inbox[pv.rank] + AICP_INBOX_CAND_OFF + (size_t)r * pv.cand_stride);
-      const unsigned int c = __ldcg(in);
-      for (unsigned int j = t; j < c; j += 256) fn(__ldcg(in + 4 + j));
+      const unsigned long long* in = reinterpret_cast<const unsigned long long*>(pv.inbox[pv.rank] + AICP_INBOX_CAND_OFF + (size_t)r * pv.cand_stride) + 1;
+      const unsigned int c = s_cnt[r];
+      // four words per thread in flight (a polled word is an uncached L2 round trip: one at a time costs 0.7 us each)
+      for (unsigned int j = t; j < c; j += 1024) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = j + 256 * u < c ? ll_load(in + j + 256 * u) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j + 256 * u >= c) continue;
+          unsigned int key = (unsigned int)v[u];
+          if ((unsigned int)(v[u] >> 32) != stamp && !ll_wait(in + j + 256 * u, stamp, &key)) { raise_status(st, AICP_B200_ERR_COMM); continue; }
+          fn(key);
+        }
+      }
     }
   };
   unsigned int h[8], bin; unsigned long long rem, total;
@@ -903,32 +930,43 @@ __device__ void loop_fold_solve(DeviceState* st, unsigned long long* slots, cons
     }
   }
   if (pv.n_ranks > 1) {
-    if (w == 0 && lane < AICP_NSUM) {
-      for (int r = 0; r < pv.n_ranks; ++r) {
-        if (r == pv.rank) continue;
-        ulonglong2* dst = reinterpret_cast<ulonglong2*>(pv.inbox[r] + AICP_INBOX_SUMS_OFF + (size_t)pv.rank * 512);
-        dst[lane] = make_ulonglong2(lo, (unsigned long long)hi);
-        if (lane == 0) dst[AICP_NSUM] = make_ulonglong2((unsigned long long)n, 0ull);      // this rank's share of the reading
+    const unsigned int stamp = peer_stamp(pv, iter, 2);
+    if (w == 0) {
+      // this rank's 28 sums as four 32-bit limbs each, its share of the reading (lane 28) and its status (lane 31)
+      unsigned int limb[4] = {(unsigned int)lo, (unsigned int)(lo >> 32), (unsigned int)hi, (unsigned int)((unsigned long long)hi >> 32)};
+      if (lane == AICP_NSUM) { limb[0] = (unsigned int)n; limb[1] = 0; limb[2] = 0; limb[3] = 0; }
+      if (lane == 31) { limb[0] = 0; limb[1] = 0; limb[2] = 0; limb[3] = *(volatile int*)&st->status != 0 ? 1u : 0u; }
+      if (lane <= AICP_NSUM || lane == 31) {
+        for (int r = 0; r < pv.n_ranks; ++r) {
+          if (r == pv.rank) continue;
+          unsigned long long* dst = reinterpret_cast<unsigned long long*>(pv.inbox[r] + AICP_INBOX_SUMS_OFF + (size_t)pv.rank * AICP_INBOX_SUMS_STRIDE) + 4 * lane;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ll_store(dst + k, limb[k], stamp);
+        }
       }
     }
-    peer_signal(pv, iter, 2, *(volatile int*)&st->status != 0);
-    if (peer_wait(pv, st, iter, 2)) { if (threadIdx.x == 0) raise_status(st, AICP_B200_ERR_COMM); }
-    if (w == 0 && lane < AICP_NSUM) {
+    const unsigned long long t0 = global_ns();
+    int bad = 0;
+    unsigned long long n_all = (unsigned long long)n;
+    if (w == 0 && (lane <= AICP_NSUM || lane == 31)) {
       for (int r = 0; r < pv.n_ranks; ++r) {
         if (r == pv.rank) continue;
-        const ulonglong2* in = reinterpret_cast<const ulonglong2*>(pv.inbox[pv.rank] + AICP_INBOX_SUMS_OFF + (size_t)r * 512);
-        const ulonglong2 v = __ldcg(in + lane);
-        unsigned long long nl = lo + v.x;
-        hi = hi + (long long)v.y + (nl < lo ? 1 : 0);
-        lo = nl;
+        const unsigned long long* in = reinterpret_cast<const unsigned long long*>(pv.inbox[pv.rank] + AICP_INBOX_SUMS_OFF + (size_t)r * AICP_INBOX_SUMS_STRIDE) + 4 * lane;
+        unsigned int x[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (!ll_wait(in + k, stamp, &x[k])) bad = 1;
+        if (lane < AICP_NSUM) {
+          const unsigned long long plo = (unsigned long long)x[0] | ((unsigned long long)x[1] << 32);
+          const long long phi = (long long)((unsigned long long)x[2] | ((unsigned long long)x[3] << 32));
+          const unsigned long long nl = lo + plo;
+          hi = hi + phi + (nl < lo ? 1 : 0);
+          lo = nl;
+        } else if (lane == AICP_NSUM) n_all += x[0];
+        else if (x[3]) bad = 1;
       }
+      if (lane == AICP_NSUM) st->n_read_total = n_all;
     }
-    if (threadIdx.x == 0) {
-      unsigned long long total = (unsigned long long)n;
-      for (int r = 0; r < pv.n_ranks; ++r)
-        if (r != pv.rank) total += __ldcg(reinterpret_cast<const ulonglong2*>(pv.inbox[pv.rank] + AICP_INBOX_SUMS_OFF + (size_t)r * 512) + AICP_NSUM).x;
-      st->n_read_total = total;
-    }
+    peer_verdict(st, bad, t0);
   }
   if (w == 0 && lane < AICP_NSUM) { st->sum_lo[lane] = lo; st->sum_hi[lane] = hi; }
   __threadfence();
