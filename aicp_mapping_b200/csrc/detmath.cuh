@@ -145,6 +145,26 @@ __device__ inline double fixed128_to_double(long long hi, unsigned long long lo)
   return neg ? -v : v;
 }
 
+// minimal-norm solution of a (numerically) singular A x = b through the eigen-decomposition (the fallback of
+// PointToPlaneErrorMinimizer::compute_in_place)
+static __device__ __noinline__ void det_solve6_minimal_norm(const double (&A)[6][6], const double (&b)[6], double* x) {
+  const double rtol = 6.0 * (double)FLT_EPSILON;
+  double a[6][6], v[6][6];
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) a[i][j] = A[i][j];
+  det_jacobi<6>(a, v);
+  double lmax = 0.0;
+  for (int i = 0; i < 6; ++i) { double l = fabs(a[i][i]); if (l > lmax) lmax = l; }
+  for (int i = 0; i < 6; ++i) x[i] = 0.0;
+  for (int e = 0; e < 6; ++e) {
+    double l = a[e][e];
+    if (!(l > rtol * lmax)) continue;
+    double proj = 0.0;
+    for (int i = 0; i < 6; ++i) proj = proj + v[i][e] * b[i];
+    double coef = proj / l;
+    for (int i = 0; i < 6; ++i) x[i] = x[i] + coef * v[i][e];
+  }
+}
+
 // sums: 21 upper-triangle entries of A (row-major, i <= j) then 6 entries of g; solves A x = -g.
 // returns 1 (LLT) or 2 (minimal-norm fallback)
 __device__ inline int det_solve6(const long long* sum_hi, const unsigned long long* sum_lo, double* x) {
@@ -183,20 +203,65 @@ __device__ inline int det_solve6(const long long* sum_hi, const unsigned long lo
     }
     return 1;
   }
-  double a[6][6], v[6][6];
-  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) a[i][j] = A[i][j];
-  det_jacobi<6>(a, v);
-  double lmax = 0.0;
-  for (int i = 0; i < 6; ++i) { double l = fabs(a[i][i]); if (l > lmax) lmax = l; }
-  for (int i = 0; i < 6; ++i) x[i] = 0.0;
-  for (int e = 0; e < 6; ++e) {
-    double l = a[e][e];
-    if (!(l > rtol * lmax)) continue;
-    double proj = 0.0;
-    for (int i = 0; i < 6; ++i) proj = proj + v[i][e] * b[i];
-    double coef = proj / l;
-    for (int i = 0; i < 6; ++i) x[i] = x[i] + coef * v[i][e];
+  det_solve6_minimal_norm(A, b, x);
+  return 2;
+}
+
+// warp-cooperative det_solve6: lane s < 28 passes sum s (already converted: fixed128_to_double) in `v`; every lane returns the
+// same x.  The LLT runs with one ROW of A and L per lane (lanes 0..5), so the matrices live in 12 registers per lane
+// instead of 72 in one thread (which spilled 2.9 KB under the loop kernel's 64-register cap and made the solve the longest
+// serial section of an iteration).  Each scalar is produced by exactly the operation sequence of det_solve6 -- same
+// operands, same order -- so the result is bit-identical; lanes that hold no row compute along on garbage.
+__device__ inline int det_solve6_warp(double v, double* x) {
+  const unsigned int FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int i = lane < 6 ? lane : 5;
+  double A[6], L[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int a = i < j ? i : j, c = i < j ? j : i;                 // A is symmetric: entry (min, max) of the upper triangle
+    A[j] = __shfl_sync(FULL, v, a * 6 - a * (a - 1) / 2 + (c - a));
+    L[j] = 0.0;
   }
+  const double b = -__shfl_sync(FULL, v, 21 + i);
+  const double rtol = 6.0 * (double)FLT_EPSILON;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    if (!ok) break;                                                 // warp-uniform
+    // lane j: d = A[j][j] - sum_k L[j][k]^2; lanes i > j: v = A[i][j] - sum_k L[i][k] L[j][k] -- the same expression
+    double acc = A[j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) acc = acc - L[k] * __shfl_sync(FULL, L[k], j);
+    const double ajj = __shfl_sync(FULL, A[j], j);
+    const double d = __shfl_sync(FULL, acc, j);
+    if (!(d > rtol * ajj) || !(d > 0.0)) { ok = false; break; }
+    const double ljj = sqrt(d);
+    L[j] = i == j ? ljj : (i > j ? acc / ljj : 0.0);
+  }
+  if (ok) {
+    double y[6], yv = b;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      y[k] = __shfl_sync(FULL, yv / L[k], k);                       // lane k holds b[k] - sum_{m<k} L[k][m] y[m] and L[k][k]
+      if (i > k) yv = yv - L[k] * y[k];
+    }
+#pragma unroll
+    for (int r = 5; r >= 0; --r) {
+      double vv = y[r];
+#pragma unroll
+      for (int k = r + 1; k < 6; ++k) vv = vv - __shfl_sync(FULL, L[r], k) * x[k];      // L[k][r] lives in lane k
+      x[r] = vv / __shfl_sync(FULL, L[r], r);
+    }
+    return 1;
+  }
+  // singular system (rare): every lane rebuilds A and b, the minimal-norm solution is computed redundantly
+  double Af[6][6], bf[6];
+  int s = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) { const double e = __shfl_sync(FULL, v, s); Af[r][c] = e; Af[c][r] = e; ++s; }
+  for (int r = 0; r < 6; ++r) { bf[r] = -__shfl_sync(FULL, v, s); ++s; }
+  det_solve6_minimal_norm(Af, bf, x);
   return 2;
 }
 

@@ -484,17 +484,23 @@ __device__ __forceinline__ void atomic_add_128(unsigned long long* lo, long long
   if (vhi) atomicAdd((unsigned long long*)hi, vhi);
 }
 
-// A.5 solve + pose update, A.7 checkers; one thread
+// A.5 solve + pose update, A.7 checkers.  Called by ALL 32 lanes of one warp: the sums are converted and the 6x6 system
+// solved cooperatively (det_solve6_warp), the pose update and the checkers -- short scalar chains -- run in lane 0.
 __device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read) {
-  long long hi[AICP_NSUM];
-  unsigned long long lo[AICP_NSUM];
-  for (int i = 0; i < AICP_NSUM; ++i) {
-    lo[i] = __ldcg(&st->sum_lo[i]); hi[i] = __ldcg(&st->sum_hi[i]);
-    st->sum_lo[i] = 0; st->sum_hi[i] = 0;
+  const int lane = threadIdx.x & 31;
+  double v = 0.0;
+  long long n_used = 0;
+  if (lane < AICP_NSUM) {
+    const unsigned long long lo = __ldcg(&st->sum_lo[lane]);
+    const long long hi = __ldcg(&st->sum_hi[lane]);
+    st->sum_lo[lane] = 0; st->sum_hi[lane] = 0;
+    v = fixed128_to_double(hi, lo);
+    n_used = (long long)lo;
   }
-  long long n_used = (long long)lo[27];
+  n_used = __shfl_sync(0xFFFFFFFFu, n_used, 27);
   double x[6];
-  det_solve6(hi, lo, x);
+  det_solve6_warp(v, x);
+  if (lane != 0) return;
   float dT[16], T[16];
   det_pose_increment(x, dT);
   for (int i = 0; i < 16; ++i) T[i] = st->T_iter[i];
@@ -675,10 +681,12 @@ __global__ void __launch_bounds__(256, 4) k_accumulate(const float4* __restrict_
   }
   __threadfence();
   __syncthreads();
-  if (tail && threadIdx.x == 0) {
+  if (tail && threadIdx.x < 32) {
     solve_and_check(st, lp, n);
-    st->tail_ns[2] += global_ns() - t0;
-    publish_progress(progress, st->iter, *(volatile int*)&st->done);
+    if (threadIdx.x == 0) {
+      st->tail_ns[2] += global_ns() - t0;
+      publish_progress(progress, st->iter, *(volatile int*)&st->done);
+    }
   }
 }
 
@@ -971,7 +979,7 @@ __device__ void loop_fold_solve(DeviceState* st, unsigned long long* slots, cons
   if (w == 0 && lane < AICP_NSUM) { st->sum_lo[lane] = lo; st->sum_hi[lane] = hi; }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0 && !ld_int(&st->done)) solve_and_check(st, lp, n);
+  if (threadIdx.x < 32 && !ld_int(&st->done)) solve_and_check(st, lp, n);
 }
 
 struct LoopArgs {
@@ -1121,10 +1129,13 @@ __global__ void k_sums_to_limbs(DeviceState* st, unsigned long long* limbs) {
 // completed; the hosts enqueue iteration `it` unless the loop had ended by iteration it - 2 -- a rule that depends only on
 // D, not on when a host happens to look, so all ranks issue the same number of NCCL calls.
 __global__ void k_limbs_solve(DeviceState* st, const unsigned long long* limbs, LoopParams lp, int n, int it, volatile int* progress) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (limbs[4 * AICP_NSUM] != 0 && st->status == 0) raise_status(st, AICP_B200_ERR_COMM);
+  if (threadIdx.x >= 32 || blockIdx.x != 0) return;
+  const int lane = threadIdx.x;
+  if (lane == 0 && limbs[4 * AICP_NSUM] != 0 && st->status == 0) raise_status(st, AICP_B200_ERR_COMM);
+  __syncwarp();
   if (!ld_int(&st->done)) {
-    for (int i = 0; i < AICP_NSUM; ++i) {
+    if (lane < AICP_NSUM) {
+      const int i = lane;
       unsigned long long l0 = limbs[4 * i], l1 = limbs[4 * i + 1], l2 = limbs[4 * i + 2], l3 = limbs[4 * i + 3];
       unsigned long long c = l0 >> 32;  unsigned long long w0 = l0 & 0xFFFFFFFFull;
       l1 += c; c = l1 >> 32;            unsigned long long w1 = l1 & 0xFFFFFFFFull;
@@ -1133,8 +1144,12 @@ __global__ void k_limbs_solve(DeviceState* st, const unsigned long long* limbs, 
       st->sum_lo[i] = w0 | (w1 << 32);
       st->sum_hi[i] = (long long)(w2 | (w3 << 32));
     }
+    __threadfence();
+    __syncwarp();
     solve_and_check(st, lp, n);
   }
+  __syncwarp();
+  if (lane != 0) return;
   if (ld_int(&st->done) && st->done_at < 0) st->done_at = it;
   if (progress) {
     if (st->done_at >= 0) { progress[1] = st->done_at + 1; __threadfence_system(); }
