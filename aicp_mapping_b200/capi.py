@@ -25,7 +25,7 @@ EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_wait_stream", "ai
            "aicp_b200_prefilter_get_sampled", "aicp_b200_prefilter_get_normals", "aicp_b200_prefilter_get_labels", "aicp_b200_voxel_grid",
            "aicp_b200_map_prefilter", "aicp_b200_accumulate_sweep", "aicp_b200_get_accumulated", "aicp_b200_download_accumulated", "aicp_b200_read_pcd", "aicp_b200_read_ply",
            "aicp_b200_write_pcd", "aicp_b200_read_pose_file", "aicp_b200_fov_overlap", "aicp_b200_get_fov_filtered", "aicp_b200_alignability", "aicp_b200_alignment_risk",
-           "aicp_b200_svm_parse", "aicp_b200_svm_load", "aicp_b200_svm_info", "aicp_b200_svm_predict", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_aicp_batch", "aicp_b200_pipeline_batch", "aicp_b200_comm_unique_id",
+           "aicp_b200_svm_parse", "aicp_b200_svm_load", "aicp_b200_svm_info", "aicp_b200_svm_predict", "aicp_b200_autotune_ratio", "aicp_b200_register_batch", "aicp_b200_register_batch_devices", "aicp_b200_aicp_batch", "aicp_b200_pipeline_batch", "aicp_b200_comm_unique_id",
            "aicp_b200_comm_init", "aicp_b200_comm_destroy", "aicp_b200_comm_info"]
 
 
@@ -158,6 +158,8 @@ def lib():
         L.aicp_b200_autotune_ratio.restype = C.c_float
         L.aicp_b200_register_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_void_p),
                                                C.POINTER(i64), fp, C.c_int, fp, C.POINTER(Stats), C.POINTER(C.c_int32), fp]
+        L.aicp_b200_register_batch_devices.argtypes = [C.c_void_p, ip, C.c_int32, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_void_p),
+                                                       C.POINTER(i64), fp, C.c_int, fp, C.POINTER(Stats), C.POINTER(C.c_int32), fp]
         L.aicp_b200_aicp_batch.argtypes = [C.c_void_p, i64, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double),
                                            C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(C.c_double), C.c_double, C.c_int, fp, fp,
                                            C.POINTER(Stats), C.POINTER(C.c_int32), fp]

@@ -133,6 +133,9 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   if (h->al_child) { aicp_b200_destroy(reinterpret_cast<aicp_b200_handle*>(h->al_child)); h->al_child = nullptr; }
   for (Handle* w : h->workers) aicp_b200_destroy(reinterpret_cast<aicp_b200_handle*>(w));
   h->workers.clear();
+  for (Handle* c : h->device_children) aicp_b200_destroy(reinterpret_cast<aicp_b200_handle*>(c));
+  h->device_children.clear();
+  cudaSetDevice(h->device);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   for (int i = 0; i < 2; ++i) if (h->batch_ev[i]) cudaEventDestroy(h->batch_ev[i]);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -918,6 +921,72 @@ int aicp_b200_register_batch(aicp_b200_handle* hh, int64_t n_pairs, const float*
                              float* out_T, aicp_b200_stats* stats, int32_t* status, float* batch_ms) {
   return batch_impl(hh, n_pairs, ref_xyzw, n_ref, read_xyzw, n_read, ratios, nullptr, nullptr, 0.0, streams, out_T, nullptr, stats,
                     status, batch_ms);
+}
+
+int aicp_b200_register_batch_devices(aicp_b200_handle* hh, const int32_t* devices, int32_t n_devices, int64_t n_pairs,
+                                     const float* const* ref_xyzw, const int64_t* n_ref, const float* const* read_xyzw,
+                                     const int64_t* n_read, const float* ratios, int streams, float* out_T, aicp_b200_stats* stats,
+                                     int32_t* status, float* batch_ms) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (!devices || n_devices < 1 || n_devices > 64 || n_pairs < 0 || (n_pairs > 0 && (!ref_xyzw || !n_ref || !read_xyzw || !n_read || !out_T)))
+    return fail(h, AICP_B200_ERR_BAD_ARG, "register_batch_devices: bad arguments");
+  if (batch_ms) *batch_ms = 0.f;
+  if (n_pairs == 0) return AICP_B200_OK;
+  int rc = load_config(h);
+  if (rc) return rc;
+  // one child handle per device, kept across calls (each grows its own worker pool inside batch_impl)
+  std::vector<Handle*> child((size_t)n_devices, nullptr);
+  for (int d = 0; d < n_devices; ++d) {
+    for (Handle* c : h->device_children) if (c->device == devices[d]) child[(size_t)d] = c;
+    for (int e = 0; e < d; ++e) if (devices[e] == devices[d]) return fail(h, AICP_B200_ERR_BAD_ARG, "register_batch_devices: device %d listed twice", devices[d]);
+    if (!child[(size_t)d]) {
+      aicp_b200_handle* c = nullptr;
+      rc = aicp_b200_create(nullptr, devices[d], &c);
+      if (rc) return fail(h, rc, "register_batch_devices: %s", aicp_b200_last_error(nullptr));
+      child[(size_t)d] = reinterpret_cast<Handle*>(c);
+      h->device_children.push_back(child[(size_t)d]);
+    }
+    Handle* c = child[(size_t)d];
+    c->cfg = h->cfg; c->cfg_from_file = false;
+    c->profiling = h->profiling; c->knn_schedule = h->knn_schedule; c->match_schedule = h->match_schedule; c->loop_schedule = h->loop_schedule;
+  }
+  std::vector<int> rcs((size_t)n_devices, 0);
+  std::vector<float> ms((size_t)n_devices, 0.f);
+  auto run = [&](int d) {
+    // the pairs of this device, i = d, d + G, d + 2G, ...: contiguous copies of the argument arrays, results scattered back
+    std::vector<const float*> refs, reads;
+    std::vector<int64_t> nr, nq, idx;
+    std::vector<float> rat;
+    for (int64_t i = d; i < n_pairs; i += n_devices) {
+      idx.push_back(i); refs.push_back(ref_xyzw[i]); reads.push_back(read_xyzw[i]); nr.push_back(n_ref[i]); nq.push_back(n_read[i]);
+      if (ratios) rat.push_back(ratios[i]);
+    }
+    const int64_t m = (int64_t)idx.size();
+    if (m == 0) return;
+    std::vector<float> T((size_t)m * 16);
+    std::vector<int32_t> stt((size_t)m, 0);
+    aicp_b200_stats* sub = stats ? static_cast<aicp_b200_stats*>(malloc(sizeof(aicp_b200_stats) * (size_t)m)) : nullptr;
+    rcs[(size_t)d] = batch_impl(reinterpret_cast<aicp_b200_handle*>(child[(size_t)d]), m, refs.data(), nr.data(), reads.data(), nq.data(),
+                                ratios ? rat.data() : nullptr, nullptr, nullptr, 0.0, streams, T.data(), nullptr, sub, stt.data(), &ms[(size_t)d]);
+    for (int64_t j = 0; j < m; ++j) {
+      memcpy(out_T + 16 * idx[(size_t)j], T.data() + 16 * j, 16 * sizeof(float));
+      if (status) status[idx[(size_t)j]] = stt[(size_t)j];
+      if (stats) stats[idx[(size_t)j]] = sub[j];
+    }
+    free(sub);
+  };
+  std::vector<std::thread> threads;
+  for (int d = 1; d < n_devices; ++d) threads.emplace_back(run, d);
+  run(0);
+  for (auto& t : threads) t.join();
+  cudaSetDevice(h->device);
+  int first = 0;
+  for (int d = 0; d < n_devices; ++d) {
+    if (batch_ms && ms[(size_t)d] > *batch_ms) *batch_ms = ms[(size_t)d];
+    if (rcs[(size_t)d] && !first) { first = rcs[(size_t)d]; h->last_error = "device " + std::to_string(devices[d]) + ": " + child[(size_t)d]->last_error; }
+  }
+  return first;
 }
 
 int aicp_b200_aicp_batch(aicp_b200_handle* hh, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,

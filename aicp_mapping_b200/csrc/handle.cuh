@@ -150,6 +150,7 @@ struct Handle {
 
   // batch workers: one child handle (own stream + buffers) per concurrent registration
   std::vector<Handle*> workers;
+  std::vector<Handle*> device_children;   // aicp_b200_register_batch_devices: one child handle (with its own workers) per GPU
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
   cudaEvent_t wait_ev = nullptr;     // aicp_b200_wait_stream: recorded on the caller's producer stream, waited on by h->stream
   cudaEvent_t done_ev = nullptr;

@@ -199,9 +199,10 @@ class B200Registration:
         pq, nq, keep_q = capi.ptr_and_count(cloud_read)
         return self._register(pr, nr, pq, nq, init_T)
 
-    def registerBatch(self, pairs, ratios=None, streams=0):
+    def registerBatch(self, pairs, ratios=None, streams=0, devices=None):
         """aicp_b200_register_batch: `pairs` is a list of (cloud_ref, cloud_read); independent pairs are registered
-        concurrently on `streams` CUDA streams.  Returns (T [n,4,4], stats list, status array, batch_ms)."""
+        concurrently on `streams` CUDA streams.  devices = [d0, d1, ...]: aicp_b200_register_batch_devices, pair i on GPU
+        devices[i % len(devices)] with `streams` streams each.  Returns (T [n,4,4], stats list, status array, batch_ms)."""
         n = len(pairs)
         keep, refs, reads = [], (C.c_void_p * n)(), (C.c_void_p * n)()
         n_ref, n_read = (C.c_int64 * n)(), (C.c_int64 * n)()
@@ -215,10 +216,17 @@ class B200Registration:
         status = np.zeros(n, dtype=np.int32)
         ms = C.c_float()
         rat = np.ascontiguousarray(ratios, dtype=np.float32) if ratios is not None else None
-        rc = self._lib.aicp_b200_register_batch(self._h, n, refs, n_ref, reads, n_read,
-                                                rat.ctypes.data_as(C.POINTER(C.c_float)) if rat is not None else None,
-                                                int(streams), T.ctypes.data_as(C.POINTER(C.c_float)), stats,
-                                                status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
+        if devices is not None:
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            rc = self._lib.aicp_b200_register_batch_devices(self._h, dv.ctypes.data_as(C.POINTER(C.c_int32)), len(dv), n, refs, n_ref, reads, n_read,
+                                                            rat.ctypes.data_as(C.POINTER(C.c_float)) if rat is not None else None,
+                                                            int(streams), T.ctypes.data_as(C.POINTER(C.c_float)), stats,
+                                                            status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
+        else:
+            rc = self._lib.aicp_b200_register_batch(self._h, n, refs, n_ref, reads, n_read,
+                                                    rat.ctypes.data_as(C.POINTER(C.c_float)) if rat is not None else None,
+                                                    int(streams), T.ctypes.data_as(C.POINTER(C.c_float)), stats,
+                                                    status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
         self._check(rc)
         return np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4), stats, status, float(ms.value)
 

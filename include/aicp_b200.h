@@ -352,6 +352,14 @@ int aicp_b200_register_batch(aicp_b200_handle* h, int64_t n_pairs, const float* 
  * sweep of BASELINE.json config 5 ("overlap + ..."): per pair the octree overlap, the clamp to [0.25, 0.70] with the 6-digit
  * text round trip, and the registration with that trimmed ratio, all inside the pair's worker stream.
  * ref_origins / read_origins: n_pairs x 3 doubles (sensor pose translations); out_overlap: nullable, n_pairs percentages. */
+/* The same over SEVERAL GPUs of the node from one process ("pair i -> GPU i mod G"): pair i is registered
+ * on devices[i % n_devices]; every device gets its own worker pool (`streams` streams and host threads) and the results are
+ * gathered on the host.  No data-path communication between the devices.  Clouds may be host pointers, or device pointers
+ * of any device (copied device to device).  batch_ms: the longest device time over the devices. */
+int aicp_b200_register_batch_devices(aicp_b200_handle* h, const int32_t* devices, int32_t n_devices, int64_t n_pairs,
+                                     const float* const* ref_xyzw, const int64_t* n_ref, const float* const* read_xyzw,
+                                     const int64_t* n_read, const float* ratios, int streams, float* out_T, aicp_b200_stats* stats,
+                                     int32_t* status, float* batch_ms);
 int aicp_b200_aicp_batch(aicp_b200_handle* h, int64_t n_pairs, const float* const* ref_xyzw, const int64_t* n_ref,
                          const double* ref_origins, const float* const* read_xyzw, const int64_t* n_read,
                          const double* read_origins, double resolution, int streams, float* out_T, float* out_overlap,

@@ -96,6 +96,41 @@ class B200Registration : public AbstractRegistrator {
     if (h_) aicp_b200_set_config(h_, config_name.c_str());
   }
 
+  // Independent pairs at once (bash/run_registration_validation.sh runs the pairwise tool once per pair): pair i is registered
+  // on GPU devices[i % devices.size()] (empty: the handle's own device), `streams` concurrent registrations per GPU, every
+  // pair with its own trimmed ratio (auto-tuned from its overlap; empty: the configured ratio).  Returns the number of pairs
+  // that failed; their transform stays the identity and status[i] holds the error code.
+  int registerBatch(const std::vector<pcl::PointCloud<pcl::PointXYZ>*>& refs, const std::vector<pcl::PointCloud<pcl::PointXYZ>*>& reads,
+                    const std::vector<float>& ratios, const std::vector<int>& devices, int streams,
+                    std::vector<Eigen::Matrix4f>& transforms, std::vector<int>* status = nullptr) {
+    const size_t n = refs.size();
+    transforms.assign(n, Eigen::Matrix4f::Identity());
+    if (status) status->assign(n, AICP_B200_ERR_BAD_ARG);
+    if (!h_ || reads.size() != n || (!ratios.empty() && ratios.size() != n)) return (int)n;
+    std::vector<std::vector<float> > stage(2 * n);
+    std::vector<const float*> pr(n), pq(n);
+    std::vector<int64_t> nr(n), nq(n);
+    for (size_t i = 0; i < n; ++i) {
+      pr[i] = b200_detail::as_xyzw(*refs[i], stage[2 * i], &nr[i]);
+      pq[i] = b200_detail::as_xyzw(*reads[i], stage[2 * i + 1], &nq[i]);
+    }
+    std::vector<float> T(16 * n);
+    std::vector<int32_t> st(n, 0), dev(devices.begin(), devices.end());
+    const float* rat = ratios.empty() ? nullptr : ratios.data();
+    int rc;
+    if (dev.empty()) rc = aicp_b200_register_batch(h_, (int64_t)n, pr.data(), nr.data(), pq.data(), nq.data(), rat, streams, T.data(), nullptr, st.data(), nullptr);
+    else rc = aicp_b200_register_batch_devices(h_, dev.data(), (int32_t)dev.size(), (int64_t)n, pr.data(), nr.data(), pq.data(), nq.data(), rat, streams,
+                                               T.data(), nullptr, st.data(), nullptr);
+    if (rc != AICP_B200_OK) std::cerr << "[B200] registerBatch (" << rc << "): " << aicp_b200_last_error(h_) << std::endl;
+    int failed = 0;
+    for (size_t i = 0; i < n; ++i) {
+      if (status) (*status)[i] = st[i];
+      if (st[i] == AICP_B200_OK) std::memcpy(transforms[i].data(), T.data() + 16 * i, 16 * sizeof(float));
+      else ++failed;
+    }
+    return failed;
+  }
+
   // conveniences beyond the reference interface
   const Eigen::Matrix4f& getOutputTransform() const { return last_T_; }
   float getWeightedPointUsedRatio() const { return stats_.weighted_point_used_ratio; }
@@ -292,6 +327,58 @@ inline bool regionGrowingUniformPlaneSegmentationFilterB200(aicp_b200_handle* h,
   for (int64_t i = 0; i < info.n_sampled; ++i)
     if (labels[(size_t)i] >= 0) clusters[(size_t)labels[(size_t)i]].push_back((int)i);
   return true;
+}
+
+// ---- FOV overlap filter: stands where overlapFilter stands (filteringUtils.cpp:111-193; caller App::computeAlignmentRisk,
+// app.cpp:153-156).  Same signature plus the handle: the points of each cloud that the OTHER sensor could have seen (range
+// and angular field of view) are appended to accepted_pointsA / accepted_pointsB, the return value is the overlap in
+// percent.  -1 on failure (the reference has no failure path).
+inline float overlapFilterB200(aicp_b200_handle* h, pcl::PointCloud<pcl::PointXYZ>& cloudA, pcl::PointCloud<pcl::PointXYZ>& cloudB,
+                               Eigen::Isometry3d poseA, Eigen::Isometry3d poseB, float range, float angularView,
+                               pcl::PointCloud<pcl::PointXYZ>& accepted_pointsA, pcl::PointCloud<pcl::PointXYZ>& accepted_pointsB) {
+  const int64_t nA = (int64_t)cloudA.points.size(), nB = (int64_t)cloudB.points.size();
+  std::vector<float> outA(4 * (size_t)(nA > 0 ? nA : 1)), outB(4 * (size_t)(nB > 0 ? nB : 1));
+  int64_t counts[2] = {0, 0};
+  float overlap = -1.f;
+  const int rc = aicp_b200_fov_overlap(h, reinterpret_cast<const float*>(cloudA.points.data()), nA, reinterpret_cast<const float*>(cloudB.points.data()), nB,
+                                       poseA.matrix().data(), poseB.matrix().data(), range, angularView, outA.data(), outB.data(), counts, &overlap);
+  if (rc != AICP_B200_OK) {
+    std::cerr << "[B200] overlapFilter failed (" << rc << "): " << aicp_b200_last_error(h) << std::endl;
+    return -1.f;
+  }
+  pcl::PointCloud<pcl::PointXYZ>* dst[2] = {&accepted_pointsA, &accepted_pointsB};
+  const std::vector<float>* src[2] = {&outA, &outB};
+  for (int c = 0; c < 2; ++c) {
+    const size_t old = dst[c]->points.size();
+    dst[c]->points.resize(old + (size_t)counts[c]);
+    if (counts[c] > 0) std::memcpy(reinterpret_cast<float*>(dst[c]->points.data()) + 4 * old, src[c]->data(), sizeof(float) * 4 * (size_t)counts[c]);
+    dst[c]->width = (uint32_t)dst[c]->points.size();
+    dst[c]->height = 1;
+  }
+  return overlap;
+}
+
+// ---- alignability: stands where alignabilityFilter stands (filteringUtils.cpp:196-430; caller app.cpp:165-167).  Same
+// signature plus the handle.  The three PointXYZRGBNormal clouds of the reference (matched planes of both clouds and the
+// eigenvectors) only feed its visualiser (aicp_ros/src/visualizer_ros.cpp) and are left as they come in; the matching
+// itself is available through the optional `matching` (for every kept plane of B the index of its plane of A, or -1).
+inline float alignabilityFilterB200(aicp_b200_handle* h, pcl::PointCloud<pcl::PointXYZ>& cloudA, pcl::PointCloud<pcl::PointXYZ>& cloudB,
+                                    Eigen::Isometry3d poseA, Eigen::Isometry3d poseB,
+                                    pcl::PointCloud<pcl::PointXYZRGBNormal>::Ptr /*cloudA_planes*/,
+                                    pcl::PointCloud<pcl::PointXYZRGBNormal>::Ptr /*cloudB_planes*/,
+                                    pcl::PointCloud<pcl::PointXYZRGBNormal>::Ptr /*eigenvectors*/, std::vector<int32_t>* matching = nullptr) {
+  const int64_t nA = (int64_t)cloudA.points.size(), nB = (int64_t)cloudB.points.size();
+  float alignability = -1.f;                                                    // the reference's initial value (:201)
+  int64_t info[3] = {0, 0, 0};
+  std::vector<int32_t> m((size_t)(nB > 0 ? nB : 1), -1);
+  const int rc = aicp_b200_alignability(h, reinterpret_cast<const float*>(cloudA.points.data()), nA, reinterpret_cast<const float*>(cloudB.points.data()), nB,
+                                        poseA.matrix().data(), poseB.matrix().data(), nullptr, &alignability, m.data(), (int64_t)m.size(), info);
+  if (rc != AICP_B200_OK) {
+    std::cerr << "[B200] alignabilityFilter failed (" << rc << "): " << aicp_b200_last_error(h) << std::endl;
+    return -1.f;
+  }
+  if (matching) matching->assign(m.begin(), m.begin() + (size_t)info[1]);
+  return alignability;
 }
 
 // ---- classifier: stands where aicp::SVM stands (aicp_core/include/aicp_classification/svm.hpp:17-34) --------------------------

@@ -83,6 +83,28 @@ int main(int argc, char** argv) {
     if (!ok || filtered->points.empty() || filtered->points.size() > in->points.size()) return 7;
     std::printf("prefilter %zu -> %zu points\n", in->points.size(), filtered->points.size());
   }
+  // the alignment-risk inputs as App::computeAlignmentRisk computes them (app.cpp:153-167): FOV overlap, then alignability of the
+  // accepted points; and the batched entry point over every GPU of the box
+  {
+    aicp_b200_handle* fh = nullptr;
+    if (aicp_b200_create(nullptr, -1, &fh) != AICP_B200_OK) return 6;
+    pcl::PointCloud<pcl::PointXYZ> accA, accB;
+    Eigen::Isometry3d poseA = Eigen::Isometry3d::Identity(), poseB = Eigen::Isometry3d::Identity();
+    const float fov = aicp::overlapFilterB200(fh, ref, read, poseA, poseB, 30.f, 270.f, accA, accB);
+    if (fov < 0.f || accA.points.empty() || accA.points.size() > ref.points.size()) { aicp_b200_destroy(fh); return 10; }
+    pcl::PointCloud<pcl::PointXYZRGBNormal>::Ptr none;
+    std::vector<int32_t> matching;
+    const float al = aicp::alignabilityFilterB200(fh, accA, accB, poseA, poseB, none, none, none, &matching);
+    aicp_b200_destroy(fh);
+    if (al < 0.f) return 11;
+    std::printf("fov_overlap %.4f alignability %.4f planes_B %zu\n", fov, al, matching.size());
+    auto* breg = static_cast<aicp::B200Registration*>(registr.get());
+    std::vector<pcl::PointCloud<pcl::PointXYZ>*> refs(3, &ref), reads(3, &read);
+    std::vector<Eigen::Matrix4f> Ts;
+    std::vector<int> st;
+    if (breg->registerBatch(refs, reads, std::vector<float>(), std::vector<int>(1, 0), 2, Ts, &st) != 0) return 12;
+    for (int i = 0; i < 16; ++i) if (Ts[2].data()[i] != T.data()[i]) return 13;          // same pair, same bits as registerClouds
+  }
   // the classifier as App::computeAlignmentRisk calls it (app.cpp:175-181): testing_data << overlap, alignability
   if (argc > 3) {
     ClassificationParams cp; cp.type = "B200"; cp.svm.threshold = 0.5; cp.svm.saveFile = argv[3];

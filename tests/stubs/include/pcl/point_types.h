@@ -24,10 +24,15 @@ struct Vector3d {
   double y() const { return v[1]; }
   double z() const { return v[2]; }
 };
+struct Matrix4d {
+  double m[16];
+  const double* data() const { return m; }
+};
 struct Isometry3d {
-  double t[3];
-  Vector3d translation() const { return Vector3d{{t[0], t[1], t[2]}}; }
-  static Isometry3d Identity() { return Isometry3d{{0, 0, 0}}; }
+  double m[16];                                           // column-major 4x4, what Isometry3d::matrix().data() points at
+  Vector3d translation() const { return Vector3d{{m[12], m[13], m[14]}}; }
+  Matrix4d matrix() const { Matrix4d r; for (int i = 0; i < 16; ++i) r.m[i] = m[i]; return r; }
+  static Isometry3d Identity() { Isometry3d I; for (int i = 0; i < 16; ++i) I.m[i] = (i % 5 == 0) ? 1.0 : 0.0; return I; }
 };
 }  // namespace Eigen
 

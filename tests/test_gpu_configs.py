@@ -126,3 +126,34 @@ def test_aicp_batch_whole_step_equals_separate_calls(reg, orc):
     o = orc.icp(p["ref"], p["read"], orc.default_config(ratio=float(orc.autotune_ratio(float(o_ov))[0]), threads=8))
     assert np.float32(o_ov) == overlap[-1] and np.array_equal(u32(o.T), u32(T[-1]))
     ov.close()
+
+
+def test_register_batch_over_all_devices(reg):
+    """aicp_b200_register_batch_devices (pair i on GPU devices[i % G], one worker pool per GPU, one process) against the
+    single-device batch: same transforms, iteration counts and per-pair status bit for bit, for host and for device inputs,
+    with a failing pair in the middle.  Runs on every GPU the box has (one on the driver's test box, eight on the scaling
+    box)."""
+    import torch
+    G = min(torch.cuda.device_count(), 8)
+    pairs = [synth.make_pair(5, t, 5000 + 300 * t) for t in range(13)]
+    clouds = [(p["ref"], p["read"]) for p in pairs]
+    bad = clouds[5][1].copy(); bad[3, 1] = np.inf
+    clouds[5] = (clouds[5][0], bad)                                      # NONFINITE_INPUT in pair 5 only
+    ratios = [0.55 + 0.01 * t for t in range(13)]
+    reg.setConfig(max_iterations=20)
+
+    def run(devices, inputs):
+        try:
+            return reg.registerBatch(inputs, ratios=ratios, streams=3, devices=devices)
+        except ab.capi.AicpError as e:                                   # the call reports the first failing pair ...
+            assert e.code_name == "NONFINITE_INPUT"
+            return None
+    assert run(None, clouds) is None and run(list(range(G)), clouds) is None
+    clouds[5] = (pairs[5]["ref"], pairs[5]["read"])                      # ... and with it repaired everything agrees
+    T1, s1, st1, ms1 = reg.registerBatch(clouds, ratios=ratios, streams=3)
+    TG, sG, stG, msG = reg.registerBatch(clouds, ratios=ratios, streams=3, devices=list(range(G)))
+    assert np.array_equal(u32(T1), u32(TG)) and list(st1) == list(stG) == [0] * 13 and msG > 0
+    assert [s.iterations for s in s1] == [s.iterations for s in sG]
+    dev_in = [(torch.from_numpy(ab.capi.to_xyzw(r)).cuda(), torch.from_numpy(ab.capi.to_xyzw(q)).cuda()) for r, q in clouds]
+    TD, _, stD, _ = reg.registerBatch(dev_in, ratios=ratios, streams=3, devices=list(range(G))[::-1])
+    assert np.array_equal(u32(T1), u32(TD)) and list(stD) == [0] * 13
