@@ -117,6 +117,7 @@ int aicp_b200_create(const char* icp_yaml_path, int device, aicp_b200_handle** o
     return fail(nullptr, AICP_B200_ERR_CUDA, "cannot initialise CUDA device %d", device);
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&nh->ev[i]);
+  if (const char* e = getenv("AICP_B200_CROP")) nh->crop_legacy = strcmp(e, "legacy") == 0;
   if (const char* e = getenv("AICP_B200_SPREAD")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nh->loop_spread = v; }
   (void)h;
   *out = reinterpret_cast<aicp_b200_handle*>(nh);
@@ -143,6 +144,8 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->read_in.release(); h->read_ix.release(); h->read0.release(); h->read_out.release(); h->read_init.release();
   h->match_pos.release(); h->d2.release(); h->hist.release(); h->cand.release(); h->acc_slots.release(); h->trace_idx.release();
   if (h->progress_host) cudaFreeHost((void*)h->progress_host);
+  if (h->crop_total_host) cudaFreeHost((void*)h->crop_total_host);
+  h->crop_stash.release();
   h->tmp_ix.release(); h->tmp_a.release(); h->tmp_b.release(); h->tmp_i.release(); h->tmp_f.release();
   h->ovl_bits_a.release(); h->ovl_bits_b.release(); h->ovl_counts.release(); h->crop_status.release(); h->crop_out.release(); h->map.release();
   h->pf_ix.release(); h->pf_sampled.release(); h->pf_normals.release(); h->pf_normals_orig.release(); h->pf_out.release();

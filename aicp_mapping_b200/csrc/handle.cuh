@@ -113,6 +113,10 @@ struct Handle {
   DevBuf<unsigned long long> ovl_counts;
   DevBuf<unsigned long long> crop_status;   // chained-scan tile status of the crop box + total + ticket
   int64_t crop_n = 0;
+  volatile unsigned long long* crop_total_host = nullptr;   // mapped pinned: the number of kept points, written by the crop kernels
+  unsigned long long* crop_total_dev = nullptr;
+  DevBuf<float4> crop_stash;                 // kept points per CTA run, before k_crop_gather puts them in input order
+  bool crop_legacy = false;                  // AICP_B200_CROP=legacy: the round-1 kernel (A/B measurements)
   DevBuf<float4> map;                       // persistent device-resident map (aicp_b200_map_*), original point order
   int64_t map_n = 0;
   DevBuf<float4> crop_out;                  // cropped cloud when the caller asks for a device-resident result
