@@ -299,16 +299,20 @@ def raw_sweep(config, trial=0, n_sweeps=None):
     raise ValueError("raw_sweep supports configs 2 and 3")
 
 
-def make_map_case(n_map=10485760, n_read=122880, trial=0, n_poses=1):
-    """C4: fixed map + reading(s) scanned inside it with the HDL-64 model, expressed through an erroneous prior."""
+def make_map_case(n_map=10485760, n_read=122880, trial=0, n_poses=1, remove_ground=False):
+    """C4: fixed map + reading(s) scanned inside it with the HDL-64 model, expressed through an erroneous prior.
+    remove_ground: drop the ground hits of the reading (z < 0.2 m) as the KITTI tools do before registration; with the
+    ground in, the trimmed half of the matches is almost all ground and the pose is not constrained along it."""
     rng = np.random.default_rng(1000 * 4 + trial)
     map_xyz, boxes = campus_map(n_map, rng)
     out = []
     for _ in range(n_poses):
         pose = rigid(rng.uniform(-60, 60), rng.uniform(-3, 3), 1.73, 0, 0, rng.uniform(-np.pi, np.pi))
-        n_az = 1024 if n_read <= 16384 else 6000
+        n_az = 1024 if n_read <= 16384 else (12000 if remove_ground else 6000)
         p = lidar_scan(pose, boxes, HDL64_ELEV, n_az, rng, max_range=100.0)
         p = p[(np.abs(p[:, 0]) < 100) & (np.abs(p[:, 1]) < 100)]
+        if remove_ground:
+            p = p[p[:, 2] >= 0.2]
         read_true = _exactly(p, n_read, "C4 reading").astype(np.float32)
         E = _prior_error(rng)
         out.append(dict(read=apply_T(E, read_true), T_true=np.linalg.inv(E), read_origin=E[:3, :3] @ pose[:3, 3] + E[:3, 3]))
