@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libaicp_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "index.cu", "sort.cu", "normals.cu", "icp.cu", "overlap.cu", "crop.cu", "prefilter.cu", "alignability.cu", "ingest.cu", "svm.cu", "comm.cu", "config_yaml.cpp"]
+SOURCES = ["api.cu", "index.cu", "sort.cu", "normals.cu", "icp.cu", "append.cu", "overlap.cu", "crop.cu", "prefilter.cu", "alignability.cu", "ingest.cu", "svm.cu", "comm.cu", "config_yaml.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++"]

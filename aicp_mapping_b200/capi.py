@@ -18,7 +18,7 @@ STOP_NONE, STOP_COUNTER, STOP_DIFFERENTIAL = 0, 1, 2
 # every symbol declared in include/aicp_b200.h
 EXPORTS = ["aicp_b200_create", "aicp_b200_destroy", "aicp_b200_wait_stream", "aicp_b200_last_error", "aicp_b200_version", "aicp_b200_set_config",
            "aicp_b200_set_config_struct", "aicp_b200_get_config", "aicp_b200_parse_icp_yaml", "aicp_b200_register",
-           "aicp_b200_set_reference", "aicp_b200_register_to_reference", "aicp_b200_get_output_reading",
+           "aicp_b200_set_reference", "aicp_b200_register_to_reference", "aicp_b200_reference_append", "aicp_b200_get_output_reading",
            "aicp_b200_get_initialized_reading", "aicp_b200_get_reference_normals", "aicp_b200_enable_match_trace",
            "aicp_b200_get_trace_matches", "aicp_b200_set_profiling", "aicp_b200_set_knn_schedule", "aicp_b200_set_match_schedule", "aicp_b200_set_loop_schedule", "aicp_b200_surface_normals", "aicp_b200_match", "aicp_b200_trim_threshold",
            "aicp_b200_overlap", "aicp_b200_crop_box", "aicp_b200_get_cropped", "aicp_b200_download_cropped", "aicp_b200_map_append", "aicp_b200_map_size", "aicp_b200_map_crop", "aicp_b200_prefilter_default_config", "aicp_b200_prefilter", "aicp_b200_get_prefiltered",
@@ -50,6 +50,10 @@ class Stats(C.Structure):
                 ("profiled", C.c_int32), ("ms_index", C.c_float), ("ms_normals", C.c_float), ("ms_match", C.c_float),
                 ("ms_select", C.c_float), ("ms_accumulate", C.c_float), ("ms_tail_pick", C.c_float), ("ms_tail_select", C.c_float),
                 ("ms_tail_solve", C.c_float), ("ms_exchange", C.c_float), ("trace", IterTrace * MAX_ITERS)]
+
+
+class AppendInfo(C.Structure):
+    _fields_ = [("n_total", C.c_int64), ("n_recomputed", C.c_int64), ("incremental", C.c_int32), ("ms", C.c_float)]
 
 
 class PrefilterConfig(C.Structure):
@@ -102,6 +106,7 @@ def lib():
         L.aicp_b200_register.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, fp, C.POINTER(Stats)]
         L.aicp_b200_set_reference.argtypes = [C.c_void_p, C.c_void_p, i64]
         L.aicp_b200_register_to_reference.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p, fp, C.POINTER(Stats)]
+        L.aicp_b200_reference_append.argtypes = [C.c_void_p, C.c_void_p, i64, C.POINTER(AppendInfo)]
         L.aicp_b200_get_output_reading.argtypes = [C.c_void_p, C.c_void_p, i64]
         L.aicp_b200_get_initialized_reading.argtypes = [C.c_void_p, C.c_void_p, i64]
         L.aicp_b200_get_reference_normals.argtypes = [C.c_void_p, C.c_void_p, i64]

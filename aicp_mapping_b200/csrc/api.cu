@@ -141,6 +141,9 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   for (int i = 0; i < 2; ++i) if (h->batch_ev[i]) cudaEventDestroy(h->batch_ev[i]);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_rec.release(); h->refc_cell.release(); h->normals.release(); h->knn_pos.release();
+  h->ref_rk2.release(); h->app_pts.release(); h->app_normals.release(); h->app_keys.release(); h->app_vals.release(); h->app_new.release(); h->app_flag.release();
+  h->app_scan.release(); h->app_tiles.release(); h->app_rk2.release(); h->app_rmax.release(); h->app_list.release();
+  if (h->app_meta) cudaFree(h->app_meta);
   h->read_in.release(); h->read_ix.release(); h->read0.release(); h->read_out.release(); h->read_init.release();
   h->match_pos.release(); h->d2.release(); h->hist.release(); h->cand.release(); h->acc_slots.release(); h->trace_idx.release();
   if (h->progress_host) cudaFreeHost((void*)h->progress_host);
@@ -260,6 +263,39 @@ int aicp_b200_register_to_reference(aicp_b200_handle* hh, const float* read_xyzw
     else init = init_T;
   }
   return run_registration(h, init, rebuild, stats, out_T);
+}
+
+int aicp_b200_reference_append(aicp_b200_handle* hh, const float* xyzw, int64_t n, aicp_b200_append_info* info) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  H_CHECK(h);
+  if (n < 0 || (n > 0 && !xyzw) || h->n_ref + n > (1ll << 28)) return fail(h, AICP_B200_ERR_BAD_ARG, "reference_append: bad arguments");
+  if (h->comm) return fail(h, AICP_B200_ERR_BAD_ARG, "reference_append: not available on a handle with a communicator");
+  if (h->n_ref < 1) return fail(h, AICP_B200_ERR_BAD_ARG, "reference_append: call aicp_b200_set_reference first");
+  if (info) { memset(info, 0, sizeof(*info)); info->n_total = h->n_ref; }
+  if (n == 0) return AICP_B200_OK;
+  int rc = load_config(h);
+  if (rc) return rc;
+  if (!h->ref_ready || h->ref_knn != h->cfg.knn_normals) {
+    // no live index to update yet (or the chain asks for other neighbourhoods): grow the stored cloud, the next registration builds
+    const int64_t total = h->n_ref + n;
+    if ((size_t)total > h->ref_in.cap) {
+      DevBuf<float4> bigger;
+      CUDA_TRY(bigger.reserve((size_t)total + (size_t)total / 4));
+      CUDA_TRY(cudaMemcpyAsync(bigger.p, h->ref_in.p, sizeof(float4) * (size_t)h->n_ref, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      h->ref_in.release();
+      h->ref_in = bigger;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->ref_in.p + h->n_ref, xyzw, sizeof(float4) * (size_t)n,
+                             is_device_ptr(xyzw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->n_ref = total; h->ref_ready = false;
+    if (info) info->n_total = total;
+    return AICP_B200_OK;
+  }
+  const float4* pts;
+  if ((rc = upload_points(h, h->tmp_a, xyzw, n, &pts))) return rc;
+  return run_reference_append(h, pts, n, info);
 }
 
 int aicp_b200_get_output_reading(aicp_b200_handle* hh, float* xyzw, int64_t n) {

@@ -70,6 +70,13 @@ struct Handle {
   DevBuf<float4> refc_cell;      // centred cell boxes
   DevBuf<float4> normals;        // Morton order (nx,ny,nz,density)
   DevBuf<int> knn_pos;           // n x knn neighbour positions (Morton order), scratch of the normals filter
+  DevBuf<float> ref_rk2;         // per reference point (Morton order): squared distance to its last k-NN list entry
+  bool ref_recentre = false;     // the reference changed by an append: centred copies and mean must be refreshed
+  DevBuf<float4> app_pts, app_normals;                       // merge targets of an append (swapped with the live arrays)
+  DevBuf<unsigned int> app_keys, app_vals, app_new, app_flag, app_scan, app_tiles;
+  DevBuf<float> app_rk2, app_rmax;
+  DevBuf<int> app_list;
+  IndexMeta* app_meta = nullptr;
   int64_t n_ref = 0;
   bool ref_ready = false;
   int ref_knn = 0;
@@ -163,12 +170,18 @@ struct Handle {
 // ---- index.cu
 // with_tree = false: Morton order only (pts), no radix tree -- enough to make the queries of a warp spatially coherent
 int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n, bool with_tree = true);
+int build_tree(Handle* h, SpatialIndex& ix, int n);     // radix tree + boxes over ix.keys / ix.pts (already Morton-ordered)
+void launch_index_stats(Handle* h, const float4* pts, int n, IndexMeta* m);
+void launch_morton_keys(Handle* h, const SpatialIndex& ix, const float4* pts, int n, unsigned int* keys, unsigned int* vals, unsigned int first_index);
+// ---- append.cu
+int run_reference_append(Handle* h, const float4* new_pts, int64_t m, aicp_b200_append_info* info);
 // ---- sort.cu
 int radix_sort_pairs(Handle* h, unsigned int* keys, unsigned int* vals, unsigned int* keys_alt, unsigned int* vals_alt, int n,
                      DevBuf<unsigned int>& scratch);
 // ---- normals.cu
-int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig, int q0 = 0, int q1 = -1);
-int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q0 = 0, int q1 = -1);   // lists -> h->knn_pos (Morton positions)
+int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig, int q0 = 0, int q1 = -1,
+                        const int* qlist = nullptr, float* rk2 = nullptr);
+int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q0 = 0, int q1 = -1, const int* qlist = nullptr);   // lists -> h->knn_pos (Morton positions)
 // ---- icp.cu
 int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference, aicp_b200_stats* stats, float* out_T);
 int run_match_stage(Handle* h, const SpatialIndex& ix, const float4* qry, int64_t n_qry, int* out_idx, float* out_d2);

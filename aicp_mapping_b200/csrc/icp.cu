@@ -1308,12 +1308,20 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
       if (!rc) rc = comm_allgather_bytes(h, h->normals.p, (size_t)per * sizeof(float4));
     } else {
       CUDA_TRY(h->normals.reserve((size_t)h->ref_ix.n));
-      rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr);
+      CUDA_TRY(h->ref_rk2.reserve((size_t)h->ref_ix.n));      // k-th neighbour distances: what aicp_b200_reference_append needs later
+      rc = run_surface_normals(h, h->ref_ix, cfg.knn_normals, h->normals.p, nullptr, 0, -1, nullptr, h->ref_rk2.p);
     }
     if (rc) return rc;
     h->ref_knn = cfg.knn_normals;
     mark(2);
-  } else { mark(1); mark(2); }
+  } else {
+    mark(1); mark(2);
+    if (h->ref_recentre) {                  // the reference grew by an append: new mean, new centred copies
+      CUDA_TRY(h->refc_pts.reserve((size_t)h->ref_ix.n));
+      CUDA_TRY(h->refc_rec.reserve((size_t)4 * h->ref_ix.n));
+      CUDA_TRY(h->refc_cell.reserve((size_t)2 * h->ref_ix.n));
+    }
+  }
   if (cfg.reading_normals) {
     // the reference runs the same filter on the reading (icp_autotuned.yaml:9-14); PointToPlane never reads the result
     rc = build_index(h, h->tmp_ix, h->read_in.p, n_read);
@@ -1328,7 +1336,8 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   }
   CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * AICP_HIST_BINS, s));
   k_loop_init<<<1, 32, 0, s>>>(h->st, h->ref_ix.meta, (long long)n_ref, init_T_host ? 1 : 0);
-  if (rebuild_reference) {
+  if (rebuild_reference || h->ref_recentre) {
+    h->ref_recentre = false;
     int n4 = 4 * (h->ref_ix.n - 1);
     int m = h->ref_ix.n > n4 ? h->ref_ix.n : n4;
     k_centre<<<(m + 255) / 256, 256, 0, s>>>(h->ref_ix.pts.p, h->ref_ix.n, h->ref_ix.rec.p, n4, h->ref_ix.cellbox.p, h->st,

@@ -89,13 +89,24 @@ __global__ void k_quant_params(IndexMeta* m) {
 }
 
 __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ pts, int n, const IndexMeta* __restrict__ m,
-                                                     unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
+                                                     unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, unsigned int first_index) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float lx = m->qlo[0], ly = m->qlo[1], lz = m->qlo[2], scale = m->qscale;
   float4 p = __ldg(&pts[i]);
   keys[i] = morton_key(morton_quant(p.x, lx, scale), morton_quant(p.y, ly, scale), morton_quant(p.z, lz, scale));
-  vals[i] = (unsigned)i;
+  vals[i] = first_index + (unsigned)i;      // original index: appended points continue the numbering (append.cu)
+}
+
+// bounding box, exact centroid sums and the non-finite flag of a cloud into *m (reset first)
+void launch_index_stats(Handle* h, const float4* pts, int n, IndexMeta* m) {
+  k_meta_init<<<1, 32, 0, h->stream>>>(m);
+  const int blocks = (n + 255) / 256;
+  k_index_stats<<<blocks < 148 * 2 ? blocks : 148 * 2, 256, 0, h->stream>>>(pts, n, m);
+}
+
+void launch_morton_keys(Handle* h, const SpatialIndex& ix, const float4* pts, int n, unsigned int* keys, unsigned int* vals, unsigned int first_index) {
+  k_morton_keys<<<(n + 255) / 256, 256, 0, h->stream>>>(pts, n, ix.meta, keys, vals, first_index);
 }
 
 __global__ void __launch_bounds__(256) k_gather(const float4* __restrict__ pts, const unsigned int* __restrict__ perm, int n,
@@ -318,26 +329,40 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
   int stat_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
   k_index_stats<<<stat_blocks, 256, 0, s>>>(pts_dev, n, ix.meta);
   k_quant_params<<<1, 32, 0, s>>>(ix.meta);
-  k_morton_keys<<<blocks, 256, 0, s>>>(pts_dev, n, ix.meta, ix.keys.p, ix.vals.p);
+  k_morton_keys<<<blocks, 256, 0, s>>>(pts_dev, n, ix.meta, ix.keys.p, ix.vals.p, 0u);
   int rc = radix_sort_pairs(h, ix.keys.p, ix.vals.p, ix.keys_alt.p, ix.vals_alt.p, n, ix.sort_tmp);    // result in keys / vals
   if (rc) return rc;
   k_gather<<<blocks, 256, 0, s>>>(pts_dev, ix.vals.p, n, ix.pts.p);
   h->launches += 5;
-  if (n > 1 && with_tree) {
-    int* parent_int = ix.flags.p;
-    int* parent_leaf = ix.flags.p + n;
-    const int n_l1 = (n + 31) / 32, n_l2 = (n + 1023) / 1024, n_l3 = (n + 32767) / 32768;
-    float4* l1 = ix.chunkbox.p;
-    float4* l2 = l1 + 2 * (size_t)n_l1;
-    float4* l3 = l2 + 2 * (size_t)n_l2;
-    k_chunk_boxes<<<n_l2, 1024, 0, s>>>(ix.pts.p, n, l1, l2);
-    k_chunk_boxes_top<<<(n_l3 * 32 + 255) / 256, 256, 0, s>>>(l2, n_l2, l3, n_l3);
-    k_radix_tree<<<blocks, 256, 0, s>>>(ix.keys.p, n, ix.node_meta.p, parent_int, parent_leaf, ix.owner.p, ix.owner.p + n, ix.meta, ix.cellbox.p);
-    k_refit<<<(2 * (n - 1) + 255) / 256, 256, 0, s>>>(ix.pts.p, n, ix.node_meta.p, parent_int, l1, l2, l3, ix.rec.p);
-    h->launches += 4;
-  }
+  if (n > 1 && with_tree && (rc = build_tree(h, ix, n))) return rc;
   CUDA_TRY(cudaGetLastError());
   ix.n = n;
+  return AICP_B200_OK;
+}
+
+// the radix tree, the chunk boxes and the node records over ix.keys (sorted) / ix.pts (Morton-ordered), n > 1; the buffers
+// are grown here, so an append that merged more points into the arrays can call it directly
+int build_tree(Handle* h, SpatialIndex& ix, int n) {
+  cudaStream_t s = h->stream;
+  CUDA_TRY(ix.rec.reserve((size_t)4 * n));
+  CUDA_TRY(ix.node_meta.reserve((size_t)n));
+  CUDA_TRY(ix.flags.reserve((size_t)2 * n));
+  CUDA_TRY(ix.chunkbox.reserve((size_t)2 * ((size_t)n / 32 + n / 1024 + n / 32768 + 3)));
+  CUDA_TRY(ix.owner.reserve((size_t)2 * n));
+  CUDA_TRY(ix.cellbox.reserve((size_t)2 * n));
+  const int blocks = (n + 255) / 256;
+  int* parent_int = ix.flags.p;
+  int* parent_leaf = ix.flags.p + n;
+  const int n_l1 = (n + 31) / 32, n_l2 = (n + 1023) / 1024, n_l3 = (n + 32767) / 32768;
+  float4* l1 = ix.chunkbox.p;
+  float4* l2 = l1 + 2 * (size_t)n_l1;
+  float4* l3 = l2 + 2 * (size_t)n_l2;
+  k_chunk_boxes<<<n_l2, 1024, 0, s>>>(ix.pts.p, n, l1, l2);
+  k_chunk_boxes_top<<<(n_l3 * 32 + 255) / 256, 256, 0, s>>>(l2, n_l2, l3, n_l3);
+  k_radix_tree<<<blocks, 256, 0, s>>>(ix.keys.p, n, ix.node_meta.p, parent_int, parent_leaf, ix.owner.p, ix.owner.p + n, ix.meta, ix.cellbox.p);
+  k_refit<<<(2 * (n - 1) + 255) / 256, 256, 0, s>>>(ix.pts.p, n, ix.node_meta.p, parent_int, l1, l2, l3, ix.rec.p);
+  h->launches += 4;
+  CUDA_TRY(cudaGetLastError());
   return AICP_B200_OK;
 }
 

@@ -140,23 +140,26 @@ __device__ __forceinline__ void knn_descend(const IndexView& ix, WarpKnn& w, int
 #define KNN_RUN 16        // consecutive Morton-ordered queries handled by one warp
 
 __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_warp(IndexView ix, int k, int* __restrict__ knn_pos,
-                                                             int* __restrict__ knn_out_orig, int q0, int q1) {
+                                                             int* __restrict__ knn_out_orig, int q0, int q1, const int* __restrict__ qlist) {
   __shared__ int s_a[KNN_WARPS][AICP_STACK];
   __shared__ int s_b[KNN_WARPS][AICP_STACK];
   __shared__ float s_d[KNN_WARPS][AICP_STACK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int run = blockIdx.x * KNN_WARPS + wid;
-  const int i0 = q0 + run * KNN_RUN;          // queries [q0, q1): the whole cloud, or this rank's slice of a replicated reference
+  // queries [q0, q1): the whole cloud, this rank's slice of a replicated reference, or (qlist) entries q0 .. q1 - 1 of a list
+  // of Morton positions in ascending order -- the points whose neighbourhood an appended cloud changed (append.cu)
+  const int i0 = q0 + run * KNN_RUN;
   if (i0 >= q1) return;
   const int i1 = i0 + KNN_RUN < q1 ? i0 + KNN_RUN : q1;
   int* st_a = s_a[wid]; int* st_b = s_b[wid]; float* st_d = s_d[wid];
   WarpKnn w;
   w.k = k; w.lane = lane;
   w.ld = INFINITY; w.lid = 0x7FFFFFFF; w.lpos = -1;
-  for (int i = i0; i < i1; ++i) {
+  for (int r = i0; r < i1; ++r) {
+    const int i = qlist ? __ldg(&qlist[r]) : r;
     float4 q = __ldg(&ix.pts[i]);
     w.qx = q.x; w.qy = q.y; w.qz = q.z;
-    if (i == i0) {
+    if (r == i0) {
       // first query of the run: seed with the 32 Morton neighbours of the query (itself included) and keep the k nearest
       int pre_lo = i - 16;
       if (pre_lo > ix.n - 32) pre_lo = ix.n - 32;
@@ -410,9 +413,17 @@ __global__ void __launch_bounds__(32 * TILE_WARPS) k_knn_tile(IndexView ix, int 
 }
 
 __global__ void __launch_bounds__(128) k_normals_from_knn(IndexView ix, int k, const int* __restrict__ knn_pos,
-                                                          float4* __restrict__ normals_morton, int q0, int q1) {
+                                                          float4* __restrict__ normals_morton, int q0, int q1,
+                                                          const int* __restrict__ qlist, float* __restrict__ rk2) {
   int i = q0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= q1) return;
+  if (qlist) i = __ldg(&qlist[i]);
+  if (rk2) {
+    // squared distance to the LAST neighbour of the list (lists are ascending in (d2, id)): a later point enters this list
+    // exactly when it is nearer than that, which is how an append finds the neighbourhoods it changed (append.cu)
+    const float4 a = __ldg(&ix.pts[i]), b = __ldg(&ix.pts[__ldg(&knn_pos[(size_t)i * k + k - 1])]);
+    rk2[i] = d2_f(a.x, a.y, a.z, b.x, b.y, b.z);
+  }
   const int* nb = knn_pos + (size_t)i * k;
   // mean and covariance in list order, float64
   double mx = 0, my = 0, mz = 0;
@@ -467,7 +478,7 @@ __global__ void __launch_bounds__(128) k_normals_from_knn(IndexView ix, int k, c
 
 // exact k-NN lists (positions in Morton order, ascending (d2, original index)) into h->knn_pos; shared by the SurfaceNormal
 // filter of the ICP chain and by the pre-filter (prefilter.cu: pcl::NormalEstimation + pcl::RegionGrowing neighbourhoods)
-int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q0, int q1) {
+int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q0, int q1, const int* qlist) {
   if (knn < 1 || knn > 32) return fail(h, AICP_B200_ERR_BAD_ARG, "k-NN search: knn %d outside [1,32]", knn);
   if (knn >= ix.n) return fail(h, AICP_B200_ERR_KNN_TOO_LARGE, "k-NN search: knn %d >= %d points", knn, ix.n);
   if (q1 < 0) q1 = ix.n;
@@ -476,10 +487,10 @@ int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q
   const int nq = q1 - q0;
   // Two schedules of the same exact search (identical output): the tile kernel executes ~45 % fewer instructions and wins
   // whenever the GPU is full (batched registrations, large clouds); the warp-per-query kernel has twice as many, shorter
-  // warps and wins the latency of ONE lidar-sized cloud on an otherwise idle GPU.
-  const bool tile = h->knn_schedule == 2 || (h->knn_schedule == 0 && (h->batch_worker || nq >= (1 << 20)));
+  // warps and wins the latency of ONE lidar-sized cloud on an otherwise idle GPU.  A query list goes to the warp kernel.
+  const bool tile = !qlist && (h->knn_schedule == 2 || (h->knn_schedule == 0 && (h->batch_worker || nq >= (1 << 20))));
   if (!tile) {
-    k_knn_warp<<<(unsigned)((nq + KNN_WARPS * KNN_RUN - 1) / (KNN_WARPS * KNN_RUN)), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig, q0, q1);
+    k_knn_warp<<<(unsigned)((nq + KNN_WARPS * KNN_RUN - 1) / (KNN_WARPS * KNN_RUN)), 32 * KNN_WARPS, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, knn_out_orig, q0, q1, qlist);
   } else {
     const size_t smem = ((size_t)knn * 32 * 12 + 512 + AICP_STACK * 4) * TILE_WARPS;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -492,13 +503,15 @@ int run_knn(Handle* h, const SpatialIndex& ix, int knn, int* knn_out_orig, int q
 }
 
 // [q0, q1): the Morton positions whose normals are computed (q1 < 0: all) -- a sharded registration gives every rank one
-// slice of the replicated reference and all-gathers the results (icp.cu); q0 must be a multiple of 32
-int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig, int q0, int q1) {
+// slice of the replicated reference and all-gathers the results (icp.cu); q0 must be a multiple of 32.  qlist: [q0, q1) are
+// entries of a list of positions instead.  rk2 (nullable): per-point squared distance to the last neighbour of the list.
+int run_surface_normals(Handle* h, const SpatialIndex& ix, int knn, float4* normals_morton, int* knn_out_orig, int q0, int q1,
+                        const int* qlist, float* rk2) {
   if (q1 < 0) q1 = ix.n;
-  int rc = run_knn(h, ix, knn, knn_out_orig, q0, q1);
+  int rc = run_knn(h, ix, knn, knn_out_orig, q0, q1, qlist);
   if (rc) return rc;
   if (q0 >= q1) return AICP_B200_OK;
-  k_normals_from_knn<<<(q1 - q0 + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton, q0, q1);
+  k_normals_from_knn<<<(q1 - q0 + 127) / 128, 128, 0, h->stream>>>(ix.view(), knn, h->knn_pos.p, normals_morton, q0, q1, qlist, rk2);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return AICP_B200_OK;

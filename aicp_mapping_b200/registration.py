@@ -182,6 +182,14 @@ class B200Registration:
         p, n, keep = capi.ptr_and_count(cloud_ref)
         self._check(self._lib.aicp_b200_set_reference(self._h, p, n))
 
+    def appendToReference(self, cloud):
+        """aicp_b200_reference_append: merge `cloud` into the reference in place (incremental index + normals update).
+        Returns capi.AppendInfo (n_total, n_recomputed, incremental, ms)."""
+        p, n, keep = capi.ptr_and_count(cloud)
+        info = capi.AppendInfo()
+        self._check(self._lib.aicp_b200_reference_append(self._h, p, n, C.byref(info)))
+        return info
+
     def registerToReference(self, cloud_read, init_T=None):
         p, n, keep = capi.ptr_and_count(cloud_read)
         T = np.zeros(16, dtype=np.float32)

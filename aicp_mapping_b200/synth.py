@@ -115,6 +115,8 @@ def _raycast(origin, dirs, boxes, max_range, ground_z=0.0, chunk=65536):
     with np.errstate(divide="ignore", invalid="ignore"):
         tg = np.where(dz < -1e-12, (ground_z - origin[2]) / dz, np.inf)
     t = np.minimum(t, np.where(tg > 0, tg, np.inf))
+    if len(boxes) > 200:
+        return _raycast_culled(origin, dirs, boxes, max_range, t)
     lo, hi = boxes[:, :3][None], boxes[:, 3:][None]
     for s in range(0, R, chunk):
         d = dirs[s:s + chunk]
@@ -127,6 +129,48 @@ def _raycast(origin, dirs, boxes, max_range, ground_z=0.0, chunk=65536):
         hit = tf >= np.maximum(tn, 0.0)
         tb = np.where(hit, np.where(tn > 1e-9, tn, tf), np.inf)
         t[s:s + chunk] = np.minimum(t[s:s + chunk], tb.min(axis=1))
+    t[t > max_range] = np.inf
+    return t
+
+
+def _raycast_culled(origin, dirs, boxes, max_range, t):
+    """The same slab test for scenes with many boxes: every box is tested only against the rays whose azimuth falls inside
+    the azimuth interval its footprint subtends from the sensor (a superset of the rays that can hit it; per ray and box the
+    arithmetic is that of _raycast, and a minimum does not depend on the order of its arguments)."""
+    phi = np.arctan2(dirs[:, 1], dirs[:, 0])
+    order = np.argsort(phi, kind="stable")
+    phis = phi[order]
+    ds = dirs[order]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / ds
+    ts = t[order]
+    for b in boxes:
+        if b[0] <= origin[0] <= b[3] and b[1] <= origin[1] <= b[4]:
+            sl = [slice(0, len(phis))]                                          # the sensor stands inside the footprint
+        else:
+            cx = np.array([b[0], b[0], b[3], b[3]]) - origin[0]
+            cy = np.array([b[1], b[4], b[1], b[4]]) - origin[1]
+            a = np.arctan2(cy, cx)
+            mid = np.arctan2(0.5 * (b[1] + b[4]) - origin[1], 0.5 * (b[0] + b[3]) - origin[0])
+            rel = (a - mid + np.pi) % (2 * np.pi) - np.pi                      # corners relative to the centre direction
+            lo_a, hi_a = mid + rel.min() - 1e-6, mid + rel.max() + 1e-6
+            if lo_a < -np.pi:
+                sl = [slice(np.searchsorted(phis, lo_a + 2 * np.pi), len(phis)), slice(0, np.searchsorted(phis, hi_a, side="right"))]
+            elif hi_a > np.pi:
+                sl = [slice(np.searchsorted(phis, lo_a), len(phis)), slice(0, np.searchsorted(phis, hi_a - 2 * np.pi, side="right"))]
+            else:
+                sl = [slice(np.searchsorted(phis, lo_a), np.searchsorted(phis, hi_a, side="right"))]
+        for q in sl:
+            if q.stop <= q.start:
+                continue
+            t1 = (b[:3] - origin) * inv[q]
+            t2 = (b[3:] - origin) * inv[q]
+            tn = np.nanmax(np.minimum(t1, t2), axis=1)
+            tf = np.nanmin(np.maximum(t1, t2), axis=1)
+            hit = tf >= np.maximum(tn, 0.0)
+            tb = np.where(hit, np.where(tn > 1e-9, tn, tf), np.inf)
+            ts[q] = np.minimum(ts[q], tb)
+    t[order] = ts
     t[t > max_range] = np.inf
     return t
 
@@ -165,8 +209,10 @@ def _prior_error(rng):
     return rigid(t[0], t[1], t[2], roll, pitch, yaw)
 
 
-def campus_map(n_points, rng, lx=200.0, ly=200.0, lz=12.0, n_boxes=120):
-    """C4 map: surfaces of a lx x ly ground plane and n_boxes buildings, area-uniformly sampled.  Returns (xyz, boxes)."""
+def campus_map(n_points, rng, lx=200.0, ly=200.0, lz=12.0, n_boxes=120, n_clutter=0):
+    """C4 map: surfaces of a lx x ly ground plane and n_boxes buildings, area-uniformly sampled.  Returns (xyz, boxes).
+    n_clutter: that many small boxes (cars, kiosks, bollards: 0.4 - 3 m) on top -- faces in every direction close to the lane,
+    so that also the better half of the matches, which is all a trimmed ratio of 0.5 keeps, constrains the pose."""
     boxes = []
     for _ in range(n_boxes):
         while True:
@@ -174,6 +220,13 @@ def campus_map(n_points, rng, lx=200.0, ly=200.0, lz=12.0, n_boxes=120):
             if abs(cy) > 6.0:                          # free boulevard along x
                 break
         sx, sy, sz = rng.uniform(3, 16), rng.uniform(3, 16), rng.uniform(2.5, lz)
+        boxes.append([cx - sx / 2, cy - sy / 2, 0.0, cx + sx / 2, cy + sy / 2, sz])
+    for _ in range(n_clutter):
+        while True:
+            cx, cy = rng.uniform(-lx / 2 + 2, lx / 2 - 2), rng.uniform(-ly / 2 + 2, ly / 2 - 2)
+            if abs(cy) > 2.5:                          # the lane itself stays free
+                break
+        sx, sy, sz = rng.uniform(0.4, 3.0), rng.uniform(0.4, 3.0), rng.uniform(0.8, 3.0)
         boxes.append([cx - sx / 2, cy - sy / 2, 0.0, cx + sx / 2, cy + sy / 2, sz])
     boxes = np.array(boxes, dtype=np.float64)
     # faces: ground + 5 visible faces per box
@@ -299,12 +352,12 @@ def raw_sweep(config, trial=0, n_sweeps=None):
     raise ValueError("raw_sweep supports configs 2 and 3")
 
 
-def make_map_case(n_map=10485760, n_read=122880, trial=0, n_poses=1, remove_ground=False):
+def make_map_case(n_map=10485760, n_read=122880, trial=0, n_poses=1, remove_ground=False, n_clutter=0):
     """C4: fixed map + reading(s) scanned inside it with the HDL-64 model, expressed through an erroneous prior.
     remove_ground: drop the ground hits of the reading (z < 0.2 m) as the KITTI tools do before registration; with the
     ground in, the trimmed half of the matches is almost all ground and the pose is not constrained along it."""
     rng = np.random.default_rng(1000 * 4 + trial)
-    map_xyz, boxes = campus_map(n_map, rng)
+    map_xyz, boxes = campus_map(n_map, rng, n_clutter=n_clutter)
     out = []
     for _ in range(n_poses):
         pose = rigid(rng.uniform(-60, 60), rng.uniform(-3, 3), 1.73, 0, 0, rng.uniform(-np.pi, np.pi))

@@ -111,6 +111,13 @@ typedef struct {
   float   ms_total;               /* device time of the call (CUDA events) */
 } aicp_b200_prefilter_info;
 
+typedef struct {
+  int64_t n_total;                /* reference points after the append */
+  int64_t n_recomputed;           /* points whose k-NN list and normal were recomputed (the new ones + the old ones they changed) */
+  int32_t incremental;            /* 1: merged into the live index; 0: outside the old bounding box, full rebuild at the next call */
+  float   ms;                     /* device time of the incremental update (CUDA events) */
+} aicp_b200_append_info;
+
 /* ---- lifetime --------------------------------------------------------------------------------------------------
  * replaces: aicp::create_registrator(params) / PointmatcherRegistration(params)
  *           aicp_core/include/aicp_registration/registration.hpp:9-19, pointmatcher_registration.cpp:7-9
@@ -156,6 +163,14 @@ int aicp_b200_register_to_reference(aicp_b200_handle* h, const float* read_xyzw,
 
 /* replaces: getOutputReading(out)        pointmatcher_registration.hpp:48-50  (T * reading, unfiltered)
  *           getInitializedReading(out)   pointmatcher_registration.hpp:37-46  (init_T * reading) */
+/* replaces: merging an aligned cloud into the reference map between registrations (App::runAicpPipeline's map update,
+ * aicp_core/src/registration/app.cpp:476-493, and AlignedCloud merging) for a reference that stays on the GPU.  Appends n
+ * points to the reference of aicp_b200_set_reference / aicp_b200_register_to_reference and updates the index and the
+ * normals IN PLACE: the state afterwards is bit for bit what set_reference(old + new) and a full rebuild give, but only the
+ * new points are sorted and only the neighbourhoods they enter are recomputed (csrc/append.cu).  A cloud that reaches
+ * outside the old bounding box falls back to the full rebuild (info->incremental = 0).  Needs a reference that has been
+ * registered against at least once; not available on a handle with a communicator.  info: nullable. */
+int aicp_b200_reference_append(aicp_b200_handle* h, const float* xyzw, int64_t n, aicp_b200_append_info* info);
 int aicp_b200_get_output_reading(aicp_b200_handle* h, float* xyzw, int64_t n);
 int aicp_b200_get_initialized_reading(aicp_b200_handle* h, float* xyzw, int64_t n);
 

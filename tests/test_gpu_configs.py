@@ -47,7 +47,10 @@ def test_c4_reduced_map_parity_with_oracle(reg, orc):
 
 def test_c4_full_size_map_properties(reg, orc):
     """BASELINE config 4 at full size: 122 880-point reading against a 10 485 760-point map."""
-    case = synth.make_map_case(n_map=10_485_760, n_read=122_880, trial=0, n_poses=1)
+    # the campus WITH street clutter (1500 small boxes): with buildings and ground alone the better half of the matches -- all a
+    # trimmed ratio of 0.5 keeps -- lies on surfaces parallel to the boulevard and the registration slides along it by
+    # decimetres, in the oracle exactly as on the GPU (round 1 accepted < 1 m here)
+    case = synth.make_map_case(n_map=10_485_760, n_read=122_880, trial=0, n_poses=1, n_clutter=1500)
     mp, rd = case["map"], case["readings"][0]
     # (1) exact NN on the full map, ALL 122 880 queries: indices and squared distances bit for bit against the oracle's
     #     kd-tree search (5 s on 8 cores), which is itself pinned by a float32 brute force with the oracle's operation order
@@ -61,8 +64,8 @@ def test_c4_full_size_map_properties(reg, orc):
         dd = (df[:, 0] * df[:, 0] + df[:, 1] * df[:, 1]) + df[:, 2] * df[:, 2]
         j = int(np.argmin(dd))                       # first minimum == lowest index on ties
         assert o_idx[k] == j and np.float32(o_d2[k]) == dd[j]
-    # (2) localisation lowers the trimmed point-to-map objective (the campus map is sampled on every face, visible or
-    #     not, and is weakly constrained along the boulevard, so the pose error itself is only bounded loosely)
+    # (2) localisation lowers the trimmed point-to-map objective and RECOVERS THE TRUE POSE: the injected prior error
+    #     (decimetres, degrees) is undone to within 5 cm / 0.01 rad of the noisy map
     reg.setConfig(ratio=0.5, max_iterations=20)
     reg.setReference(mp)
     T = reg.registerToReference(rd["read"])
@@ -76,7 +79,7 @@ def test_c4_full_size_map_properties(reg, orc):
     before, after = trimmed(rd["read"]), trimmed(aligned)
     assert after < 0.5 * before, (before, after)
     d = T.astype(np.float64) @ np.linalg.inv(rd["T_true"])
-    assert np.linalg.norm(d[:3, 3]) < 1.0 and rot_angle(d[:3, :3]) < 0.05
+    assert np.linalg.norm(d[:3, 3]) < 0.05 and rot_angle(d[:3, :3]) < 0.01, (np.linalg.norm(d[:3, 3]), rot_angle(d[:3, :3]))
     reg.setReference(mp)                                   # reg.match used the scratch index; the map index is kept
     T = reg.registerToReference(rd["read"])
     # (3) deterministic and reference reuse is stateless: the same call again gives the same bits

@@ -263,7 +263,7 @@ def main():
         al.close()
     if "4" in want:
         t0 = time.perf_counter()
-        case = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=8)
+        case = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=8, n_clutter=1500)
         gen_s = time.perf_counter() - t0
         mp = dev(case["map"])
         reads = [dev(r["read"]) for r in case["readings"]]
@@ -297,7 +297,7 @@ def main():
     if "4crop" in want:
         # the way App does it (app.cpp:41-69): crop the whole map to +-15 m around the prior pose, register against the crop
         from aicp_mapping_b200 import filtering
-        case = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=4)
+        case = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=4, n_clutter=1500)
         mp = dev(case["map"])
         crop = ab.B200CropBox(device=0)
         reg.setConfig(ratio=0.5, max_iterations=20)
