@@ -606,7 +606,7 @@ __device__ __forceinline__ void acc_point_terms(bool in, const float4& r, const 
 #define ACC_SLOTS 64          // partial-sum slots: block b adds into slot b % ACC_SLOTS, the last block folds the slots
 #define ACC_PTS 2             // reading points per thread
 
-__global__ void __launch_bounds__(256, 4) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
+__global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict__ refc, const float4* __restrict__ normals,
                                                     const float4* __restrict__ read0, const int* __restrict__ match_pos,
                                                     const float* __restrict__ d2, int n, DeviceState* st, LoopParams lp, int tail,
                                                     volatile int* progress, unsigned long long* slots) {

@@ -516,7 +516,7 @@ def sharded_leg(args, rank, world, local_rank, dist, dev, pairs, ratios):
                     "n_reference": int(ref_dev.shape[0]), "n_reading": int(read_dev.shape[0])}
 
         out["c3"] = case(dev[0][0], dev[0][1], ratios[0], False)
-        mp_ = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=0, n_poses=1, n_clutter=1500)
+        mp_ = synth.make_map_case(n_map=args.map_points, n_read=122880, trial=1, n_poses=1, n_clutter=1500)
         map_dev = torch.from_numpy(capi.to_xyzw(mp_["map"])).cuda()
         read_dev = torch.from_numpy(capi.to_xyzw(mp_["readings"][0]["read"])).cuda()
         out["c4"] = case(map_dev, read_dev, ab.autotune_ratio(50.0), True)      # app.cpp:123-127: overlap forced to 50 % against a prior map
