@@ -118,6 +118,7 @@ int aicp_b200_create(const char* icp_yaml_path, int device, aicp_b200_handle** o
   }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&nh->ev[i]);
   if (const char* e = getenv("AICP_B200_CROP")) nh->crop_legacy = strcmp(e, "legacy") == 0;
+  if (const char* e = getenv("AICP_B200_FUSED_TAIL")) nh->fused_tail = atoi(e) != 0;
   if (const char* e = getenv("AICP_B200_SPREAD")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nh->loop_spread = v; }
   (void)h;
   *out = reinterpret_cast<aicp_b200_handle*>(nh);

@@ -104,6 +104,7 @@ struct Handle {
   bool batch_worker = false;     // this handle is one of the concurrent workers of aicp_b200_register_batch
   int batch_streams = 1;         // how many such workers share the GPU (the persistent loop kernel takes 1 / batch_streams of its blocks)
   int loop_schedule = 0;         // ICP loop: 0 auto, 1 three launches per iteration + host look-ahead, 2 one persistent cooperative kernel
+  bool fused_tail = true;        // multi-launch loop: k_quantile_accumulate instead of k_select23 + k_accumulate (AICP_B200_FUSED_TAIL=0: off)
   int loop_spread = 0;           // experiments (AICP_B200_SPREAD): lanes per query in the search phase of the loop kernel, 0 = automatic
   int loop_occ[2] = {0, 0};      // co-resident blocks per SM of k_icp_loop<false / true>
   int n_sm = 0;

@@ -999,6 +999,65 @@ struct LoopArgs {
   int spread;                    // search phase: one query per `spread` lanes (1, 2, 4, 8), see launch_loop
 };
 
+// phase 2 of an iteration: the d2 keys whose first digit is the picked one are appended to the candidate list
+__device__ __forceinline__ void loop_candidates(const LoopArgs& a, int Q, int n_tiles) {
+  DeviceState* st = a.st;
+  const int tid = threadIdx.x, lane = tid & 31, n = a.n;
+  const unsigned int prefix = __ldcg(&st->prefix);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int i = tid < Q ? t * Q + tid : n;
+    unsigned int key = 0;
+    bool hit = false;
+    if (i < n) {
+      const float d = __ldcg(&a.d2[i]);
+      key = __float_as_uint(d);
+      hit = d2_valid(d) && (key >> 20) == prefix;
+    }
+    const unsigned int m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned int off = 0;
+      if (lane == leader) off = atomicAdd(&st->cand_n, (unsigned)__popc(m));
+      off = __shfl_sync(0xFFFFFFFFu, off, leader);
+      if (hit) a.cand[off + __popc(m & ((1u << lane) - 1u))] = key;
+    }
+  }
+}
+
+// phase 3 of an iteration: exact fixed-point normal equations of the inliers (d2 <= limit) into the 128-bit slots
+__device__ __forceinline__ void loop_accumulate(const LoopArgs& a, int Q, int n_tiles, const float* sT, long long (*s_hi)[32]) {
+  DeviceState* st = a.st;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, n = a.n;
+  const float limit = __ldcg(&st->limit);
+  long long acc = 0;
+  int held = 0;                                  // tiles folded into acc since the last flush
+  auto flush = [&] {
+    // |term| < 2^52.6 and at most 4 tiles (1024 points) per flush: the block total fits in 64 bits; the slots are 128-bit
+    s_hi[w][lane] = acc;
+    __syncthreads();
+    if (w == 0) {
+      long long tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += s_hi[k][lane];
+      unsigned long long* slot = a.slots + ((size_t)(blockIdx.x % ACC_SLOTS) * 32 + lane) * 2;
+      if (lane < AICP_NSUM && tot != 0) atomic_add_128(slot, (long long*)(slot + 1), tot);
+    }
+    __syncthreads();
+    acc = 0; held = 0;
+  };
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int i = tid < Q ? t * Q + tid : n;
+    bool in = false;
+    int pos = 0;
+    if (i < n) { in = __ldcg(&a.d2[i]) <= limit; pos = __ldcg(&a.match_pos[i]); }      // TrimmedDist weight (A.4); false for NaN
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f), q = r, nr = r;
+    if (in) { r = __ldg(&a.read0[i]); q = __ldg(&a.ix.pts[pos]); nr = __ldg(&a.normals[pos]); }
+    acc_point_terms(in, r, q, nr, sT, lane, acc);
+    if (++held == 4) flush();
+  }
+  if (held) flush();
+}
+
 template <bool TILE>
 __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ LoopArgs a) {
   __shared__ unsigned int sh[AICP_HIST_BINS];
@@ -1042,27 +1101,7 @@ __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ Loo
     });
     if (ld_int(&st->done)) break;
     // ---- phase 2: candidate keys of the picked bin -> digits 2 and 3
-    {
-      const unsigned int prefix = __ldcg(&st->prefix);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int i = tid < Q ? t * Q + tid : n;
-        unsigned int key = 0;
-        bool hit = false;
-        if (i < n) {
-          const float d = __ldcg(&a.d2[i]);
-          key = __float_as_uint(d);
-          hit = d2_valid(d) && (key >> 20) == prefix;
-        }
-        const unsigned int m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (m) {
-          const int leader = __ffs(m) - 1;
-          unsigned int off = 0;
-          if (lane == leader) off = atomicAdd(&st->cand_n, (unsigned)__popc(m));
-          off = __shfl_sync(0xFFFFFFFFu, off, leader);
-          if (hit) a.cand[off + __popc(m & ((1u << lane) - 1u))] = key;
-        }
-      }
-    }
+    loop_candidates(a, Q, n_tiles);
     grid_serial(st, epoch, [&] {
       const unsigned long long t0 = global_ns();
       loop_select23(st, a.cand, sh, pv, it);
@@ -1070,42 +1109,59 @@ __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ Loo
     });
     if (ld_int(&st->done)) break;
     // ---- phase 3: normal equations of the inliers (d2 <= limit), exact fixed point
-    {
-      const float limit = __ldcg(&st->limit);
-      long long acc = 0;
-      int held = 0;                                  // tiles folded into acc since the last flush
-      auto flush = [&] {
-        // |term| < 2^52.6 and at most 4 tiles (1024 points) per flush: the block total fits in 64 bits; the slots are 128-bit
-        s_hi[w][lane] = acc;
-        __syncthreads();
-        if (w == 0) {
-          long long tot = 0;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) tot += s_hi[k][lane];
-          unsigned long long* slot = a.slots + ((size_t)(blockIdx.x % ACC_SLOTS) * 32 + lane) * 2;
-          if (lane < AICP_NSUM && tot != 0) atomic_add_128(slot, (long long*)(slot + 1), tot);
-        }
-        __syncthreads();
-        acc = 0; held = 0;
-      };
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int i = tid < Q ? t * Q + tid : n;
-        bool in = false;
-        int pos = 0;
-        if (i < n) { in = __ldcg(&a.d2[i]) <= limit; pos = __ldcg(&a.match_pos[i]); }      // TrimmedDist weight (A.4); false for NaN
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f), q = r, nr = r;
-        if (in) { r = __ldg(&a.read0[i]); q = __ldg(&a.ix.pts[pos]); nr = __ldg(&a.normals[pos]); }
-        acc_point_terms(in, r, q, nr, sT, lane, acc);
-        if (++held == 4) flush();
-      }
-      if (held) flush();
-    }
+    loop_accumulate(a, Q, n_tiles, sT, s_hi);
     grid_serial(st, epoch, [&] {
       const unsigned long long t0 = global_ns();
       loop_fold_solve(st, a.slots, a.lp, n, pv, it, s_lo, s_hi);
       if (tid == 0) { const unsigned long long t1 = global_ns(); st->tail_ns[2] += t1 - t0; st->phase_ns[2] += t1 - st->t_mark; st->t_mark = t1; }
     });
     if (ld_int(&st->done)) break;
+  }
+}
+
+// The multi-launch loop (batch workers) after k_match*: digits 2 + 3 of the trimmed quantile AND the normal equations +
+// solve in ONE small cooperative launch -- candidates -> grid barrier whose serial section finishes the radix select ->
+// exact sums -> the last block folds and solves.  Replaces k_select23 + k_accumulate (two launches, each costing ~45 us of
+// queueing while eight registrations share the GPU).  `seq` (iteration + 1) is what the barrier's release word counts up to.
+__global__ void __launch_bounds__(256, 4) k_quantile_accumulate(const __grid_constant__ LoopArgs a, unsigned int seq, int tail,
+                                                                volatile int* progress) {
+  DeviceState* st = a.st;
+  if (ld_int(&st->done)) { publish_done(progress); return; }
+  __shared__ unsigned int sh[AICP_HIST_BINS];
+  __shared__ float sT[16];
+  __shared__ unsigned long long s_lo[8][32];
+  __shared__ long long s_hi[8][32];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int n_tiles = (a.n + 255) / 256;
+  if (tid < 16) sT[tid] = st->T_iter[tid];
+  loop_candidates(a, 256, n_tiles);
+  // grid barrier with a serial section (see grid_serial); the arrival counter is re-armed by the block that runs the section
+  __syncthreads();
+  if (tid == 0) s_last = atom_add_release_gpu_u32(&st->bar_arrive, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const unsigned long long t0 = global_ns();
+    loop_select23(st, a.cand, sh, a.pv, 0);
+    if (tid == 0) { st->tail_ns[1] += global_ns() - t0; st->bar_arrive = 0u; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu_u32(&st->bar_release, seq);
+  } else if (tid == 0) {
+    while (ld_relaxed_gpu_u32(&st->bar_release) < seq) {}
+    __threadfence();
+  }
+  __syncthreads();
+  loop_accumulate(a, 256, n_tiles, sT, s_hi);
+  if (!block_is_last(&st->ticket[2])) return;
+  const unsigned long long t0 = global_ns();
+  if (tail) {
+    loop_fold_solve(st, a.slots, a.lp, a.n, a.pv, 0, s_lo, s_hi);
+    if (tid == 0) {
+      st->tail_ns[2] += global_ns() - t0;
+      publish_progress(progress, st->iter, *(volatile int*)&st->done);
+    }
   }
 }
 
@@ -1422,11 +1478,24 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
       else
         k_match_tile<<<blocks, 256, 0, s>>>(cix, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, trace_idx, cfg.ratio, 1, prog_dev);
       mark_match(4 + 4 * (size_t)it);
-      k_select23<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->cand.p, prog_dev);
-      mark(5 + 4 * (size_t)it);
-      k_accumulate<<<acc_blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1, prog_dev, h->acc_slots.p);
-      mark(6 + 4 * (size_t)it);
-      h->launches += 3;
+      if (h->fused_tail) {
+        // quantile digits 2 + 3, normal equations and solve in one cooperative launch (k_quantile_accumulate)
+        LoopArgs la{cix, h->normals.p, read_s, n_read, h->st, h->match_pos.p, h->d2.p, h->hist.p, h->cand.p, trace_idx, h->acc_slots.p, lp, pv, 1};
+        unsigned int seq = (unsigned int)it + 1u;
+        int one = 1;
+        void* params[] = {&la, &seq, &one, &prog_dev};
+        int qgrid = blocks < 74 ? blocks : 74;
+        mark(5 + 4 * (size_t)it);
+        CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_quantile_accumulate, dim3((unsigned)qgrid), dim3(256), params, 0, s));
+        mark(6 + 4 * (size_t)it);
+        h->launches += 2;
+      } else {
+        k_select23<<<sel_blocks, 256, 0, s>>>(h->d2.p, n_read, h->st, h->cand.p, prog_dev);
+        mark(5 + 4 * (size_t)it);
+        k_accumulate<<<acc_blocks, 256, 0, s>>>(h->refc_pts.p, h->normals.p, read_s, h->match_pos.p, h->d2.p, n_read, h->st, lp, 1, prog_dev, h->acc_slots.p);
+        mark(6 + 4 * (size_t)it);
+        h->launches += 3;
+      }
     } else {
       // reading sharded over the ranks: the trimmed quantile is GLOBAL, so each radix-select digit is
       // picked from the all-reduced histogram; then the 27 normal-equation partials (+ count) are all-reduced

@@ -200,7 +200,7 @@ def test_icp_parity_c2_vlp16(reg, orc, pair_cache, match_schedule, knn_schedule,
 
 def test_loop_schedules_agree_and_persistent_is_one_launch(reg, pair_cache):
     """The persistent loop kernel and the multi-launch loop give the same bits; the persistent one costs one launch for all
-    iterations (the multi-launch loop: three per iteration), and fills the per-phase clocks of the stats."""
+    iterations (the multi-launch loop: two per iteration), and fills the per-phase clocks of the stats."""
     pair = pair_cache(2, 0)
     reg.setConfig(ratio=0.7)
     out = {}
@@ -210,7 +210,7 @@ def test_loop_schedules_agree_and_persistent_is_one_launch(reg, pair_cache):
         out[ls] = (u32(T).copy(), reg.stats.iterations, reg.stats.gpu_launches, reg.stats.ms_match, u32(reg.getOutputReading()).copy())
     reg.setLoopSchedule(0)
     assert np.array_equal(out[2][0], out[1][0]) and out[2][1] == out[1][1] and np.array_equal(out[2][4], out[1][4])
-    assert out[1][2] - out[2][2] >= 3 * out[2][1] - 1
+    assert out[1][2] - out[2][2] >= 2 * out[2][1] - 1        # multi-launch: search + (quantile, normal equations, solve) per iteration
     assert out[2][3] > 0.0
 
 
