@@ -167,6 +167,10 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);
   for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_init) cudaEventDestroy(h->ev_init);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -56,6 +56,8 @@ struct Handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t side = nullptr;   // reading-side setup of a single registration runs here, beside the reference's normals
+  cudaEvent_t ev_fork = nullptr, ev_init = nullptr, ev_join = nullptr;
   aicp_b200_icp_config cfg;
   std::string cfg_path;
   bool cfg_from_file = false;
@@ -170,7 +172,7 @@ struct Handle {
 
 // ---- index.cu
 // with_tree = false: Morton order only (pts), no radix tree -- enough to make the queries of a warp spatially coherent
-int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n, bool with_tree = true);
+int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n, bool with_tree = true, cudaEvent_t after_stats = nullptr);
 int build_tree(Handle* h, SpatialIndex& ix, int n);     // radix tree + boxes over ix.keys / ix.pts (already Morton-ordered)
 void launch_index_stats(Handle* h, const float4* pts, int n, IndexMeta* m);
 void launch_morton_keys(Handle* h, const SpatialIndex& ix, const float4* pts, int n, unsigned int* keys, unsigned int* vals, unsigned int first_index);

@@ -23,6 +23,10 @@
 #include "detmath.cuh"
 #include "handle.cuh"
 
+#ifndef AICP_SIDE_STREAM
+#define AICP_SIDE_STREAM 1      // 0: reading-side setup behind the reference's (A/B builds)
+#endif
+
 namespace aicp {
 
 __device__ __forceinline__ int ld_int(const int* p) { return *(const volatile int*)p; }
@@ -486,14 +490,12 @@ __device__ __forceinline__ void atomic_add_128(unsigned long long* lo, long long
 
 // A.5 solve + pose update, A.7 checkers.  Called by ALL 32 lanes of one warp: the sums are converted and the 6x6 system
 // solved cooperatively (det_solve6_warp), the pose update and the checkers -- short scalar chains -- run in lane 0.
-__device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read) {
+// lane s < 28 passes sum s as (lo, hi)
+__device__ __noinline__ void solve_and_check(DeviceState* st, const LoopParams lp, int n_read, unsigned long long lo, long long hi) {
   const int lane = threadIdx.x & 31;
   double v = 0.0;
   long long n_used = 0;
   if (lane < AICP_NSUM) {
-    const unsigned long long lo = __ldcg(&st->sum_lo[lane]);
-    const long long hi = __ldcg(&st->sum_hi[lane]);
-    st->sum_lo[lane] = 0; st->sum_hi[lane] = 0;
     v = fixed128_to_double(hi, lo);
     n_used = (long long)lo;
   }
@@ -682,7 +684,11 @@ __global__ void __launch_bounds__(256, 2) k_accumulate(const float4* __restrict_
   __threadfence();
   __syncthreads();
   if (tail && threadIdx.x < 32) {
-    solve_and_check(st, lp, n);
+    const bool has = lane < AICP_NSUM;
+    const unsigned long long slo = has ? __ldcg(&st->sum_lo[lane]) : 0ull;
+    const long long shi = has ? __ldcg(&st->sum_hi[lane]) : 0ll;
+    if (has) { st->sum_lo[lane] = 0; st->sum_hi[lane] = 0; }
+    solve_and_check(st, lp, n, slo, shi);
     if (threadIdx.x == 0) {
       st->tail_ns[2] += global_ns() - t0;
       publish_progress(progress, st->iter, *(volatile int*)&st->done);
@@ -976,10 +982,8 @@ __device__ void loop_fold_solve(DeviceState* st, unsigned long long* slots, cons
     }
     peer_verdict(st, bad, t0);
   }
-  if (w == 0 && lane < AICP_NSUM) { st->sum_lo[lane] = lo; st->sum_hi[lane] = hi; }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x < 32 && !ld_int(&st->done)) solve_and_check(st, lp, n);
+  // the sums go from the fold to the solve in registers (lane s of warp 0 holds sum s)
+  if (w == 0 && !ld_int(&st->done)) solve_and_check(st, lp, n, lo, hi);
 }
 
 struct LoopArgs {
@@ -1202,7 +1206,11 @@ __global__ void k_limbs_solve(DeviceState* st, const unsigned long long* limbs, 
     }
     __threadfence();
     __syncwarp();
-    solve_and_check(st, lp, n);
+    const bool has = lane < AICP_NSUM;
+    const unsigned long long slo = has ? __ldcg(&st->sum_lo[lane]) : 0ull;
+    const long long shi = has ? __ldcg(&st->sum_hi[lane]) : 0ll;
+    if (has) { st->sum_lo[lane] = 0; st->sum_hi[lane] = 0; }
+    solve_and_check(st, lp, n, slo, shi);
   }
   __syncwarp();
   if (lane != 0) return;
@@ -1346,9 +1354,20 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   CUDA_TRY(cudaEventRecord(h->ev[0], s));
   mark(0);
 
+  // One registration at a time: the reading-side setup (T_refMean_dataIn * reading, Morton sort of the reading) only needs
+  // the reference's centroid, which the first kernel of its index build delivers -- it runs on a side stream beside the
+  // reference's tree and SurfaceNormal filter instead of behind them (~50 us of a 1.27 ms registration).  Batch workers
+  // share the GPU with seven other registrations and gain nothing from it.
+  const bool fork = rebuild_reference && !h->batch_worker && !cfg.reading_normals && AICP_SIDE_STREAM;
+  if (fork && !h->side) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_init, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   if (rebuild_reference) {
     h->ref_ready = false;
-    rc = build_index(h, h->ref_ix, h->ref_in.p, n_ref);
+    rc = build_index(h, h->ref_ix, h->ref_in.p, n_ref, true, fork ? h->ev_fork : nullptr);
     if (rc) return rc;
     mark(1);
     CUDA_TRY(h->refc_pts.reserve((size_t)h->ref_ix.n));
@@ -1386,12 +1405,18 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     rc = run_surface_normals(h, h->tmp_ix, cfg.knn_normals, h->tmp_a.p, nullptr);
     if (rc) return rc;
   }
+  cudaStream_t rs = fork ? h->side : s;                   // the stream of the reading-side setup
+  if (fork) CUDA_TRY(cudaStreamWaitEvent(rs, h->ev_fork, 0));
   if (init_T_host) {
     memcpy(h->st_host->T_init, init_T_host, 16 * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(h->st->T_init, h->st_host->T_init, 16 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->st->T_init, h->st_host->T_init, 16 * sizeof(float), cudaMemcpyHostToDevice, rs));
   }
   CUDA_TRY(cudaMemsetAsync(h->hist.p, 0, sizeof(unsigned int) * AICP_HIST_BINS, s));
-  k_loop_init<<<1, 32, 0, s>>>(h->st, h->ref_ix.meta, (long long)n_ref, init_T_host ? 1 : 0);
+  k_loop_init<<<1, 32, 0, rs>>>(h->st, h->ref_ix.meta, (long long)n_ref, init_T_host ? 1 : 0);
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(h->ev_init, rs));
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_init, 0));      // k_centre reads the mean
+  }
   if (rebuild_reference || h->ref_recentre) {
     h->ref_recentre = false;
     int n4 = 4 * (h->ref_ix.n - 1);
@@ -1414,11 +1439,17 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
     h->trace_iters = cfg.max_iterations; h->trace_n = n_read;
   }
   const int blocks = (n_read + 255) / 256;
-  k_read_prepare<<<blocks, 256, 0, s>>>(h->read_in.p, n_read, h->st, h->read0.p, read_init);
+  k_read_prepare<<<blocks, 256, 0, rs>>>(h->read_in.p, n_read, h->st, h->read0.p, read_init);
   h->launches += 2;
   // Morton-order the reading so that the 32 queries of a warp walk the same part of the reference tree
+  h->stream = rs;                                           // build_index works on the handle's stream
   rc = build_index(h, h->read_ix, h->read0.p, n_read, false);
+  h->stream = s;
   if (rc) return rc;
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(h->ev_join, rs));
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+  }
   const float4* read_s = h->read_ix.pts.p;
   CUDA_TRY(cudaEventRecord(h->ev[1], s));
 

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) k_refit(const float4* __restrict__ pts, i
   }
 }
 
-int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64, bool with_tree) {
+int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64, bool with_tree, cudaEvent_t after_stats) {
   if (n64 < 1 || n64 > (1ll << 28)) return fail(h, AICP_B200_ERR_BAD_ARG, "cloud size %lld out of range [1, 2^28]", (long long)n64);
   int n = (int)n64;
   cudaStream_t s = h->stream;
@@ -329,6 +329,7 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
   int stat_blocks = blocks < 148 * 2 ? blocks : 148 * 2;
   k_index_stats<<<stat_blocks, 256, 0, s>>>(pts_dev, n, ix.meta);
   k_quant_params<<<1, 32, 0, s>>>(ix.meta);
+  if (after_stats) CUDA_TRY(cudaEventRecord(after_stats, s));      // bounding box and centroid sums are final: dependants may start
   k_morton_keys<<<blocks, 256, 0, s>>>(pts_dev, n, ix.meta, ix.keys.p, ix.vals.p, 0u);
   int rc = radix_sort_pairs(h, ix.keys.p, ix.vals.p, ix.keys_alt.p, ix.vals_alt.p, n, ix.sort_tmp);    // result in keys / vals
   if (rc) return rc;
