@@ -79,8 +79,8 @@ struct DeviceState {
 // the payload -- no fence on the sending side, no separate flag, one NVLink write latency per exchange (the first version
 // used plain stores + __threadfence_system + a flag + a fence after the flag: 16 us per exchange at 8 ranks).
 // Layout of an inbox, per SOURCE rank s (all 64-bit words):
-//   sums   @ SUMS_OFF + 1024 s         28 x 4 limbs of 32 bits, 2 words n_reading, word 127 = status of the source
-//   hist   @ HIST_OFF + (2048 + 8) 8 s 2048 digit-1 bins, then one status word
+//   sums   @ SUMS_OFF + 1024 s         word 32 k + l: limb k of sum l (l < 28), l = 28: points of the source's shard, l = 31: its status
+//   hist   @ HIST_OFF + (2048 + 8) 8 s word 256 j + t: bin 8 t + j (a warp stores 256 contiguous bytes), then one status word
 //   cand   @ CAND_OFF + stride s       header (count | status << 31), then the source's candidate keys (capacity cand_cap)
 #define AICP_MAX_RANKS 16
 #define AICP_INBOX_SUMS_OFF 0
