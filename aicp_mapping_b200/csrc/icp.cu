@@ -1005,32 +1005,40 @@ struct LoopArgs {
   int spread;                    // search phase: one query per `spread` lanes (1, 2, 4, 8), see launch_loop
 };
 
-// phase 2 of an iteration: the d2 keys whose first digit is the picked one are appended to the candidate list
+// phase 2 of an iteration: the d2 keys whose first digit is the picked one are appended to the candidate list.  A block that
+// owns several tiles (the 74-block launches of batch workers: 7 tiles each) reads four of them before it touches the first:
+// the phase is a chain of L2 round trips otherwise (57 us alone for 131 072 points, profiles/round2_g_ncu_table_batch_schedule.txt)
 __device__ __forceinline__ void loop_candidates(const LoopArgs& a, int Q, int n_tiles) {
   DeviceState* st = a.st;
   const int tid = threadIdx.x, lane = tid & 31, n = a.n;
   const unsigned int prefix = __ldcg(&st->prefix);
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int i = tid < Q ? t * Q + tid : n;
-    unsigned int key = 0;
-    bool hit = false;
-    if (i < n) {
-      const float d = __ldcg(&a.d2[i]);
-      key = __float_as_uint(d);
-      hit = d2_valid(d) && (key >> 20) == prefix;
+  for (int t0 = blockIdx.x; t0 < n_tiles; t0 += 4 * gridDim.x) {
+    float d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * gridDim.x;
+      const int i = (t < n_tiles && tid < Q) ? t * Q + tid : n;
+      d[u] = i < n ? __ldcg(&a.d2[i]) : __int_as_float(0x7FC00000);          // NaN: never a candidate
     }
-    const unsigned int m = __ballot_sync(0xFFFFFFFFu, hit);
-    if (m) {
-      const int leader = __ffs(m) - 1;
-      unsigned int off = 0;
-      if (lane == leader) off = atomicAdd(&st->cand_n, (unsigned)__popc(m));
-      off = __shfl_sync(0xFFFFFFFFu, off, leader);
-      if (hit) a.cand[off + __popc(m & ((1u << lane) - 1u))] = key;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u * (int)gridDim.x >= n_tiles) break;                          // block-uniform
+      const unsigned int key = __float_as_uint(d[u]);
+      const bool hit = d2_valid(d[u]) && (key >> 20) == prefix;
+      const unsigned int m = __ballot_sync(0xFFFFFFFFu, hit);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned int off = 0;
+        if (lane == leader) off = atomicAdd(&st->cand_n, (unsigned)__popc(m));
+        off = __shfl_sync(0xFFFFFFFFu, off, leader);
+        if (hit) a.cand[off + __popc(m & ((1u << lane) - 1u))] = key;
+      }
     }
   }
 }
 
-// phase 3 of an iteration: exact fixed-point normal equations of the inliers (d2 <= limit) into the 128-bit slots
+// phase 3 of an iteration: exact fixed-point normal equations of the inliers (d2 <= limit) into the 128-bit slots; two tiles
+// of a block are in flight at a time (their five loads per point each)
 __device__ __forceinline__ void loop_accumulate(const LoopArgs& a, int Q, int n_tiles, const float* sT, long long (*s_hi)[32]) {
   DeviceState* st = a.st;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, n = a.n;
@@ -1051,15 +1059,27 @@ __device__ __forceinline__ void loop_accumulate(const LoopArgs& a, int Q, int n_
     __syncthreads();
     acc = 0; held = 0;
   };
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int i = tid < Q ? t * Q + tid : n;
-    bool in = false;
-    int pos = 0;
-    if (i < n) { in = __ldcg(&a.d2[i]) <= limit; pos = __ldcg(&a.match_pos[i]); }      // TrimmedDist weight (A.4); false for NaN
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f), q = r, nr = r;
-    if (in) { r = __ldg(&a.read0[i]); q = __ldg(&a.ix.pts[pos]); nr = __ldg(&a.normals[pos]); }
-    acc_point_terms(in, r, q, nr, sT, lane, acc);
-    if (++held == 4) flush();
+  for (int t0 = blockIdx.x; t0 < n_tiles; t0 += 2 * gridDim.x) {
+    bool in[2]; int pos[2]; int idx[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * gridDim.x;
+      idx[u] = (t < n_tiles && tid < Q) ? t * Q + tid : n;
+      in[u] = false; pos[u] = 0;
+      if (idx[u] < n) { in[u] = __ldcg(&a.d2[idx[u]]) <= limit; pos[u] = __ldcg(&a.match_pos[idx[u]]); }   // TrimmedDist weight (A.4); false for NaN
+    }
+    float4 r[2], q[2], nr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      r[u] = q[u] = nr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in[u]) { r[u] = __ldg(&a.read0[idx[u]]); q[u] = __ldg(&a.ix.pts[pos[u]]); nr[u] = __ldg(&a.normals[pos[u]]); }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (t0 + u * (int)gridDim.x >= n_tiles) break;                          // block-uniform
+      acc_point_terms(in[u], r[u], q[u], nr[u], sT, lane, acc);
+      if (++held == 4) flush();
+    }
   }
   if (held) flush();
 }

@@ -15,7 +15,9 @@ reg.setConfig(ratio=0.5)
 reg.setProfiling(2)
 reg.setReference(mp)
 rd = case["readings"]
-T = reg.registerToReference(rd[0]["read"])
+T = reg.registerToReference(rd[0]["read"])          # first build: allocates
+reg.setReference(mp)
+T = reg.registerToReference(rd[0]["read"])          # the full rebuild an append replaces, buffers in place
 full_build_ms = reg.stats.ms_index + reg.stats.ms_normals
 out = []
 for k in range(3):
