@@ -20,3 +20,6 @@ try:
 except Exception as e:
     print("failed", e); print(open("$OUT/${TAG}_bench_n$N.log").read()[-3000:])
 PY
+if [ "${4:-0}" = "1" ]; then
+  timeout 900 python tools/bench_devices.py --pairs 64 --steps 5 > $OUT/${TAG}_devices_n$N.json 2>&1; echo "bench_devices rc=$?"; tail -1 $OUT/${TAG}_devices_n$N.json | cut -c1-400
+fi
