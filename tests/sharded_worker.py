@@ -1,9 +1,11 @@
 """Worker for the multi-rank tests (launched by torch.distributed.run).
 
-  --backend gloo : CPU restatement of the sharded-registration exchange protocol of csrc/comm.cu + icp.cu, built from the
-                   ORACLE's stage functions: each rank matches its shard, the three radix-select digit histograms and the
-                   32-bit limbs of the 128-bit normal-equation sums are all-reduced as integers, every rank solves.  Checks
-                   that the sharded trajectory equals the single-process oracle bit for bit.
+  --backend gloo : CPU restatement of the sharded-registration exchange protocols of csrc/comm.cu + icp.cu, built from the
+                   ORACLE's stage functions: each rank matches its shard; the trimmed quantile is found both ways -- three
+                   all-reduced radix-select digit histograms (NCCL carrier) and one histogram + an all-gather of the candidate
+                   keys of the picked bin (peer-memory carrier); the 32-bit limbs of the 128-bit normal-equation sums are
+                   summed as integers, every rank solves.  Checks that the sharded trajectory equals the single-process
+                   oracle bit for bit.
   --backend nccl : the real thing on GPUs: aicp_b200_comm_init + aicp_b200_register on each rank's shard, compared with the
                    unsharded registration on the same GPU.
 """
@@ -64,6 +66,23 @@ def run_gloo(args):
             prefix = (prefix << bits) | b
         limit = np.array([prefix], dtype=np.uint32).view(np.float32)[0]
         assert limit == full.trace[it]["limit_d2"] and n_valid == full.trace[it]["n_valid"]
+        # the peer-memory carrier's version of the same quantile (csrc/icp.cu, loop_pick / loop_select23): ONE histogram
+        # exchange (digit 1), then the candidate KEYS of the picked bin are all-gathered and digits 2 and 3 are finished over the
+        # gathered list by every rank
+        h1 = torch.from_numpy(np.bincount(key[valid] >> 20, minlength=2048).astype(np.int64))
+        dist.all_reduce(h1)
+        h1 = h1.numpy()
+        k1 = min(int(np.float32(int(h1.sum())) * ratio), int(h1.sum()) - 1)
+        b1, k1 = pick_digit(h1, k1)
+        mine = key[valid & ((key >> 20) == b1)]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine.tolist())
+        cand = np.array(sum(gathered, []), dtype=np.int64)
+        assert len(cand) == h1[b1]
+        b2, k2 = pick_digit(np.bincount((cand >> 9) & 2047, minlength=2048), k1)
+        p22 = (b1 << 11) | b2
+        b3, _ = pick_digit(np.bincount(cand[(cand >> 9) == p22] & 511, minlength=512), k2)
+        assert np.array([(p22 << 9) | b3], dtype=np.uint32).view(np.float32)[0] == limit
         # exact normal-equation partials as 32-bit limbs
         hi, lo, used = orc.normal_equations(step, refc, normals, idx, d2, limit)
         limbs = np.zeros(27 * 4 + 1, dtype=np.int64)

@@ -45,7 +45,7 @@ def test_ctypes_structs_match_the_compiled_header(tmp_path):
         pytest.skip("no C compiler")
     structs = {"aicp_b200_icp_config": capi.IcpConfig, "aicp_b200_iter_trace": capi.IterTrace, "aicp_b200_stats": capi.Stats,
                "aicp_b200_prefilter_config": capi.PrefilterConfig, "aicp_b200_prefilter_info": capi.PrefilterInfo,
-               "aicp_b200_svm_summary": capi.SvmSummary}
+               "aicp_b200_svm_summary": capi.SvmSummary, "aicp_b200_append_info": capi.AppendInfo}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "aicp_b200.h"', "int main(void) {"]
     for cname, ct in structs.items():
         lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
