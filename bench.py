@@ -78,7 +78,7 @@ def load_pairs(n_distinct, n_points=N_POINTS, generate=True):
         if len(missing) == 1:
             _make_scene(missing[0])
         else:
-            with mp.get_context("fork").Pool(min(len(missing), os.cpu_count() or 1)) as pool:
+            with mp.get_context("fork").Pool(min(len(missing), host_cores())) as pool:
                 pool.map(_make_scene, missing)
     t0 = time.time()
     while any(not os.path.exists(_scene_path(sc, n_points)) for sc in range(n_scenes)):
@@ -97,6 +97,14 @@ def load_pairs(n_distinct, n_points=N_POINTS, generate=True):
 def load_pair(trial, n_points=N_POINTS):
     """Pair `trial` of the distinct set (tools/)."""
     return load_pairs(trial + 1, n_points)[trial]
+
+
+def host_cores():
+    """Host threads this process may use (the affinity mask, not the machine's core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def profiled_traffic():
@@ -206,7 +214,7 @@ def run_reference(args, rank, world):
     D = min(args.pairs, D_MAX)
     pairs = load_pairs(D)
     ratios = oracle_ratios(pairs)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     R = REF_REGS_PER_STEP
     k = 0
     for _ in range(args.warmup):
@@ -419,7 +427,7 @@ def run_b200(args, rank, world, local_rank):
                         "d2h_bytes_per_step": int(P * 64)},
                 "gpu_launches": int(agg["launches"]), "clocks": clocks, "wall_s": wall_s, "ratios": ratios}
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
+            cores = host_cores()
             sec_all, it_all = 0.0, 0
             for k in range(D):                  # the step's D distinct pairs once each: ~5 s on 16 cores
                 s_, i_ = oracle_register(pairs[k], ratios[k], cores, 0)
