@@ -221,6 +221,12 @@ __device__ __forceinline__ void hist_flush(const unsigned int* sh, unsigned int*
     if (sh[b]) atomicAdd(&hist[b], sh[b]);
 }
 
+#ifdef AICP_DEBUG_WARP_TIMES
+__device__ uint4 g_query_stats[131072];      // (climb levels | sibling descents << 16, nodes visited, points scanned, ns)
+extern "C" int aicp_b200_debug_query_stats(unsigned int* out, int n_words) {
+  return (int)cudaMemcpyFromSymbol(out, g_query_stats, sizeof(unsigned int) * (size_t)n_words);
+}
+#endif
 // One query per thread: T_iter * reading' (float, fixed order) -> exact 1-NN, cold (root descent) in the first iteration,
 // bottom-up from the previous match afterwards.  Writes (position, d2), the optional trace and the first radix-select
 // digit into the block's shared histogram.  match_pos / d2out are read back later by the same launch of the persistent
@@ -231,8 +237,18 @@ __device__ __forceinline__ void match_thread(const IndexView& ix, const float* s
   float4 r = __ldg(&read0[i]);
   float3 p = xform_f(sT, r.x, r.y, r.z);
   int pos; float d;
-  if (iter > 0) nn_search_up(ix, p.x, p.y, p.z, match_pos[i], &pos, &d);
-  else nn_search(ix, p.x, p.y, p.z, &pos, &d);
+#ifdef AICP_DEBUG_WARP_TIMES
+  DbgCnt cnt{0, 0, 0, 0};
+  DbgCnt* dbg = &cnt;
+  const unsigned long long q0 = global_ns();
+#endif
+  if (iter > 0) nn_search_up(ix, p.x, p.y, p.z, match_pos[i], &pos, &d AICP_DBG_ARG);
+  else nn_search(ix, p.x, p.y, p.z, &pos, &d AICP_DBG_ARG);
+#ifdef AICP_DEBUG_WARP_TIMES
+  if (iter == AICP_DEBUG_WARP_TIMES && i < 131072) {
+    g_query_stats[i] = make_uint4((unsigned)cnt.levels | ((unsigned)cnt.descents << 16), (unsigned)cnt.nodes, (unsigned)cnt.points, (unsigned)(global_ns() - q0));
+  }
+#endif
   match_pos[i] = pos;
   d2out[i] = d;
   if (trace_idx) trace_idx[(size_t)iter * n + __float_as_int(r.w)] = __float_as_int(__ldg(&ix.pts[pos]).w);
@@ -1084,6 +1100,15 @@ __device__ __forceinline__ void loop_accumulate(const LoopArgs& a, int Q, int n_
   if (held) flush();
 }
 
+#ifdef AICP_DEBUG_WARP_TIMES
+// experiment builds only (tools/warp_times_probe.py): per warp of the search phase of iteration AICP_DEBUG_WARP_TIMES, its duration
+// in ns, its start offset from the phase start, how many of its lanes were outliers of the previous iteration, and its SM
+__device__ unsigned int g_warp_times[4 * 8192];
+extern "C" int aicp_b200_debug_warp_times(unsigned int* out, int n_words) {
+  return (int)cudaMemcpyFromSymbol(out, g_warp_times, sizeof(unsigned int) * (size_t)n_words);
+}
+#endif
+
 template <bool TILE>
 __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ LoopArgs a) {
   __shared__ unsigned int sh[AICP_HIST_BINS];
@@ -1114,8 +1139,26 @@ __global__ void __launch_bounds__(256, 4) k_icp_loop(const __grid_constant__ Loo
     __syncthreads();
     if (!dead) {
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (TILE && it > 0) match_tile(a.ix, sT, a.read0, n, t * 256 + tid, it, a.match_pos, a.d2, a.trace_idx, sh, s_stage[TILE ? w : 0], s_stack[TILE ? w : 0]);
-        else if ((tid & (S - 1)) == 0) match_thread(a.ix, sT, a.read0, n, t * Q + tid / S, it, a.match_pos, a.d2, a.trace_idx, sh);
+        if (TILE && it > 0) {
+          match_tile(a.ix, sT, a.read0, n, t * 256 + tid, it, a.match_pos, a.d2, a.trace_idx, sh, s_stage[TILE ? w : 0], s_stack[TILE ? w : 0]);
+        } else {
+#ifdef AICP_DEBUG_WARP_TIMES
+          const unsigned long long w0 = global_ns();
+          bool hard = false;
+          if (it > 0 && t * Q + tid / S < n) hard = a.d2[t * Q + tid / S] > __ldcg(&st->limit);
+          const unsigned int n_hard = __popc(__ballot_sync(0xFFFFFFFFu, hard));
+#endif
+          if ((tid & (S - 1)) == 0) match_thread(a.ix, sT, a.read0, n, t * Q + tid / S, it, a.match_pos, a.d2, a.trace_idx, sh);
+#ifdef AICP_DEBUG_WARP_TIMES
+          __syncwarp();
+          if (it == AICP_DEBUG_WARP_TIMES && lane == 0 && t * 8 + w < 8192) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned int* o = g_warp_times + 4 * (t * 8 + w);
+            o[0] = (unsigned int)(global_ns() - w0); o[1] = (unsigned int)(w0 - st->t_mark); o[2] = n_hard; o[3] = smid;
+          }
+#endif
+        }
       }
     }
     __syncthreads();
@@ -1283,7 +1326,10 @@ __global__ void __launch_bounds__(256) k_match_plain(IndexView ix, const float4*
   if (i >= n) return;
   float4 q = __ldg(&qry[i]);
   int pos; float d;
-  nn_search(ix, q.x, q.y, q.z, &pos, &d);
+#ifdef AICP_DEBUG_WARP_TIMES
+  DbgCnt* dbg = nullptr;
+#endif
+  nn_search(ix, q.x, q.y, q.z, &pos, &d AICP_DBG_ARG);
   out_idx[i] = __float_as_int(__ldg(&ix.pts[pos]).w);
   out_d2[i] = d;
 }

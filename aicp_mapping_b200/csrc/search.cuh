@@ -86,6 +86,18 @@ __device__ __forceinline__ bool ball_inside_node(const IndexView& ix, int node, 
 
 #define AICP_STACK 64
 
+// experiment builds (-DAICP_DEBUG_WARP_TIMES=<iteration>): per-query work counters threaded through the 1-NN search
+#ifdef AICP_DEBUG_WARP_TIMES
+struct DbgCnt { int levels, nodes, points, descents; };
+#define AICP_DBG_PARAM , DbgCnt* dbg
+#define AICP_DBG_ARG , dbg
+#define AICP_DBG(x) do { if (dbg) { x; } } while (0)
+#else
+#define AICP_DBG_PARAM
+#define AICP_DBG_ARG
+#define AICP_DBG(x) do { } while (0)
+#endif
+
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) {
   return d2a < d2b || (d2a == d2b && ia < ib);
 }
@@ -103,8 +115,9 @@ struct NnBest {
 #ifndef AICP_SCAN_BATCH
 #define AICP_SCAN_BATCH 4
 #endif
-__device__ __forceinline__ void nn_scan(const IndexView& ix, float qx, float qy, float qz, int first, int cnt, NnBest& b) {
+__device__ __forceinline__ void nn_scan(const IndexView& ix, float qx, float qy, float qz, int first, int cnt, NnBest& b AICP_DBG_PARAM) {
   const int last = first + cnt - 1;
+  AICP_DBG(dbg->points += cnt);
   for (int j = first; j <= last; j += AICP_SCAN_BATCH) {
     float4 p[AICP_SCAN_BATCH];
 #pragma unroll
@@ -119,15 +132,16 @@ __device__ __forceinline__ void nn_scan(const IndexView& ix, float qx, float qy,
 }
 
 // top-down walk of one subtree (code >= 0: internal node, code < 0: scan range [~code, ~code + cnt))
-__device__ inline void nn_descend(const IndexView& ix, float qx, float qy, float qz, int code, int cnt, NnBest& b) {
+__device__ inline void nn_descend(const IndexView& ix, float qx, float qy, float qz, int code, int cnt, NnBest& b AICP_DBG_PARAM) {
   int st_a[AICP_STACK];      // internal node index, or ~first for a scan range
   int st_b[AICP_STACK];      // point count of a scan range
   float st_d[AICP_STACK];
   int sp = 0;
   while (true) {
     if (code < 0) {
-      nn_scan(ix, qx, qy, qz, ~code, cnt, b);
+      nn_scan(ix, qx, qy, qz, ~code, cnt, b AICP_DBG_ARG);
     } else {
+      AICP_DBG(dbg->nodes += 1);
       const float4* r = ix.rec + 4 * (size_t)code;
       float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
       int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w);
@@ -155,10 +169,10 @@ __device__ inline void nn_descend(const IndexView& ix, float qx, float qy, float
 }
 
 // 1-NN from the root: returns position in the Morton-ordered array (so the caller can gather normals) and d2.
-__device__ inline void nn_search(const IndexView& ix, float qx, float qy, float qz, int* out_pos, float* out_d2) {
+__device__ inline void nn_search(const IndexView& ix, float qx, float qy, float qz, int* out_pos, float* out_d2 AICP_DBG_PARAM) {
   NnBest b{INFINITY, 0x7FFFFFFF, -1};
-  if (ix.n <= AICP_LEAF) nn_scan(ix, qx, qy, qz, 0, ix.n, b);
-  else nn_descend(ix, qx, qy, qz, 0, ix.n, b);
+  if (ix.n <= AICP_LEAF) nn_scan(ix, qx, qy, qz, 0, ix.n, b AICP_DBG_ARG);
+  else nn_descend(ix, qx, qy, qz, 0, ix.n, b AICP_DBG_ARG);
   *out_pos = b.pos;
   *out_d2 = b.d;
 }
@@ -169,21 +183,22 @@ __device__ inline void nn_search(const IndexView& ix, float qx, float qy, float 
 // ancestor has a key outside the cell, hence (monotone quantisation) lies outside the ball.  Once ICP has pulled the
 // clouds together the ball is a few centimetres wide and the climb ends 3-5 levels above the leaf instead of walking a
 // root-to-leaf path; the result is identical to nn_search (the same candidates can win).
-__device__ inline void nn_search_up(const IndexView& ix, float qx, float qy, float qz, int seed_pos, int* out_pos, float* out_d2) {
+__device__ inline void nn_search_up(const IndexView& ix, float qx, float qy, float qz, int seed_pos, int* out_pos, float* out_d2 AICP_DBG_PARAM) {
   NnBest b{INFINITY, 0x7FFFFFFF, -1};
   if (ix.n <= AICP_LEAF) {
-    nn_scan(ix, qx, qy, qz, 0, ix.n, b);
+    nn_scan(ix, qx, qy, qz, 0, ix.n, b AICP_DBG_ARG);
   } else {
     int own = __ldg(&ix.owner8[seed_pos]);
     int node = own >> 1, side = own & 1;
     bool first_level = true;
     while (true) {
+      AICP_DBG(dbg->levels += 1);
       const float4* r = ix.rec + 4 * (size_t)node;
       float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3);
       int first = __float_as_int(r0.w), split = __float_as_int(r1.w), end = __float_as_int(r2.w), up = __float_as_int(r3.w);
       if (first_level) {
         // the seed's own small range first: it holds the seed, so the bound is at most the seed's distance afterwards
-        if (side == 0) nn_scan(ix, qx, qy, qz, first, split - first, b); else nn_scan(ix, qx, qy, qz, split, end - split, b);
+        if (side == 0) nn_scan(ix, qx, qy, qz, first, split - first, b AICP_DBG_ARG); else nn_scan(ix, qx, qy, qz, split, end - split, b AICP_DBG_ARG);
         first_level = false;
       }
       // sibling subtree of the side we came from
@@ -192,7 +207,8 @@ __device__ inline void nn_search_up(const IndexView& ix, float qx, float qy, flo
       if (ds <= b.d) {
         int sf = side == 0 ? split : first, sc = side == 0 ? end - split : split - first;
         int scode = sc <= AICP_LEAF ? ~sf : (side == 0 ? split : split - 1);
-        nn_descend(ix, qx, qy, qz, scode, sc, b);
+        AICP_DBG(dbg->descents += 1);
+        nn_descend(ix, qx, qy, qz, scode, sc, b AICP_DBG_ARG);
       }
       if (up < 0) break;                                   // root done
       // stop once the ball (q, best) cannot reach outside this node (see ball_inside_node)
