@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) k_vg_centroids(const unsigned int* __rest
 // look-back over the tiles (the protocol of k_crop_box: tiles take their number from an atomic ticket, so a tile only waits
 // for tiles that are already running); the thread of a head sums its run (which may continue into the next tiles).
 #define VG_ROWS 8
+#define VG_SERIAL_RUN 48     // points of a voxel summed by its head thread before the warp takes over the rest of the run
 #define VG_TILE (256 * VG_ROWS)
 #define VG_AGG (1ull << 62)
 #define VG_PREFIX (2ull << 62)
@@ -337,21 +338,58 @@ __global__ void __launch_bounds__(256) k_vg_fused(const unsigned int* __restrict
   const double sc = 1.0 / PF_FIXED;
 #pragma unroll
   for (int r = 0; r < VG_ROWS; ++r) {
-    if (!(head & (1u << r))) continue;
+    const bool is_head = (head & (1u << r)) != 0;
     const int i = (int)(base + r * 256 + threadIdx.x);
-    const unsigned int k = __ldg(&keys[i]);
+    unsigned int k = 0;
     long long sx = 0, sy = 0, sz = 0;
     int j = i;
-    do {
-      const float4 p = __ldg(&pts[__ldg(&vals[j])]);
-      sx += __double2ll_rn((double)p.x * PF_FIXED);
-      sy += __double2ll_rn((double)p.y * PF_FIXED);
-      sz += __double2ll_rn((double)p.z * PF_FIXED);
-      ++j;
-    } while (j < n && __ldg(&keys[j]) == k);
-    const double cnt = (double)(j - i);
-    out[obase + (unsigned long long)(s_cnt[r * 8 + w] + rank[r])] =
-        make_float4((float)(((double)sx / cnt) * sc), (float)(((double)sy / cnt) * sc), (float)(((double)sz / cnt) * sc), 1.0f);
+    bool more = false;
+    if (is_head) {
+      k = __ldg(&keys[i]);
+      do {
+        const float4 p = __ldg(&pts[__ldg(&vals[j])]);
+        sx += __double2ll_rn((double)p.x * PF_FIXED);
+        sy += __double2ll_rn((double)p.y * PF_FIXED);
+        sz += __double2ll_rn((double)p.z * PF_FIXED);
+        ++j;
+      } while (j < n && __ldg(&keys[j]) == k && j - i < VG_SERIAL_RUN);
+      more = j < n && __ldg(&keys[j]) == k;
+    }
+    // A voxel with more than VG_SERIAL_RUN points (a leaf size far above the point spacing, or a dense blob): the rest of its
+    // run is summed by the whole warp, 32 points per step, instead of one thread walking it alone -- the sums are exact
+    // integers, so the order of the additions does not matter
+    unsigned int mm = __ballot_sync(0xFFFFFFFFu, more);
+    while (mm) {
+      const int src = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const unsigned int kk = __shfl_sync(0xFFFFFFFFu, k, src);
+      int jj = __shfl_sync(0xFFFFFFFFu, j, src) + lane;
+      long long ax = 0, ay = 0, az = 0;
+      int seen = 0;
+      while (true) {
+        const bool ok = jj < n && __ldg(&keys[jj]) == kk;
+        if (!__any_sync(0xFFFFFFFFu, ok)) break;
+        if (ok) {
+          const float4 p = __ldg(&pts[__ldg(&vals[jj])]);
+          ax += __double2ll_rn((double)p.x * PF_FIXED);
+          ay += __double2ll_rn((double)p.y * PF_FIXED);
+          az += __double2ll_rn((double)p.z * PF_FIXED);
+          ++seen;
+        }
+        jj += 32;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        ax += __shfl_xor_sync(0xFFFFFFFFu, ax, off); ay += __shfl_xor_sync(0xFFFFFFFFu, ay, off);
+        az += __shfl_xor_sync(0xFFFFFFFFu, az, off); seen += __shfl_xor_sync(0xFFFFFFFFu, seen, off);
+      }
+      if (lane == src) { sx += ax; sy += ay; sz += az; j += seen; }
+    }
+    if (is_head) {
+      const double cnt = (double)(j - i);
+      out[obase + (unsigned long long)(s_cnt[r * 8 + w] + rank[r])] =
+          make_float4((float)(((double)sx / cnt) * sc), (float)(((double)sy / cnt) * sc), (float)(((double)sz / cnt) * sc), 1.0f);
+    }
   }
 }
 

@@ -358,6 +358,16 @@ def test_voxel_grid_parity_lidar_and_edge_cases(orc, pf):
     # duplicates: many points in one voxel, sums exact in any order
     dup = np.repeat(np.float32([[1.01, 2.02, 3.03], [1.02, 2.03, 3.01]]), 5000, axis=0)
     assert np.array_equal(pf.voxelGrid(dup).view(np.uint32), orc.voxel_grid(dup).view(np.uint32))
+    # voxels holding 1 .. 5000 distinct points, around the length where the warp takes over a voxel's run from its head thread
+    # (48) and across tile boundaries (2048): the whole run is still summed exactly
+    rng = np.random.default_rng(77)
+    parts = []
+    for v, cnt in enumerate([1, 47, 48, 49, 50, 79, 80, 81, 96, 97, 2047, 2048, 2049, 5000, 3, 640]):
+        corner = np.float32([0.08 * (3 * v + 1), 0.08 * (2 * v + 1), 0.08 * (v % 5)])
+        parts.append((corner + rng.uniform(0.005, 0.075, (cnt, 3))).astype(np.float32))
+    blob = rng.permutation(np.concatenate(parts, 0))
+    got, want = pf.voxelGrid(blob), orc.voxel_grid(blob)
+    assert got.shape[0] == 16 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
 @pytest.mark.gpu
