@@ -214,6 +214,29 @@ def test_loop_schedules_agree_and_persistent_is_one_launch(reg, pair_cache):
     assert out[2][3] > 0.0
 
 
+def test_wait_stream_orders_device_inputs_produced_on_another_stream(reg, pair_cache):
+    """aicp_b200_wait_stream: a device cloud produced on a side stream (behind a long-running kernel) and handed over without
+    synchronising that stream gives the same transform as the host arrays."""
+    import torch
+    pair = pair_cache(2, 0)
+    reg.setConfig(ratio=0.7)
+    T_host = reg.registerClouds(pair["ref"], pair["read"])
+    side = torch.cuda.Stream()
+    src_ref = torch.from_numpy(capi.to_xyzw(pair["ref"])).cuda()
+    src_read = torch.from_numpy(capi.to_xyzw(pair["read"])).cuda()
+    big = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for _ in range(20):
+            big.mul_(1.0001)                       # ~ms of queued work in front of the copies
+        ref_dev = torch.zeros_like(src_ref); ref_dev.copy_(src_ref)
+        read_dev = torch.zeros_like(src_read); read_dev.copy_(src_read)
+    reg.waitStream(side)                           # the wrapper itself only synchronises the CURRENT (default) stream
+    T_dev = reg.registerClouds(ref_dev, read_dev)
+    assert np.array_equal(u32(T_dev), u32(T_host))
+    side.synchronize()
+
+
 @pytest.mark.parametrize("n_ref,n_qry", [(20, 7), (33, 40), (100, 31), (5000, 1000)])
 def test_icp_tile_kernels_ragged_sizes(reg, orc, n_ref, n_qry):
     """Tile kernels on cloud sizes around the 32-point tile boundary (partial warps, single-chunk references)."""
