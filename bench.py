@@ -117,12 +117,36 @@ def profiled_traffic():
         return None, None
 
 
+def profiled_instructions(iterations_mean):
+    """Warp instructions of one registration with `iterations_mean` iterations, from the committed ncu launch list of the batch
+    schedule (profiles/roofline_traffic.json), or (None, None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            d = json.load(f)["warp_instructions"]
+        return d["setup"] + d["cold_iteration"] + max(0.0, iterations_mean - 1.0) * d["warm_iteration"], d["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def issue_slots(iterations_mean, regs_per_s_per_gpu, clocks):
+    """The path is bound by instruction issue and latency, not by HBM: warp instructions per second of the batched leg against
+    the GPU's issue peak (148 SMs x 4 schedulers x SM clock).  Instruction counts are the profiled ones (ncu), not live."""
+    inst, src = profiled_instructions(iterations_mean)
+    mhz = (clocks or {}).get("sm_mhz") or 0.0
+    if inst is None or mhz <= 0:
+        return None
+    peak = 148 * 4 * mhz * 1e6
+    achieved = inst * regs_per_s_per_gpu
+    return {"warp_instructions_per_registration": inst, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s",
+            "frac": achieved / peak, "source": src}
 
 
 class ClockSampler:
@@ -418,6 +442,7 @@ def run_b200(args, rank, world, local_rank):
                 "roofline_registration": {"algorithmic_bytes": b_reg, "iterations_mean": I, "ms": reg_ms,
                                           "achieved": b_reg / (reg_ms * 1e-3) / 1e9, "frac": b_reg / (reg_ms * 1e-3) / 1e9 / peak,
                                           "unit": "GB/s"},
+                "issue_slots": issue_slots(I, value / world, clocks),
                 "aicp_step": aicp_step,
                 "stage_ms_per_registration": None if stage is None else dict(
                     {k: stage[k] / (P * 2) for k in ("index", "normals", "match", "select", "accumulate", "tail_pick", "tail_select",
