@@ -360,6 +360,29 @@ def test_register_batch_concurrent_streams_equals_sequential(reg, orc):
         reg.registerBatch(bad, ratios=ratios[:3], streams=2)
 
 
+def test_register_batch_reuses_worker_buffers_across_sizes(reg):
+    """Many small pairs of different sizes on 2 streams (every worker's staging and index buffers are reused by clouds of other
+    sizes) give the transforms of one-by-one calls, twice in a row and again after a batch in which a pair in the middle failed."""
+    pairs = [synth.make_pair(5, t, 3000 + 371 * (t % 5)) for t in range(11)]
+    ratios = [0.7, 0.6, 0.5, 0.65, 0.7, 0.55, 0.7, 0.6, 0.5, 0.65, 0.7]
+    reg.setConfig(max_iterations=20)
+    seq = []
+    for p, r in zip(pairs, ratios):
+        reg.setConfig(ratio=r)
+        seq.append(reg.registerClouds(p["ref"], p["read"]))
+    for _ in range(2):
+        T, stats, status, ms = reg.registerBatch([(p["ref"], p["read"]) for p in pairs], ratios=ratios, streams=2)
+        assert not status.any()
+        for a, b in zip(seq, T):
+            assert np.array_equal(u32(a), u32(b))
+    bad = [(p["ref"], p["read"]) for p in pairs]
+    bad[3] = (pairs[3]["ref"], pairs[3]["ref"])
+    with pytest.raises(capi.AicpError, match="NO_VALID_MATCH"):
+        reg.registerBatch(bad, ratios=ratios, streams=2)
+    T, stats, status, ms = reg.registerBatch([(p["ref"], p["read"]) for p in pairs], ratios=ratios, streams=2)
+    assert not status.any() and all(np.array_equal(u32(a), u32(b)) for a, b in zip(seq, T))
+
+
 def test_cpp_adapter_demo():
     """The C++ adapters (include/aicp_b200_adapter.hpp) compiled against the reference's own abstract plug-in headers:
     overlap -> updateConfigParams -> registerClouds -> getOutputReading through the factories, as App::runAicpPipeline does.
