@@ -44,11 +44,25 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Host-to-device copy of a cloud in pieces of 512 KB (AICP_B200_H2D_CHUNK_KB, 0 = one copy).  While a copy engine has a
+// long read of host memory in flight, the GPU's own fetches of launch commands wait behind it on the same PCIe link; with
+// eight registrations launching kernels beside the uploads of the next pairs that costs throughput (measured: a saturating
+// background upload halves the batched rate; tools/e2e_probe.py).  Pieces leave gaps for the command fetches: +1.4 % on the
+// end-to-end rate of a 64-pair batch; 64 KB pieces cost more in commands than they give (profiles/round2_k_e2e_probe.txt).
+static int h2d_copy(Handle* h, void* dst, const void* src, size_t bytes) {
+  static const size_t chunk = [] { const char* e = getenv("AICP_B200_H2D_CHUNK_KB"); return (size_t)(e ? atoi(e) : 512) * 1024; }();
+  if (!chunk || bytes <= chunk) { CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream)); return AICP_B200_OK; }
+  for (size_t off = 0; off < bytes; off += chunk)
+    CUDA_TRY(cudaMemcpyAsync((char*)dst + off, (const char*)src + off, bytes - off < chunk ? bytes - off : chunk, cudaMemcpyHostToDevice, h->stream));
+  return AICP_B200_OK;
+}
+
 // make `n` points available on the device: device pointers are used in place, host pointers are staged into `buf`
 int upload_points(Handle* h, DevBuf<float4>& buf, const float* xyzw, int64_t n, const float4** out_dev) {
   if (is_device_ptr(xyzw)) { *out_dev = reinterpret_cast<const float4*>(xyzw); return AICP_B200_OK; }
   CUDA_TRY(buf.reserve((size_t)n));
-  CUDA_TRY(cudaMemcpyAsync(buf.p, xyzw, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  int rc = h2d_copy(h, buf.p, xyzw, sizeof(float4) * (size_t)n);
+  if (rc) return rc;
   *out_dev = buf.p;
   return AICP_B200_OK;
 }
@@ -64,8 +78,8 @@ static int stage_owned(Handle* h, DevBuf<float4>& buf, const float* xyzw, int64_
   // registration keeps its own copy of both clouds (the reference copies into its DP members too,
   // pointmatcher_registration.cpp:16-20), so device inputs are copied device-to-device
   CUDA_TRY(buf.reserve((size_t)n));
-  CUDA_TRY(cudaMemcpyAsync(buf.p, xyzw, sizeof(float4) * (size_t)n,
-                           is_device_ptr(xyzw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  if (!is_device_ptr(xyzw)) return h2d_copy(h, buf.p, xyzw, sizeof(float4) * (size_t)n);
+  CUDA_TRY(cudaMemcpyAsync(buf.p, xyzw, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
   return AICP_B200_OK;
 }
 
