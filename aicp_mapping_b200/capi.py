@@ -192,8 +192,9 @@ def to_xyzw(xyz):
     return out
 
 
-def ptr_and_count(cloud):
-    """Accepts numpy arrays (host) or torch CUDA tensors of shape n x 4 float32 (device, used in place)."""
+def ptr_and_count(cloud, synced=None):
+    """Accepts numpy arrays (host) or torch CUDA tensors of shape n x 4 float32 (device, used in place).  `synced`: a set shared
+    by the clouds of ONE call (a batch); torch's stream of a device is synchronised once per call, not once per cloud."""
     if hasattr(cloud, "data_ptr"):      # torch tensor
         if cloud.dim() != 2 or cloud.shape[1] != 4 or str(cloud.dtype) != "torch.float32" or not cloud.is_contiguous():
             raise ValueError("device clouds must be contiguous n x 4 float32 tensors")
@@ -201,7 +202,11 @@ def ptr_and_count(cloud):
             # the library reads device inputs on its own streams (aicp_b200.h, "STREAM ORDER"): whatever torch still has in
             # flight on the current stream of the tensor's device -- the op or copy that produces it -- must finish first
             import torch
-            torch.cuda.current_stream(cloud.device).synchronize()
+            key = (cloud.device.index, torch.cuda.current_stream(cloud.device).cuda_stream)
+            if synced is None or key not in synced:
+                torch.cuda.current_stream(cloud.device).synchronize()
+                if synced is not None:
+                    synced.add(key)
         return C.c_void_p(cloud.data_ptr()), int(cloud.shape[0]), cloud
     a = to_xyzw(cloud)
     return C.c_void_p(a.ctypes.data), int(a.shape[0]), a

@@ -214,9 +214,10 @@ class B200Registration:
         n = len(pairs)
         keep, refs, reads = [], (C.c_void_p * n)(), (C.c_void_p * n)()
         n_ref, n_read = (C.c_int64 * n)(), (C.c_int64 * n)()
+        synced = set()
         for i, (r, q) in enumerate(pairs):
-            pr, nr, kr = capi.ptr_and_count(r)
-            pq, nq, kq = capi.ptr_and_count(q)
+            pr, nr, kr = capi.ptr_and_count(r, synced)
+            pq, nq, kq = capi.ptr_and_count(q, synced)
             refs[i], reads[i], n_ref[i], n_read[i] = pr, pq, nr, nq
             keep.append((kr, kq))
         T = np.zeros((n, 16), dtype=np.float32)
@@ -245,9 +246,10 @@ class B200Registration:
         n = len(pairs)
         keep, refs, reads = [], (C.c_void_p * n)(), (C.c_void_p * n)()
         n_ref, n_read = (C.c_int64 * n)(), (C.c_int64 * n)()
+        synced = set()
         for i, (r, q) in enumerate(pairs):
-            pr, nr, kr = capi.ptr_and_count(r)
-            pq, nq, kq = capi.ptr_and_count(q)
+            pr, nr, kr = capi.ptr_and_count(r, synced)
+            pq, nq, kq = capi.ptr_and_count(q, synced)
             refs[i], reads[i], n_ref[i], n_read[i] = pr, pq, nr, nq
             keep.append((kr, kq))
         ro = np.ascontiguousarray([o[0] for o in origins], dtype=np.float64).reshape(n, 3)
@@ -275,9 +277,10 @@ class B200Registration:
         n = len(pairs)
         keep, refs, reads = [], (C.c_void_p * n)(), (C.c_void_p * n)()
         n_ref, n_read = (C.c_int64 * n)(), (C.c_int64 * n)()
+        synced = set()
         for i, (r, q) in enumerate(pairs):
-            pr, nr, kr = capi.ptr_and_count(r)
-            pq, nq, kq = capi.ptr_and_count(q)
+            pr, nr, kr = capi.ptr_and_count(r, synced)
+            pq, nq, kq = capi.ptr_and_count(q, synced)
             refs[i], reads[i], n_ref[i], n_read[i] = pr, pq, nr, nq
             keep.append((kr, kq))
         pa = np.ascontiguousarray([np.asarray(p[0], dtype=np.float64).T.ravel() for p in poses], dtype=np.float64).reshape(n, 16)
