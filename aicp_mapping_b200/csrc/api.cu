@@ -153,6 +153,7 @@ int aicp_b200_destroy(aicp_b200_handle* hh) {
   h->device_children.clear();
   cudaSetDevice(h->device);
   if (h->done_ev) cudaEventDestroy(h->done_ev);
+  if (h->setup_exec) cudaGraphExecDestroy(h->setup_exec);
   for (int i = 0; i < 2; ++i) if (h->batch_ev[i]) cudaEventDestroy(h->batch_ev[i]);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->ref_in.release(); h->ref_ix.release(); h->refc_pts.release(); h->refc_rec.release(); h->refc_cell.release(); h->normals.release(); h->knn_pos.release();

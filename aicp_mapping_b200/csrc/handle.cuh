@@ -2,6 +2,7 @@
 // cudaMalloc on the steady-state path), the stream, the parsed libpointmatcher chain and the last error text.
 #pragma once
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -10,6 +11,10 @@
 
 namespace aicp {
 
+// bumped by every (re)allocation of a device buffer: a captured CUDA graph holds raw pointers, so a graph is only replayed
+// while this number is what it was when the graph was captured (icp.cu, setup graph of the batch workers)
+inline std::atomic<unsigned long long> g_alloc_generation{0};
+
 // grow-only device buffer
 template <typename T>
 struct DevBuf {
@@ -17,6 +22,7 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    g_alloc_generation.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     size_t want = n + n / 8 + 64;
@@ -24,7 +30,17 @@ struct DevBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) { cudaFree(p); g_alloc_generation.fetch_add(1, std::memory_order_relaxed); } p = nullptr; cap = 0; }
+};
+
+// what the captured setup of a registration depends on besides the data (icp.cu)
+struct SetupKey {
+  int n_ref = -1, n_read = -1, knn = 0, has_init = 0, knn_schedule = 0;
+  unsigned long long generation = 0;
+  bool operator==(const SetupKey& o) const {
+    return n_ref == o.n_ref && n_read == o.n_read && knn == o.knn && has_init == o.has_init && knn_schedule == o.knn_schedule &&
+           generation == o.generation;
+  }
 };
 
 // Morton-ordered spatial index over one cloud
@@ -168,6 +184,11 @@ struct Handle {
   cudaEvent_t batch_ev[2] = {nullptr, nullptr};
   cudaEvent_t wait_ev = nullptr;     // aicp_b200_wait_stream: recorded on the caller's producer stream, waited on by h->stream
   cudaEvent_t done_ev = nullptr;
+  // batch workers: the ~30 launches of a registration's setup as one CUDA graph, replayed while sizes and buffers stay put
+  cudaGraphExec_t setup_exec = nullptr;
+  SetupKey setup_key, setup_seen;
+  int setup_launches = 0;
+  bool setup_graph_off = false;      // a capture failed on this handle: stay with plain launches
 };
 
 // ---- index.cu

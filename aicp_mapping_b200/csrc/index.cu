@@ -311,7 +311,7 @@ int build_index(Handle* h, SpatialIndex& ix, const float4* pts_dev, int64_t n64,
   if (n64 < 1 || n64 > (1ll << 28)) return fail(h, AICP_B200_ERR_BAD_ARG, "cloud size %lld out of range [1, 2^28]", (long long)n64);
   int n = (int)n64;
   cudaStream_t s = h->stream;
-  if (!ix.meta) CUDA_TRY(cudaMalloc((void**)&ix.meta, sizeof(IndexMeta)));
+  if (!ix.meta) { CUDA_TRY(cudaMalloc((void**)&ix.meta, sizeof(IndexMeta))); g_alloc_generation.fetch_add(1, std::memory_order_relaxed); }
   CUDA_TRY(ix.pts.reserve((size_t)n));
   if (with_tree) {
     CUDA_TRY(ix.rec.reserve((size_t)4 * n));
