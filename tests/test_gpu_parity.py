@@ -282,6 +282,48 @@ def test_icp_counter_stop_and_init_transform(reg, orc):
     assert np.array_equal(u32(reg.getInitializedReading()), u32(orc.transform_points(init, pair["read"])))
 
 
+def test_setup_graph_replay_and_invalidation(orc):
+    """The setup of a registration (index, normals, loop state, reading) is replayed as a CUDA graph from the third meeting
+    of the same cloud sizes on (icp.cu, run_registration).  Same sizes with other DATA, other sizes in between (buffers grow,
+    the graph must be dropped), an initial transform (another graph key), another knn, and profiling level 2 (plain
+    launches): every result equals the oracle's, whichever way the setup ran."""
+    reg = ab.B200Registration()
+    try:
+        a = [synth.make_pair(5, t, 5000) for t in range(3)]            # three different pairs of one size
+        b = synth.make_pair(5, 7, 9000)                                # a larger pair: every buffer is reallocated
+        want = {}
+
+        def check(pair, tag, ratio=0.6, init=None, knn=20):
+            reg.setConfig(ratio=ratio, max_iterations=20, knn_normals=knn)
+            T = reg.registerClouds(pair["ref"], pair["read"]) if init is None else reg.registerCloudsInit(pair["ref"], pair["read"], init)
+            if tag not in want:
+                o = orc.icp(pair["ref"], pair["read"], orc.default_config(ratio=ratio, threads=NCPU, max_iterations=20, knn_normals=knn), init_T=init)
+                assert o.rc == 0
+                want[tag] = (o.T, o.iterations)
+            assert np.array_equal(u32(T), u32(want[tag][0])) and reg.stats.iterations == want[tag][1], tag
+
+        for rep in range(2):
+            for t in range(3):
+                check(a[t], "a%d" % t)                                 # rep 0: plain, plain (seen), captured; rep 1: replayed
+        check(b, "b")                                                  # other sizes: reallocation, graph dropped
+        for t in range(3):
+            check(a[t], "a%d" % t)
+        check(b, "b"); check(b, "b"); check(b, "b")
+        init = synth.rigid(0.02, -0.01, 0.0, 0, 0, 0.01).astype(np.float32)
+        for _ in range(3):
+            check(a[1], "a1_init", init=init)
+            assert np.array_equal(u32(reg.getInitializedReading()), u32(orc.transform_points(init, a[1]["read"])))
+        for _ in range(3):
+            check(a[2], "a2_knn10", knn=10)
+        check(a[0], "a0")
+        reg.setProfiling(2)
+        check(a[0], "a0"); check(a[0], "a0")
+        reg.setProfiling(0)
+        check(a[0], "a0"); check(a[0], "a0"); check(a[0], "a0")
+    finally:
+        reg.close()
+
+
 def test_icp_through_yaml_file_like_app(reg, orc, tmp_path):
     """App::computeRegistration path: clamp -> rewrite YAML -> updateConfigParams -> registerClouds (app.cpp:187-216)."""
     pair = synth.make_pair(5, 5, 8000)
