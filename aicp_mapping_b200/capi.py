@@ -218,3 +218,8 @@ def mat_to_colmajor(T):
 
 def colmajor_to_mat(t16):
     return np.asarray(t16, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+def colmajor_batch_to_mats(T):
+    """n x 16 column-major transforms -> n x 4 x 4 row-major matrices (one vectorised transpose, not n small ones)."""
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(-1, 4, 4).transpose(0, 2, 1))

@@ -237,7 +237,7 @@ class B200Registration:
                                                     int(streams), T.ctypes.data_as(C.POINTER(C.c_float)), stats,
                                                     status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
         self._check(rc)
-        return np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4), stats, status, float(ms.value)
+        return capi.colmajor_batch_to_mats(T), stats, status, float(ms.value)
 
     def aicpBatch(self, pairs, origins, resolution=float(np.float32(0.2)), streams=0):
         """aicp_b200_aicp_batch: one AICP step (overlap -> auto-tuned ratio -> registration, app.cpp:218-247) per pair.
@@ -265,7 +265,7 @@ class B200Registration:
                                             T.ctypes.data_as(fp), ov.ctypes.data_as(fp), stats,
                                             status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
         self._check(rc)
-        return (np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4)), ov, stats, status, float(ms.value)
+        return (capi.colmajor_batch_to_mats(T)), ov, stats, status, float(ms.value)
 
     def pipelineBatch(self, pairs, poses, svm_model, sensor_range, angular_view, risk_threshold=0.5,
                       resolution=float(np.float32(0.2)), streams=0, prefilter_first=False):
@@ -300,7 +300,7 @@ class B200Registration:
                                                 self.n_filtered.ctypes.data_as(C.POINTER(C.c_int64)), stats,
                                                 status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ms))
         self._check(rc)
-        return ((np.stack([capi.colmajor_to_mat(t) for t in T]) if n else T.reshape(0, 4, 4)), ov, al, risk, stats, status,
+        return ((capi.colmajor_batch_to_mats(T)), ov, al, risk, stats, status,
                 float(ms.value))
 
     # ---- multi-GPU single registration (reading sharded over ranks) --------------------------------------------------
