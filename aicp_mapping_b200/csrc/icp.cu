@@ -1535,7 +1535,8 @@ int run_registration(Handle* h, const float* init_T_host, bool rebuild_reference
   const bool graph_ok = (h->batch_worker ? setup_graphs >= 1 : setup_graphs >= 2) && !h->setup_graph_off && rebuild_reference && prof < 2 && !h->comm &&
                         !cfg.reading_normals && !h->trace_matches && !h->ref_recentre && cfg.knn_normals <= 24;
   SetupKey key;
-  key.n_ref = n_ref; key.n_read = n_read; key.knn = cfg.knn_normals; key.has_init = init_T_host ? 1 : 0; key.knn_schedule = h->knn_schedule;
+  key.n_ref = n_ref; key.n_read = n_read; key.knn = cfg.knn_normals; key.has_init = init_T_host ? 1 : 0;
+  key.knn_schedule = h->knn_schedule | (h->batch_worker ? 16 : 0);      // both decide which kernels the setup launches
   key.generation = g_alloc_generation.load(std::memory_order_relaxed);
   if (graph_ok && h->setup_exec && key == h->setup_key) {
     h->ref_ready = false;
